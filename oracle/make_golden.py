@@ -1,0 +1,82 @@
+"""Generate tests/golden/*.npz by running the imported, unmodified reference (build container only).
+
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden [--only cfg1|cfg2]
+The inputs are regenerated from ``sfm_b200.synth`` by seed; each file stores a SHA-256 of the input bytes so that a
+drift of the generator is detected instead of silently comparing against stale outputs.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'carla-social-force-model_b200')]
+
+from oracle import ref_loader          # noqa: E402
+from sfm_b200 import synth             # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def workload_digest(w):
+    h = hashlib.sha256()
+    for a in (w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode):
+        h.update(np.ascontiguousarray(a).tobytes())
+    for b in w.borders:
+        h.update(np.ascontiguousarray(b).tobytes())
+    if w.section_center is not None:
+        h.update(np.ascontiguousarray(w.section_center).tobytes())
+        h.update(np.ascontiguousarray(w.section_length).tobytes())
+    for c, r in w.static_obstacles:
+        h.update(np.ascontiguousarray(c).tobytes())
+        h.update(np.ascontiguousarray(r).tobytes())
+    veh = w.vehicles_at(3)
+    if veh is not None:
+        for ring in veh[5]:
+            h.update(np.ascontiguousarray(ring).tobytes())
+    return h.hexdigest()
+
+
+def golden_cfg1(ref, cfg):
+    w = synth.make_config(1)
+    out = ref_loader.run_ticks(ref, w, cfg, 100, record_forces=True)
+    keep = [0, 1, 10, 50, 99]
+    np.savez_compressed(os.path.join(GOLDEN, 'cfg1_trajectory.npz'), digest=workload_digest(w), loc=out['loc'],
+                        vel=out['vel'], force_steps=np.array(keep),
+                        **{f'F_{k}': v[keep] for k, v in out['forces'].items()})
+
+
+def golden_cfg2(ref, cfg):
+    for use_radius in (False, True):
+        for z_spread in (0.0, 0.2):
+            w = synth.make_config(2, z_spread=z_spread)
+            c = dict(cfg, use_ped_radius=use_radius)
+            sim = ref_loader.build_simulation(ref, w, c)
+            sim.update_dynamic_obstacles(w.vehicles_at(0))
+            t0 = time.time()
+            forces = {name: f.get_force(sim.peds) for name, f in sim.forces.items()}
+            print(f'cfg2 radius={use_radius} z={z_spread}: {time.time() - t0:.1f}s', flush=True)
+            tag = f"r{int(use_radius)}_z{int(z_spread > 0)}"
+            np.savez_compressed(os.path.join(GOLDEN, f'cfg2_forces_{tag}.npz'), digest=workload_digest(w),
+                                **{f'F_{k}': v for k, v in forces.items()})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--only', default=None)
+    args = ap.parse_args()
+    ref, cfg = ref_loader.load(), ref_loader.load_config()
+    os.makedirs(GOLDEN, exist_ok=True)
+    if args.only in (None, 'cfg1'):
+        golden_cfg1(ref, cfg)
+    if args.only in (None, 'cfg2'):
+        golden_cfg2(ref, cfg)
+
+
+if __name__ == '__main__':
+    main()

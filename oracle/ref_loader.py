@@ -1,0 +1,106 @@
+"""Import the *unmodified* reference (``/root/reference``) so the oracle can be pinned against it.
+
+TEST INFRASTRUCTURE.  Works only in the build container: the GPU box has no ``/root/reference``, so nothing that runs
+there imports this module (``available()`` is the guard).  Two shims, both documented in SURVEY.md section 8c:
+
+* ``shapely`` (check_traffic.py:2) is not installed -> a stub module is registered before the import.  ``check_traffic``
+  is only *called* for pedestrians in CHECKING_TRAFFIC (pedestrian_simulation.py:67-70), which the synthetic crowds avoid.
+* ``BorderForce.__init__`` does ``np.array(section_info)`` on a ragged list (forces.py:130), which numpy >= 1.24
+  rejects -> ``section_info`` is passed as a pre-built ``dtype=object`` array, the form the reference's own ``.npz`` cache
+  yields (obstacles.py:43-45).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_DIR = os.environ.get('SFM_REFERENCE_DIR', '/root/reference')
+_OWN_MODULES = ('forces', 'stateutils', 'pedestrian_state', 'pedestrian_simulation', 'ped_mode_manager', 'check_traffic')
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_DIR, 'forces.py'))
+
+
+def load():
+    """Return a namespace with the reference's modules, imported under private names.
+
+    The reference's modules import each other by bare top-level name (forces.py:7-8), and the drop-in package uses the
+    same names, so the import happens with ``REFERENCE_DIR`` first on ``sys.path`` and the resulting modules are then
+    *removed* from ``sys.modules`` again -- both implementations can live in one test process.
+    """
+    if not available():
+        raise RuntimeError(f'reference not found at {REFERENCE_DIR}')
+    saved = {name: sys.modules.pop(name) for name in _OWN_MODULES if name in sys.modules}
+    saved_flag = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True                       # the reference tree is read-only
+    if 'shapely' not in sys.modules:
+        sh, geo = types.ModuleType('shapely'), types.ModuleType('shapely.geometry')
+        geo.LineString = geo.Point = object
+        sh.geometry = geo
+        sys.modules['shapely'], sys.modules['shapely.geometry'] = sh, geo
+    sys.path.insert(0, REFERENCE_DIR)
+    try:
+        import forces, stateutils, pedestrian_state, pedestrian_simulation, ped_mode_manager   # noqa: E401
+        ns = types.SimpleNamespace(forces=forces, stateutils=stateutils, pedestrian_state=pedestrian_state,
+                                   pedestrian_simulation=pedestrian_simulation, ped_mode_manager=ped_mode_manager)
+    finally:
+        sys.path.remove(REFERENCE_DIR)
+        for name in _OWN_MODULES:
+            sys.modules.pop(name, None)
+        sys.modules.update(saved)
+        sys.dont_write_bytecode = saved_flag
+    return ns
+
+
+def load_config():
+    import tomllib
+    with open(os.path.join(REFERENCE_DIR, 'config', 'sfm_config.toml'), 'rb') as f:
+        return tomllib.load(f)
+
+
+def build_simulation(ref, workload, sfm_config):
+    """A reference ``PedestrianSimulation`` holding the workload's pedestrians (bulk-filled structured array)."""
+    sim = ref.pedestrian_simulation.PedestrianSimulation(list(workload.borders), workload.section_info(),
+                                                         list(workload.static_obstacles), sfm_config,
+                                                         workload.step_length)
+    PedMode, Manager = ref.ped_mode_manager.PedMode, ref.ped_mode_manager.PedModeManager
+    state = np.zeros(workload.n, dtype=sim.peds.ped_state_dtype)
+    state['name'] = [f'p{i}'[:8] for i in range(workload.n)]
+    state['id'] = np.arange(workload.n)
+    state['loc'], state['vel'], state['next_waypoint'] = workload.loc, workload.vel, workload.next_waypoint
+    state['radius'], state['target_speed'] = workload.radius, workload.target_speed
+    for i in range(workload.n):
+        # crossing_speed_factor 1.0 keeps target_speed == the drawn value in both modes (ped_mode_manager.py:22,61-63)
+        m = Manager(state['name'][i], float(workload.target_speed[i]), PedMode(int(workload.mode[i])), 1.0, -1.0)
+        state['mode'][i] = m
+    sim.peds.state = state
+    return sim
+
+
+def run_ticks(ref, workload, sfm_config, n_steps, record_forces=True):
+    """Drive the reference's own tick loop headless: tick -> read new velocities -> x += dt * v (the CARLA stub).
+
+    Returns dict(loc=(T+1,N,3), vel=(T+1,N,3), forces={class: (T,N,3)}).
+    """
+    sim = build_simulation(ref, workload, sfm_config)
+    dt = workload.step_length
+    locs, vels = [sim.peds.state['loc'].copy()], [sim.peds.state['vel'].copy()]
+    forces = {name: [] for name in sim.forces}
+    for step in range(n_steps):
+        veh = workload.vehicles_at(step)
+        if veh is not None:
+            sim.update_dynamic_obstacles(veh)                                    # pedestrian_simulation.py:108-115
+        if record_forces:
+            for name, f in sim.forces.items():
+                forces[name].append(f.get_force(sim.peds))
+        sim.tick(step * dt)                                                      # pedestrian_simulation.py:57-83
+        nv = sim.get_new_velocities()                                            # aliases state['vel']
+        sim.peds.state['loc'] += nv['vel'] * dt                                  # CARLA stub
+        sim.peds.all_states.clear()                                              # unbounded history, not needed
+        locs.append(sim.peds.state['loc'].copy())
+        vels.append(sim.peds.state['vel'].copy())
+    return dict(loc=np.array(locs), vel=np.array(vels), forces={k: np.array(v) for k, v in forces.items()})
