@@ -1,0 +1,383 @@
+// K2 -- uniform-grid cell lists and the cutoff-limited pedestrian x point-set forces, float64, sm_100a.
+//
+// Replaces BorderForce._get_force (reference forces.py:138-179) and ObstacleForce._get_force (forces.py:208-283), whose
+// per-pedestrian linear filters (forces.py:149-151, :222-225) become a cell-list lookup.
+//
+//  K2a  binning.  Set items (border sections / obstacles) are keyed by the grid cell of their *centre* -- the point the
+//       reference's cutoff is tested against -- and ordered by (cell, index) with a stable LSD radix sort, so every
+//       pedestrian visits its candidate items in one fixed order.  The cell edge is >= the largest cutoff of the set,
+//       hence every item within the cutoff of a pedestrian lies in the 3x3 cells around it.  Pedestrians are binned
+//       too (Morton-ordered counting sort) purely for locality: a CTA then owns pedestrians that share candidates.
+//  K2b/c  one CTA = 128 spatially adjacent pedestrians, one per thread.  The CTA walks the cells overlapping its
+//       bounding box (+1 ring), rejects items whose cutoff disc misses the box, stages the item's points in shared
+//       memory and lets every thread that passes the reference's exact filter scan them.
+//
+// Bit-exact enumeration: the filter sqrt(dx*dx + dy*dy) < cutoff and the nearest-point argmin are evaluated in float64
+// with numpy's operation order (np.linalg.norm = sqrt(add.reduce(x*x)), unfused), np.argmin's first-index tie rule
+// included -- so the (pedestrian, item, nearest point) triplets equal the reference's exactly, and the forces (also
+// float64, reference operation order) agree to a few ulp.
+#pragma once
+
+#include "sfm_common.cuh"
+
+namespace sfm {
+
+constexpr int K2_THREADS = 128;
+constexpr int K2_CHUNK = 256;           // points staged per pass
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_RADIX_BITS = 4;
+
+__device__ __forceinline__ double norm2_np(double dx, double dy) {   // np.linalg.norm of a 2-vector
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ int cell_coord(double v, double v0, double inv_cell, int n) {
+    int c = (int)floor((v - v0) * inv_cell);
+    return min(max(c, 0), n - 1);
+}
+
+// ---- K2a: set items -> (cell, index) order ------------------------------------------------------------------------
+__global__ void k2_item_keys(const double2* __restrict__ center, int count, CellGrid g, unsigned* __restrict__ key,
+                             int* __restrict__ val) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    const double2 c = center[s];
+    key[s] = (unsigned)(cell_coord(c.y, g.y0, g.inv_cell, g.ny) * g.nx + cell_coord(c.x, g.x0, g.inv_cell, g.nx));
+    val[s] = s;
+}
+
+// Stable LSD radix sort of (key, val) by one CTA; each thread owns a contiguous run of the input, so equal keys keep
+// their input (= index) order without any atomics.
+__global__ void __launch_bounds__(SORT_THREADS) k2_radix_sort(unsigned* key_a, int* val_a, unsigned* key_b, int* val_b,
+                                                              int count, int key_bits) {
+    constexpr int R = 1 << SORT_RADIX_BITS;
+    __shared__ int hist[R][SORT_THREADS];
+    __shared__ int digit_base[R];
+    const int tid = threadIdx.x;
+    const int per = (count + SORT_THREADS - 1) / SORT_THREADS;
+    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    unsigned* kin = key_a;
+    int* vin = val_a;
+    unsigned* kout = key_b;
+    int* vout = val_b;
+    for (int shift = 0; shift < key_bits; shift += SORT_RADIX_BITS) {
+        int cnt[R];
+#pragma unroll
+        for (int d = 0; d < R; ++d) cnt[d] = 0;
+        for (int i = lo; i < hi; ++i) {
+            const int d = (kin[i] >> shift) & (R - 1);
+#pragma unroll
+            for (int e = 0; e < R; ++e) cnt[e] += (e == d);
+        }
+#pragma unroll
+        for (int d = 0; d < R; ++d) hist[d][tid] = cnt[d];
+        __syncthreads();
+        // exclusive scan over (digit-major, thread-minor): per-digit scan across threads, then digit bases
+        if (tid < R) {
+            int run = 0;
+            for (int t = 0; t < SORT_THREADS; ++t) {
+                const int c = hist[tid][t];
+                hist[tid][t] = run;
+                run += c;
+            }
+            digit_base[tid] = run;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int d = 0; d < R; ++d) {
+                const int c = digit_base[d];
+                digit_base[d] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        int pos[R];
+#pragma unroll
+        for (int d = 0; d < R; ++d) pos[d] = digit_base[d] + hist[d][tid];
+        for (int i = lo; i < hi; ++i) {
+            const unsigned k = kin[i];
+            const int d = (k >> shift) & (R - 1);
+            int p = 0;
+#pragma unroll
+            for (int e = 0; e < R; ++e) {
+                if (e == d) {
+                    p = pos[e];
+                    pos[e] = p + 1;
+                }
+            }
+            kout[p] = k;
+            vout[p] = vin[i];
+        }
+        __syncthreads();
+        unsigned* tk = kin; kin = kout; kout = tk;
+        int* tv = vin; vin = vout; vout = tv;
+    }
+    // result is in (kin, vin); make sure it ends in buffer a
+    if (kin != key_a) {
+        for (int i = lo; i < hi; ++i) {
+            key_a[i] = kin[i];
+            val_a[i] = vin[i];
+        }
+    }
+}
+
+// cell_start[c] = first position in the sorted key array whose key is >= c  (c in [0, ncell])
+__global__ void k2_cell_bounds(const unsigned* __restrict__ sorted_key, int count, int ncell,
+                               int* __restrict__ cell_start) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncell) return;
+    int lo = 0, hi = count;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sorted_key[mid] < (unsigned)c) lo = mid + 1; else hi = mid;
+    }
+    cell_start[c] = lo;
+}
+
+// ---- K2a: pedestrians -> Morton-ordered permutation (locality only; order inside a cell is irrelevant) ------------
+__device__ __forceinline__ unsigned morton2(unsigned x, unsigned y) {
+    auto spread = [](unsigned v) {
+        v &= 0xffffu;
+        v = (v | (v << 8)) & 0x00ff00ffu;
+        v = (v | (v << 4)) & 0x0f0f0f0fu;
+        v = (v | (v << 2)) & 0x33333333u;
+        v = (v | (v << 1)) & 0x55555555u;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+
+__global__ void k2_ped_count(const double4* __restrict__ locr, int n, CellGrid g, unsigned* __restrict__ ped_cell,
+                             int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 L = locr[i];
+    const unsigned c = morton2((unsigned)cell_coord(L.x, g.x0, g.inv_cell, g.nx),
+                               (unsigned)cell_coord(L.y, g.y0, g.inv_cell, g.ny));
+    ped_cell[i] = c;
+    atomicAdd(&count[c], 1);
+}
+
+// in-place exclusive scan of data[0..n) by one CTA (n is a few 10^5 at most here)
+__global__ void __launch_bounds__(1024) k2_exclusive_scan(int* data, int n) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < n) ? data[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const int prefix = carry + (wid ? warp_sum[wid - 1] : 0) + x - v;
+        if (i < n) data[i] = prefix;
+        __syncthreads();
+        if (tid == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+}
+
+__global__ void k2_ped_fill(const unsigned* __restrict__ ped_cell, int n, const int* __restrict__ cell_start,
+                            int* __restrict__ cursor, int* __restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned c = ped_cell[i];
+    perm[cell_start[c] + atomicAdd(&cursor[c], 1)] = i;
+}
+
+// ---- K2b / K2c ---------------------------------------------------------------------------------------------------
+struct SegArgs {
+    const double4* locr;
+    const double4* vels;
+    const uint8_t* mode;
+    const int* perm;
+    int n;
+    // the set
+    const double2* center;
+    const double* cutoff;
+    const double2* velocity;
+    const int* offset;
+    const double2* point;
+    CellGrid grid;
+    const int* cell_start;
+    const int* cell_item;
+    // parameters
+    MoussaidD mp;
+    double border_a, border_b;
+    int use_radius;
+    double2* f_out;                 // [n]
+    long long* emit;                // optional [capacity][3]
+    unsigned long long* emit_count;
+    long long emit_capacity;
+};
+
+template <int KIND>   // 0: border (exponential repulsion), 1: obstacle (Moussaid)
+__device__ __forceinline__ double2 segment_force(const SegArgs& a, double px, double py, double vx, double vy,
+                                                 double radius, double2 P, double2 ovel) {
+    if (KIND == 0) {
+        // forces.py:158-165: direction from the border point to the pedestrian
+        const double dx = __dsub_rn(px, P.x), dy = __dsub_rn(py, P.y);
+        const double nrm = norm2_np(dx, dy);
+        const double dv = (nrm == 0.0) ? 1.0 : nrm;
+        const double ex = __ddiv_rn(dx, dv), ey = __ddiv_rn(dy, dv);
+        double dist = nrm;
+        if (a.use_radius) dist = __dsub_rn(dist, radius);
+        const double mag = exp(__ddiv_rn(__dmul_rn(-1.0, dist), a.border_b));
+        return make_double2(__dmul_rn(__dmul_rn(ex, a.border_a), mag), __dmul_rn(__dmul_rn(ey, a.border_a), mag));
+    } else {
+        // forces.py:233-270
+        const double dx = __dsub_rn(P.x, px), dy = __dsub_rn(P.y, py);
+        const double nrm = norm2_np(dx, dy);
+        const double dv = (nrm == 0.0) ? 1.0 : nrm;
+        const double ex = __ddiv_rn(dx, dv), ey = __ddiv_rn(dy, dv);
+        double dl = nrm;
+        if (a.use_radius) dl = __dsub_rn(dl, radius);
+        const double wx = __dsub_rn(vx, ovel.x), wy = __dsub_rn(vy, ovel.y);
+        const double Dx = __dadd_rn(__dmul_rn(a.mp.lambda, wx), ex), Dy = __dadd_rn(__dmul_rn(a.mp.lambda, wy), ey);
+        const double Dn = norm2_np(Dx, Dy);
+        const double Dv = (Dn == 0.0) ? 1.0 : Dn;
+        const double tx = __ddiv_rn(Dx, Dv), ty = __ddiv_rn(Dy, Dv);
+        const double nx = __dmul_rn(ty, -1.0), ny = tx;
+        double th = __dsub_rn(atan2(ey, ex), atan2(ty, tx));                 // stateutils.py:104-112
+        const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
+        if (th > PI) th = __dsub_rn(th, TWO_PI);
+        if (th < -PI) th = __dadd_rn(th, TWO_PI);
+        const double B = __dmul_rn(a.mp.gamma, Dn);
+        th = __dadd_rn(th, __dmul_rn(B, -a.mp.epsilon));
+        const double base = __ddiv_rn(__dmul_rn(-1.0, dl), B);
+        const double qv = __dmul_rn(__dmul_rn(a.mp.n_prime, B), th);
+        const double qt = __dmul_rn(__dmul_rn(a.mp.n, B), th);
+        const double fv = __dmul_rn(__dmul_rn(-1.0, a.mp.A), exp(__dsub_rn(base, __dmul_rn(qv, qv))));
+        const double sgn = (th > 0.0) ? 1.0 : ((th < 0.0) ? -1.0 : th);      // np.sign (nan stays nan)
+        const double ft = __dmul_rn(__dmul_rn(__dmul_rn(-1.0, a.mp.A), sgn), exp(__dsub_rn(base, __dmul_rn(qt, qt))));
+        return make_double2(__dadd_rn(__dmul_rn(fv, tx), __dmul_rn(ft, nx)),
+                            __dadd_rn(__dmul_rn(fv, ty), __dmul_rn(ft, ny)));
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
+    __shared__ double2 sp[K2_CHUNK];
+    __shared__ double red[4][K2_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int slot = blockIdx.x * K2_THREADS + tid;
+    const bool active = slot < a.n;
+    const int i = active ? a.perm[slot] : -1;
+    double px = 0.0, py = 0.0, radius = 0.0, vx = 0.0, vy = 0.0;
+    if (active) {
+        const double4 L = a.locr[i];
+        const double4 V = a.vels[i];
+        px = L.x; py = L.y; radius = L.w; vx = V.x; vy = V.y;
+    }
+    // CTA bounding box of the live pedestrians
+    const double BIG = 1.0e300;
+    double x0 = active ? px : BIG, x1 = active ? px : -BIG, y0 = active ? py : BIG, y1 = active ? py : -BIG;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+        x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (lane == 0) { red[0][wid] = x0; red[1][wid] = x1; red[2][wid] = y0; red[3][wid] = y1; }
+    __syncthreads();
+    x0 = red[0][0]; x1 = red[1][0]; y0 = red[2][0]; y1 = red[3][0];
+#pragma unroll
+    for (int w = 1; w < K2_THREADS / 32; ++w) {
+        x0 = fmin(x0, red[0][w]); x1 = fmax(x1, red[1][w]); y0 = fmin(y0, red[2][w]); y1 = fmax(y1, red[3][w]);
+    }
+    const CellGrid g = a.grid;
+    const int cx0 = max(cell_coord(x0, g.x0, g.inv_cell, g.nx) - 1, 0);
+    const int cx1 = min(cell_coord(x1, g.x0, g.inv_cell, g.nx) + 1, g.nx - 1);
+    const int cy0 = max(cell_coord(y0, g.y0, g.inv_cell, g.ny) - 1, 0);
+    const int cy1 = min(cell_coord(y1, g.y0, g.inv_cell, g.ny) + 1, g.ny - 1);
+
+    double fx = 0.0, fy = 0.0;
+    for (int cy = cy0; cy <= cy1; ++cy) {
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            const int c = cy * g.nx + cx;
+            const int k_end = a.cell_start[c + 1];
+            for (int k = a.cell_start[c]; k < k_end; ++k) {
+                const int s = a.cell_item[k];
+                const double2 cen = a.center[s];
+                const double cut = a.cutoff[s];
+                // CTA-uniform conservative reject: the cutoff disc misses the bounding box (with slack for rounding)
+                const double gx = fmax(fmax(x0 - cen.x, cen.x - x1), 0.0), gy = fmax(fmax(y0 - cen.y, cen.y - y1), 0.0);
+                if (gx * gx + gy * gy > cut * cut * 1.000000001) continue;
+                // the reference's filter, bit for bit: norm(loc - centre) < cutoff  (forces.py:149-150, :222-223)
+                const bool pass = active && (norm2_np(__dsub_rn(px, cen.x), __dsub_rn(py, cen.y)) < cut);
+                const bool warp_pass = __any_sync(0xffffffffu, pass);
+                const int o0 = a.offset[s], o1 = a.offset[s + 1];
+                double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+                int best_q = o0;
+                for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
+                    const int m = min(K2_CHUNK, o1 - c0);
+                    __syncthreads();
+                    for (int q = tid; q < m; q += K2_THREADS) sp[q] = a.point[c0 + q];
+                    __syncthreads();
+                    if (warp_pass) {
+                        for (int q = 0; q < m; ++q) {
+                            const double2 P = sp[q];
+                            const double dx = __dsub_rn(px, P.x), dy = __dsub_rn(py, P.y);
+                            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                            if (d2 < best) {
+                                // np.argmin runs on the rounded square roots: a smaller d2 whose sqrt rounds to the
+                                // same double is a tie and keeps the earlier index (forces.py:154, :228)
+                                if (d2 < best * 0.99999999999999 || __dsqrt_rn(d2) < __dsqrt_rn(best)) {
+                                    best = d2;
+                                    best_q = c0 + q;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (pass) {
+                    const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
+                                                          KIND ? a.velocity[s] : make_double2(0.0, 0.0));
+                    fx = __dadd_rn(fx, f.x);
+                    fy = __dadd_rn(fy, f.y);
+                    if (a.emit) {
+                        const unsigned long long e = atomicAdd(a.emit_count, 1ull);
+                        if ((long long)e < a.emit_capacity) {
+                            a.emit[3 * e + 0] = i;
+                            a.emit[3 * e + 1] = s;
+                            a.emit[3 * e + 2] = best_q - o0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (active) {
+        if (KIND == 0) {
+            const uint8_t md = a.mode[i];                   // forces.py:176-177
+            if (md == SFM_CROSSING_ROAD || md == SFM_ROAD_TO_SIDEWALK) { fx = __dmul_rn(fx, 0.0); fy = __dmul_rn(fy, 0.0); }
+        }
+        a.f_out[i] = make_double2(fx, fy);
+    }
+}
+
+__global__ void k2_zero(double2* f, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = make_double2(0.0, 0.0);
+}
+
+}  // namespace sfm

@@ -1,0 +1,162 @@
+// K3 -- fused acceleration force + force sum + Euler step + speed clamp + restaging, float64, HBM-bound.
+//
+// Replaces AccelerationForce._get_force (reference forces.py:46-53 with stateutils.desired_directions :7-15), the
+// dict-order force sum of PedestrianSimulation.tick (pedestrian_simulation.py:81), calculate_new_velocities (:117-124)
+// with stateutils.cap_velocity (stateutils.py:18-23) and PedState.max_speed (pedestrian_state.py:72-73), and -- when
+// integrate_positions is set -- the position update the reference leaves to the CARLA server (run_simulation.py:77-87),
+// defined here as semi-implicit Euler x+ = x + dt v+.
+//
+// The master state stays float64 (the reference dtype, pedestrian_state.py:17): products and sums use the unfused
+// __dmul_rn/__dadd_rn forms in numpy's operation order, so with identical force inputs the new velocities are
+// bit-identical to numpy's.  The same pass re-emits the float32 staging planes the pair kernel reads next step.
+#pragma once
+
+#include "sfm_common.cuh"
+
+namespace sfm {
+
+struct StepArgs {
+    // master state of the local rows
+    double4* locr;               // (x, y, z, radius)
+    double4* vels;               // (vx, vy, vz, target_speed)
+    const double2* wp;           // next waypoint xy
+    const uint8_t* mode;
+    int64_t n;                   // live local rows
+    int64_t rows_pad;            // staged rows of one rank block
+    // force inputs
+    const float4* ped_partial;   // [nsplit][rows_pad]
+    int nsplit;
+    const double2* f_border;     // [n] or nullptr
+    const double2* f_static;
+    const double2* f_dynamic;
+    // outputs
+    double* f_total;             // [n][3]
+    double* f_accel;             // [n][3] or nullptr (kept only when class forces are requested)
+    double* f_ped;               // [n][3] or nullptr
+    float* planes_own;           // this rank's block of the gather buffer: [NPLANES][rows_pad]
+    // parameters
+    double dt, tau, max_speed_factor, lambda_ped;
+    double ox, oy, oz;
+    int enable_accel, enable_ped;
+    int update_velocity;         // 0: forces only (Force.get_force path)
+    int integrate_positions;
+};
+
+__device__ __forceinline__ void stage_row(float* planes, int64_t rows_pad, int64_t i, double x, double y, double z,
+                                          double r, double vx, double vy, double vz, const StepArgs& a) {
+    planes[PX * rows_pad + i] = (float)(x - a.ox);
+    planes[PY * rows_pad + i] = (float)(y - a.oy);
+    planes[PZ * rows_pad + i] = (float)(z - a.oz);
+    planes[PR * rows_pad + i] = (float)r;
+    planes[PVX * rows_pad + i] = (float)(a.lambda_ped * vx);
+    planes[PVY * rows_pad + i] = (float)(a.lambda_ped * vy);
+    planes[PVZ * rows_pad + i] = (float)(a.lambda_ped * vz);
+}
+
+__device__ __forceinline__ void stage_pad(float* planes, int64_t rows_pad, int64_t i) {
+    planes[PX * rows_pad + i] = PAD_POS;
+    planes[PY * rows_pad + i] = PAD_POS;
+    planes[PZ * rows_pad + i] = 0.0f;
+    planes[PR * rows_pad + i] = 0.0f;
+    planes[PVX * rows_pad + i] = 0.0f;
+    planes[PVY * rows_pad + i] = 0.0f;
+    planes[PVZ * rows_pad + i] = 0.0f;
+}
+
+// Staging only: master state -> float32 planes (after an upload or a kinematics refresh).
+__global__ void __launch_bounds__(256) k3_stage(StepArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.rows_pad) return;
+    if (i >= a.n) {
+        stage_pad(a.planes_own, a.rows_pad, i);
+        return;
+    }
+    const double4 L = a.locr[i], V = a.vels[i];
+    stage_row(a.planes_own, a.rows_pad, i, L.x, L.y, L.z, L.w, V.x, V.y, V.z, a);
+}
+
+__global__ void __launch_bounds__(256) k3_integrate(StepArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;                      // pad rows keep the staging k3_stage gave them
+    const double4 L = a.locr[i];
+    const double4 V = a.vels[i];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (a.enable_accel) {
+        const double2 w = a.wp[i];
+        const double ex = __dsub_rn(w.x, L.x), ey = __dsub_rn(w.y, L.y);
+        const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+        const double dv = (nrm == 0.0) ? 1.0 : nrm;                        // stateutils.py:88-90
+        const double dirx = __ddiv_rn(ex, dv), diry = __ddiv_rn(ey, dv);
+        const double inv_tau = __ddiv_rn(1.0, a.tau);                      // forces.py:51  1.0 / tau * (...)
+        const double ax = __dmul_rn(inv_tau, __dsub_rn(__dmul_rn(V.w, dirx), V.x));
+        const double ay = __dmul_rn(inv_tau, __dsub_rn(__dmul_rn(V.w, diry), V.y));
+        const double az = __dmul_rn(inv_tau, __dsub_rn(__dmul_rn(V.w, 0.0), V.z));
+        if (a.f_accel) {
+            a.f_accel[3 * i + 0] = ax;
+            a.f_accel[3 * i + 1] = ay;
+            a.f_accel[3 * i + 2] = az;
+        }
+        fx = __dadd_rn(fx, ax);
+        fy = __dadd_rn(fy, ay);
+        fz = __dadd_rn(fz, az);
+    }
+    if (a.enable_ped) {
+        double px = 0.0, py = 0.0, pz = 0.0;
+        for (int s = 0; s < a.nsplit; ++s) {                              // fixed order: deterministic
+            const float4 p = a.ped_partial[(size_t)s * a.rows_pad + i];
+            px += (double)p.x;
+            py += (double)p.y;
+            pz += (double)p.z;
+        }
+        if (a.f_ped) {
+            a.f_ped[3 * i + 0] = px;
+            a.f_ped[3 * i + 1] = py;
+            a.f_ped[3 * i + 2] = pz;
+        }
+        fx = __dadd_rn(fx, px);
+        fy = __dadd_rn(fy, py);
+        fz = __dadd_rn(fz, pz);
+    }
+    if (a.f_border) {
+        const double2 f = a.f_border[i];
+        fx = __dadd_rn(fx, f.x);
+        fy = __dadd_rn(fy, f.y);
+    }
+    if (a.f_static) {
+        const double2 f = a.f_static[i];
+        fx = __dadd_rn(fx, f.x);
+        fy = __dadd_rn(fy, f.y);
+    }
+    if (a.f_dynamic) {
+        const double2 f = a.f_dynamic[i];
+        fx = __dadd_rn(fx, f.x);
+        fy = __dadd_rn(fy, f.y);
+    }
+    a.f_total[3 * i + 0] = fx;
+    a.f_total[3 * i + 1] = fy;
+    a.f_total[3 * i + 2] = fz;
+    if (!a.update_velocity) return;
+
+    // pedestrian_simulation.py:120-121, stateutils.py:18-23
+    double vx = __dadd_rn(V.x, __dmul_rn(a.dt, fx));
+    double vy = __dadd_rn(V.y, __dmul_rn(a.dt, fy));
+    double vz = __dadd_rn(V.z, __dmul_rn(a.dt, fz));
+    double sp = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+    if (sp == 0.0) sp = 1.0;
+    const double vmax = __dmul_rn(V.w, a.max_speed_factor);               // pedestrian_state.py:72-73
+    const double factor = fmin(1.0, __ddiv_rn(vmax, sp));
+    vx = __dmul_rn(vx, factor);
+    vy = __dmul_rn(vy, factor);
+    vz = __dmul_rn(vz, factor);
+    a.vels[i] = make_double4(vx, vy, vz, V.w);
+    double x = L.x, y = L.y, z = L.z;
+    if (a.integrate_positions) {                                          // CARLA stub: x += v+ * dt
+        x = __dadd_rn(x, __dmul_rn(vx, a.dt));
+        y = __dadd_rn(y, __dmul_rn(vy, a.dt));
+        z = __dadd_rn(z, __dmul_rn(vz, a.dt));
+        a.locr[i] = make_double4(x, y, z, L.w);
+    }
+    stage_row(a.planes_own, a.rows_pad, i, x, y, z, L.w, vx, vy, vz, a);
+}
+
+}  // namespace sfm

@@ -1,0 +1,828 @@
+// C ABI of sfm_b200 (include/sfm_b200.h): context, device memory, launch sequencing.  sm_100a only, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "k1_ped_pairs.cuh"
+#include "k2_cells.cuh"
+#include "k3_integrate.cuh"
+
+using namespace sfm;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const std::string& msg) {
+    g_error = msg;
+    return 1;
+}
+
+#define SFM_CUDA(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess)                                                                           \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(err__) + " (" __FILE__ ":" +         \
+                        std::to_string(__LINE__) + ")");                                                    \
+    } while (0)
+
+#define SFM_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) SFM_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        SFM_CUDA(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum StatClass { ST_PAIRS = 0, ST_CELLS = 1, ST_SEGMENTS = 2, ST_INTEGRATE = 3, ST_COUNT = 4 };
+
+struct TimedSpan {
+    cudaEvent_t start, stop;
+    int cls;
+};
+
+struct SetStorage {
+    SegmentSet s;
+    DevBuf<double2> center, velocity, point;
+    DevBuf<double> cutoff;
+    DevBuf<int> offset, cell_start, cell_item, val_tmp;
+    DevBuf<unsigned> key, key_tmp;
+    void release() {
+        center.release(); velocity.release(); point.release(); cutoff.release(); offset.release();
+        cell_start.release(); cell_item.release(); val_tmp.release(); key.release(); key_tmp.release();
+    }
+};
+
+}  // namespace
+
+struct sfm_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    sfm_params params{};
+    bool have_params = false;
+    double ox = 0.0, oy = 0.0, oz = 0.0;
+    int world = 1, rank = 0;
+    int64_t rows_pad = 0;
+    bool partition_fixed = false;
+    int64_t n = 0;
+    bool staged = false;            // planes_own reflects the master state
+
+    DevBuf<double4> locr, vels;
+    DevBuf<double2> wp;
+    DevBuf<uint8_t> mode;
+    DevBuf<float> planes;           // [world][NPLANES][rows_pad]
+    DevBuf<float4> partial;         // [nsplit][rows_pad]
+    int nsplit = 1;
+    DevBuf<double2> f_border, f_static, f_dynamic;
+    DevBuf<double> f_total, f_accel, f_ped;
+    DevBuf<double> raw_a, raw_b, raw_c, raw_d, raw_e;   // upload / download scratch
+    DevBuf<uint8_t> raw_mode;
+    // pedestrian binning
+    CellGrid ped_grid{};
+    int ped_cells = 0;
+    DevBuf<int> perm, ped_start, ped_cursor;
+    DevBuf<unsigned> ped_cell;
+    bool perm_valid = false;
+    // point sets
+    SetStorage borders, stat, dyn;
+    // enumeration scratch
+    DevBuf<long long> emit;
+    DevBuf<unsigned long long> emit_count;
+    // accounting
+    bool profiling = false;
+    int64_t launches = 0, steps = 0, pair_launches = 0;
+    double ms[ST_COUNT] = {0, 0, 0, 0};
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    int k1_target_ctas = 148 * 4 * 16;
+};
+
+namespace {
+
+struct SpanGuard {
+    sfm_ctx* c;
+    int idx = -1;
+    SpanGuard(sfm_ctx* ctx, int cls) : c(ctx) {
+        if (!c->profiling) return;
+        TimedSpan sp;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        sp.start = get();
+        sp.stop = get();
+        sp.cls = cls;
+        cudaEventRecord(sp.start, c->stream);
+        c->spans.push_back(sp);
+        idx = (int)c->spans.size() - 1;
+    }
+    ~SpanGuard() {
+        if (idx >= 0) cudaEventRecord(c->spans[idx].stop, c->stream);
+    }
+};
+
+int drain_spans(sfm_ctx* c) {
+    if (c->spans.empty()) return 0;
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& sp : c->spans) {
+        float t = 0.f;
+        SFM_CUDA(cudaEventElapsedTime(&t, sp.start, sp.stop));
+        c->ms[sp.cls] += t;
+        c->event_pool.push_back(sp.start);
+        c->event_pool.push_back(sp.stop);
+    }
+    c->spans.clear();
+    return 0;
+}
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- small packing kernels (host layout [n][3] float64 <-> device double4) ----------------------------------------
+__global__ void pack_state(int64_t n, const double* loc, const double* vel, const double* wp3, const double* radius,
+                           const double* speed, const uint8_t* mode_in, double4* locr, double4* vels, double2* wp,
+                           uint8_t* mode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (loc) {
+        const double r = radius ? radius[i] : locr[i].w;
+        locr[i] = make_double4(loc[3 * i], loc[3 * i + 1], loc[3 * i + 2], r);
+    }
+    if (vel) {
+        const double s = speed ? speed[i] : vels[i].w;
+        vels[i] = make_double4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], s);
+    } else if (speed) {
+        vels[i].w = speed[i];
+    }
+    if (wp3) wp[i] = make_double2(wp3[3 * i], wp3[3 * i + 1]);
+    if (mode_in) mode[i] = mode_in[i];
+}
+
+__global__ void unpack_state(int64_t n, const double4* locr, const double4* vels, double* loc, double* vel) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (loc) {
+        const double4 L = locr[i];
+        loc[3 * i] = L.x; loc[3 * i + 1] = L.y; loc[3 * i + 2] = L.z;
+    }
+    if (vel) {
+        const double4 V = vels[i];
+        vel[3 * i] = V.x; vel[3 * i + 1] = V.y; vel[3 * i + 2] = V.z;
+    }
+}
+
+__global__ void expand_xy(int64_t n, const double2* f, double* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 v = f[i];
+    out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = 0.0;
+}
+
+int check_ctx(sfm_ctx* c) {
+    if (!c) return fail("null context");
+    SFM_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+PairParams make_pair_params(const sfm_moussaid_params& m) {
+    const double l2e = 1.4426950408889634;
+    PairParams p;
+    p.lambda = (float)m.lambda_weight;
+    p.eps_gamma = (float)(m.epsilon * m.gamma);
+    p.neg_l2e_over_gamma = (float)(-l2e / m.gamma);
+    p.c_nprime = (float)(m.n_prime * m.gamma * m.n_prime * m.gamma * l2e);
+    p.c_n = (float)(m.n * m.gamma * m.n * m.gamma * l2e);
+    p.log2A = (float)std::log2(m.A);
+    return p;
+}
+
+MoussaidD make_moussaid_d(const sfm_moussaid_params& m) {
+    MoussaidD d;
+    d.lambda = m.lambda_weight; d.A = m.A; d.gamma = m.gamma; d.n = m.n; d.n_prime = m.n_prime;
+    d.epsilon = m.epsilon; d.threshold = m.perception_threshold;
+    return d;
+}
+
+int ensure_layout(sfm_ctx* c, int64_t n) {
+    if (!c->partition_fixed) {
+        c->world = 1;
+        c->rank = 0;
+        c->rows_pad = std::max<int64_t>(ROW_ALIGN, (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN);
+    } else if (n > c->rows_pad) {
+        return fail("row count exceeds the rows_pad given to sfm_set_partition");
+    }
+    if (c->rows_pad * (int64_t)c->world > (int64_t)1 << 30) return fail("too many staged rows");
+    SFM_TRY(c->planes.ensure((size_t)c->world * NPLANES * c->rows_pad));
+    return 0;
+}
+
+StepArgs step_args(sfm_ctx* c) {
+    StepArgs a{};
+    a.locr = c->locr.p; a.vels = c->vels.p; a.wp = c->wp.p; a.mode = c->mode.p;
+    a.n = c->n; a.rows_pad = c->rows_pad;
+    a.ped_partial = c->partial.p; a.nsplit = c->nsplit;
+    a.f_total = c->f_total.p;
+    a.planes_own = c->planes.p + (size_t)c->rank * NPLANES * c->rows_pad;
+    a.dt = c->params.step_length; a.tau = c->params.tau; a.max_speed_factor = c->params.max_speed_factor;
+    a.lambda_ped = c->params.ped.lambda_weight;
+    a.ox = c->ox; a.oy = c->oy; a.oz = c->oz;
+    return a;
+}
+
+int launch_stage(sfm_ctx* c) {
+    SpanGuard g(c, ST_INTEGRATE);
+    StepArgs a = step_args(c);
+    k3_stage<<<cdiv(c->rows_pad, 256), 256, 0, c->stream>>>(a);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->staged = true;
+    return 0;
+}
+
+int launch_pairs(sfm_ctx* c) {
+    if (!c->staged) SFM_TRY(launch_stage(c));
+    constexpr int IR = 2;
+    const int rows_per_cta = K1_THREADS * IR;
+    const int itiles = (int)(c->rows_pad / rows_per_cta);
+    const int total_tiles = (int)((int64_t)c->world * c->rows_pad / K1_TJ);
+    int nsplit = std::max(1, cdiv(c->k1_target_ctas, itiles));
+    nsplit = std::min(nsplit, std::min(total_tiles, 512));
+    c->nsplit = nsplit;
+    SFM_TRY(c->partial.ensure((size_t)nsplit * c->rows_pad));
+    const PairParams pp = make_pair_params(c->params.ped);
+    SpanGuard g(c, ST_PAIRS);
+    dim3 grid(itiles, nsplit);
+    if (c->params.use_ped_radius)
+        k1_ped_pairs<IR, true><<<grid, K1_THREADS, 0, c->stream>>>(c->planes.p, (int)c->rows_pad, total_tiles, c->rank,
+                                                                  c->partial.p, (int)c->rows_pad, pp);
+    else
+        k1_ped_pairs<IR, false><<<grid, K1_THREADS, 0, c->stream>>>(c->planes.p, (int)c->rows_pad, total_tiles, c->rank,
+                                                                   c->partial.p, (int)c->rows_pad, pp);
+    c->launches += 1;
+    c->pair_launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int rebin_peds(sfm_ctx* c) {
+    const int n = (int)c->n;
+    SFM_TRY(c->perm.ensure(n));
+    SFM_TRY(c->ped_cell.ensure(n));
+    SFM_TRY(c->ped_start.ensure(c->ped_cells + 1));
+    SFM_TRY(c->ped_cursor.ensure(c->ped_cells + 1));
+    SpanGuard g(c, ST_CELLS);
+    SFM_CUDA(cudaMemsetAsync(c->ped_start.p, 0, sizeof(int) * (c->ped_cells + 1), c->stream));
+    SFM_CUDA(cudaMemsetAsync(c->ped_cursor.p, 0, sizeof(int) * (c->ped_cells + 1), c->stream));
+    k2_ped_count<<<cdiv(n, 256), 256, 0, c->stream>>>(c->locr.p, n, c->ped_grid, c->ped_cell.p, c->ped_start.p);
+    k2_exclusive_scan<<<1, 1024, 0, c->stream>>>(c->ped_start.p, c->ped_cells + 1);
+    k2_ped_fill<<<cdiv(n, 256), 256, 0, c->stream>>>(c->ped_cell.p, n, c->ped_start.p, c->ped_cursor.p, c->perm.p);
+    c->launches += 3;
+    SFM_CUDA(cudaGetLastError());
+    c->perm_valid = true;
+    return 0;
+}
+
+// Pedestrian grid from the host-side bounding box at upload time; later positions are clamped into it (the
+// permutation only provides locality, never correctness).
+void plan_ped_grid(sfm_ctx* c, int64_t n, const double* loc) {
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int64_t i = 0; i < n; ++i) {
+        const double x = loc[3 * i], y = loc[3 * i + 1];
+        if (x < x0) x0 = x;
+        if (x > x1) x1 = x;
+        if (y < y0) y0 = y;
+        if (y > y1) y1 = y;
+    }
+    if (n == 0 || !(x1 >= x0) || !(y1 >= y0)) { x0 = y0 = 0.0; x1 = y1 = 1.0; }
+    const double w = std::max(x1 - x0, 1.0), h = std::max(y1 - y0, 1.0);
+    x0 -= 0.05 * w; y0 -= 0.05 * h;
+    const double W = 1.1 * w, H = 1.1 * h;
+    double cell = std::max(1.0, std::sqrt(16.0 * W * H / (double)std::max<int64_t>(n, 1)));
+    int bits = 1;
+    for (;;) {
+        const int nx = (int)std::ceil(W / cell), ny = (int)std::ceil(H / cell);
+        bits = 1;
+        while ((1 << bits) < std::max(nx, ny)) ++bits;
+        if (bits <= 9) break;          // at most 512 x 512 cells
+        cell *= 2.0;
+    }
+    c->ped_grid.x0 = x0; c->ped_grid.y0 = y0; c->ped_grid.cell = cell; c->ped_grid.inv_cell = 1.0 / cell;
+    c->ped_grid.nx = 1 << bits; c->ped_grid.ny = 1 << bits;
+    c->ped_cells = (1 << bits) * (1 << bits);
+}
+
+int build_set_grid(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers, double max_cut) {
+    SegmentSet& s = st.s;
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int64_t i = 0; i < count; ++i) {
+        x0 = std::min(x0, centers[2 * i]); x1 = std::max(x1, centers[2 * i]);
+        y0 = std::min(y0, centers[2 * i + 1]); y1 = std::max(y1, centers[2 * i + 1]);
+    }
+    double cell = std::max(max_cut, 1e-3);
+    for (;;) {
+        const double nx = std::floor((x1 - x0) / cell) + 1.0, ny = std::floor((y1 - y0) / cell) + 1.0;
+        if (nx * ny <= 1048576.0 && nx <= 4096.0 && ny <= 4096.0) break;
+        cell *= 2.0;
+    }
+    s.grid.x0 = x0; s.grid.y0 = y0; s.grid.cell = cell; s.grid.inv_cell = 1.0 / cell;
+    s.grid.nx = (int)(std::floor((x1 - x0) / cell) + 1.0);
+    s.grid.ny = (int)(std::floor((y1 - y0) / cell) + 1.0);
+    const int ncell = s.grid.nx * s.grid.ny;
+    SFM_TRY(st.cell_start.ensure(ncell + 2));
+    SFM_TRY(st.cell_item.ensure(count));
+    SFM_TRY(st.val_tmp.ensure(count));
+    SFM_TRY(st.key.ensure(count));
+    SFM_TRY(st.key_tmp.ensure(count));
+    int key_bits = 1;
+    while ((1 << key_bits) < ncell) ++key_bits;
+    SpanGuard g(c, ST_CELLS);
+    k2_item_keys<<<cdiv(count, 256), 256, 0, c->stream>>>(st.center.p, (int)count, s.grid, st.key.p, st.cell_item.p);
+    k2_radix_sort<<<1, SORT_THREADS, 0, c->stream>>>(st.key.p, st.cell_item.p, st.key_tmp.p, st.val_tmp.p, (int)count,
+                                                     key_bits);
+    k2_cell_bounds<<<cdiv(ncell + 1, 256), 256, 0, c->stream>>>(st.key.p, (int)count, ncell, st.cell_start.p);
+    c->launches += 3;
+    SFM_CUDA(cudaGetLastError());
+    s.cell_start = st.cell_start.p;
+    s.cell_item = st.cell_item.p;
+    return 0;
+}
+
+int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers, const double* cutoffs,
+               double uniform_cut, const double* velocities, const int64_t* offsets, const double* points) {
+    SegmentSet& s = st.s;
+    s.count = 0;
+    if (count <= 0) return 0;
+    if (!centers || !offsets || !points) return fail("null point-set array");
+    const int64_t np = offsets[count];
+    if (np > (int64_t)INT32_MAX || count > (int64_t)INT32_MAX) return fail("point set too large");
+    for (int64_t i = 0; i < count; ++i)
+        if (offsets[i + 1] <= offsets[i]) return fail("every section / obstacle needs at least one point");
+    SFM_TRY(st.center.ensure(count));
+    SFM_TRY(st.cutoff.ensure(count));
+    SFM_TRY(st.velocity.ensure(count));
+    SFM_TRY(st.offset.ensure(count + 1));
+    SFM_TRY(st.point.ensure(np));
+    std::vector<double> cut(count);
+    std::vector<int> off(count + 1);
+    double max_cut = 0.0;
+    for (int64_t i = 0; i < count; ++i) {
+        cut[i] = cutoffs ? cutoffs[i] : uniform_cut;
+        if (std::isfinite(cut[i])) max_cut = std::max(max_cut, cut[i]);
+    }
+    for (int64_t i = 0; i <= count; ++i) off[i] = (int)offsets[i];
+    // synchronous copies from pageable host memory: the inputs may be temporaries of the caller
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    SFM_CUDA(cudaMemcpy(st.center.p, centers, sizeof(double2) * count, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.cutoff.p, cut.data(), sizeof(double) * count, cudaMemcpyHostToDevice));
+    if (velocities) SFM_CUDA(cudaMemcpy(st.velocity.p, velocities, sizeof(double2) * count, cudaMemcpyHostToDevice));
+    else SFM_CUDA(cudaMemset(st.velocity.p, 0, sizeof(double2) * count));
+    SFM_CUDA(cudaMemcpy(st.offset.p, off.data(), sizeof(int) * (count + 1), cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.point.p, points, sizeof(double2) * np, cudaMemcpyHostToDevice));
+    s.center = st.center.p; s.cutoff = st.cutoff.p; s.velocity = st.velocity.p; s.offset = st.offset.p;
+    s.point = st.point.p; s.n_points = np;
+    SFM_TRY(build_set_grid(c, st, count, centers, max_cut));
+    s.count = count;
+    return 0;
+}
+
+int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity) {
+    SetStorage& st = (cls == SFM_FORCE_BORDER) ? c->borders : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->stat : c->dyn);
+    DevBuf<double2>& out = (cls == SFM_FORCE_BORDER) ? c->f_border
+                                                     : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->f_static : c->f_dynamic);
+    const int n = (int)c->n;
+    SFM_TRY(out.ensure(n));
+    if (st.s.count == 0) {       // forces.py:140-141, :209-210: zeros
+        SpanGuard g(c, ST_SEGMENTS);
+        k2_zero<<<cdiv(n, 256), 256, 0, c->stream>>>(out.p, n);
+        c->launches += 1;
+        SFM_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (!c->perm_valid) SFM_TRY(rebin_peds(c));
+    SegArgs a{};
+    a.locr = c->locr.p; a.vels = c->vels.p; a.mode = c->mode.p; a.perm = c->perm.p; a.n = n;
+    a.center = st.s.center; a.cutoff = st.s.cutoff; a.velocity = st.s.velocity; a.offset = st.s.offset;
+    a.point = st.s.point; a.grid = st.s.grid; a.cell_start = st.s.cell_start; a.cell_item = st.s.cell_item;
+    a.mp = make_moussaid_d(cls == SFM_FORCE_DYNAMIC_OBSTACLE ? c->params.dynamic_obs : c->params.static_obs);
+    a.border_a = c->params.border_a; a.border_b = c->params.border_b;
+    a.use_radius = c->params.use_ped_radius;
+    a.f_out = out.p;
+    if (emit) {
+        a.emit = c->emit.p; a.emit_count = c->emit_count.p; a.emit_capacity = emit_capacity;
+    }
+    SpanGuard g(c, ST_SEGMENTS);
+    if (cls == SFM_FORCE_BORDER) k2_segments<0><<<cdiv(n, K2_THREADS), K2_THREADS, 0, c->stream>>>(a);
+    else k2_segments<1><<<cdiv(n, K2_THREADS), K2_THREADS, 0, c->stream>>>(a);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ensure_force_buffers(sfm_ctx* c) {
+    SFM_TRY(c->f_total.ensure((size_t)3 * c->n));
+    SFM_TRY(c->f_accel.ensure((size_t)3 * c->n));
+    SFM_TRY(c->f_ped.ensure((size_t)3 * c->n));
+    return 0;
+}
+
+// One tick on the device: all enabled forces, then K3.
+int step_once(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool keep_class_forces) {
+    const sfm_params& P = c->params;
+    SFM_TRY(ensure_force_buffers(c));
+    if (P.enable[SFM_FORCE_PEDESTRIAN]) SFM_TRY(launch_pairs(c));
+    const bool any_set = (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) ||
+                         (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) ||
+                         (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count);
+    if (any_set && !c->perm_valid) SFM_TRY(rebin_peds(c));
+    StepArgs a = step_args(c);
+    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) {
+        SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0));
+        a.f_border = c->f_border.p;
+    }
+    if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) {
+        SFM_TRY(launch_segments(c, SFM_FORCE_STATIC_OBSTACLE, false, 0));
+        a.f_static = c->f_static.p;
+    }
+    if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count) {
+        SFM_TRY(launch_segments(c, SFM_FORCE_DYNAMIC_OBSTACLE, false, 0));
+        a.f_dynamic = c->f_dynamic.p;
+    }
+    a.enable_accel = P.enable[SFM_FORCE_ACCELERATION];
+    a.enable_ped = P.enable[SFM_FORCE_PEDESTRIAN];
+    a.ped_partial = c->partial.p;
+    a.nsplit = c->nsplit;
+    a.update_velocity = update_velocity;
+    a.integrate_positions = integrate_positions;
+    if (keep_class_forces) { a.f_accel = c->f_accel.p; a.f_ped = c->f_ped.p; }
+    {
+        SpanGuard g(c, ST_INTEGRATE);
+        k3_integrate<<<cdiv(std::max<int64_t>(c->n, 1), 256), 256, 0, c->stream>>>(a);
+        c->launches += 1;
+        SFM_CUDA(cudaGetLastError());
+    }
+    if (update_velocity) {
+        c->steps += 1;
+        c->perm_valid = false;      // positions moved; rebin before the next segment pass
+    }
+    return 0;
+}
+
+int download3(sfm_ctx* c, const double* dev, int64_t n, double* out) {
+    SFM_CUDA(cudaMemcpyAsync(out, dev, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfm_abi_version(void) { return SFM_ABI_VERSION; }
+
+const char* sfm_last_error(void) { return g_error.c_str(); }
+
+int sfm_device_count(int* count) {
+    if (!count) return fail("null pointer");
+    SFM_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int sfm_create(int device, sfm_ctx** out) {
+    if (!out) return fail("null pointer");
+    *out = nullptr;
+    int count = 0;
+    SFM_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail("no such CUDA device");
+    cudaDeviceProp prop;
+    SFM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(std::string("sfm_b200 needs an sm_100 (B200) device, found ") + prop.name + " (sm_" +
+                    std::to_string(prop.major) + std::to_string(prop.minor) + "); there is no fallback path");
+    SFM_CUDA(cudaSetDevice(device));
+    sfm_ctx* c = new sfm_ctx();
+    c->device = device;
+    SFM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    if (const char* env = std::getenv("SFM_K1_TARGET_CTAS")) c->k1_target_ctas = std::max(1, std::atoi(env));
+    else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
+    *out = c;
+    return 0;
+}
+
+int sfm_destroy(sfm_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& sp : c->spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    c->locr.release(); c->vels.release(); c->wp.release(); c->mode.release(); c->planes.release();
+    c->partial.release(); c->f_border.release(); c->f_static.release(); c->f_dynamic.release();
+    c->f_total.release(); c->f_accel.release(); c->f_ped.release();
+    c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
+    c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
+    c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release();
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int sfm_set_stream(sfm_ctx* c, void* cuda_stream) {
+    SFM_TRY(check_ctx(c));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return 0;
+}
+
+int sfm_synchronize(sfm_ctx* c) {
+    SFM_TRY(check_ctx(c));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_set_params(sfm_ctx* c, const sfm_params* p) {
+    SFM_TRY(check_ctx(c));
+    if (!p) return fail("null params");
+    if (!(p->step_length > 0.0)) return fail("step_length must be positive");
+    if (!(p->tau > 0.0)) return fail("tau must be positive");
+    const sfm_moussaid_params* sets[3] = {&p->ped, &p->static_obs, &p->dynamic_obs};
+    for (auto* m : sets)
+        if (!(m->gamma > 0.0) || !(m->A > 0.0)) return fail("Moussaid parameters gamma and A must be positive");
+    if (!(p->border_b != 0.0)) return fail("border_force.b must be non-zero");
+    const bool lambda_changed = !c->have_params || c->params.ped.lambda_weight != p->ped.lambda_weight;
+    c->params = *p;
+    c->have_params = true;
+    if (lambda_changed) c->staged = false;
+    return 0;
+}
+
+int sfm_set_origin(sfm_ctx* c, double ox, double oy, double oz) {
+    SFM_TRY(check_ctx(c));
+    c->ox = ox; c->oy = oy; c->oz = oz;
+    c->staged = false;
+    return 0;
+}
+
+int sfm_set_partition(sfm_ctx* c, int world, int rank, int64_t rows_pad) {
+    SFM_TRY(check_ctx(c));
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad world / rank");
+    if (rows_pad <= 0 || rows_pad % ROW_ALIGN != 0) return fail("rows_pad must be a positive multiple of 256");
+    c->world = world; c->rank = rank; c->rows_pad = rows_pad;
+    c->partition_fixed = true;
+    c->staged = false;
+    return 0;
+}
+
+int sfm_upload_state(sfm_ctx* c, int64_t n, const double* loc, const double* vel, const double* wp3,
+                     const double* radius, const double* speed, const uint8_t* mode) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (n < 0 || n > (int64_t)1 << 28) return fail("bad row count");
+    if (n > 0 && (!loc || !vel || !wp3 || !radius || !speed || !mode)) return fail("null state array");
+    SFM_TRY(ensure_layout(c, n));
+    c->n = n;
+    c->staged = false;
+    c->perm_valid = false;
+    if (n == 0) return 0;
+    SFM_TRY(c->locr.ensure(n)); SFM_TRY(c->vels.ensure(n)); SFM_TRY(c->wp.ensure(n)); SFM_TRY(c->mode.ensure(n));
+    SFM_TRY(c->raw_a.ensure(3 * n)); SFM_TRY(c->raw_b.ensure(3 * n)); SFM_TRY(c->raw_c.ensure(3 * n));
+    SFM_TRY(c->raw_d.ensure(n)); SFM_TRY(c->raw_e.ensure(n)); SFM_TRY(c->raw_mode.ensure(n));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_a.p, loc, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_b.p, vel, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_c.p, wp3, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_d.p, radius, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_e.p, speed, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_mode.p, mode, n, cudaMemcpyHostToDevice, c->stream));
+    pack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->raw_a.p, c->raw_b.p, c->raw_c.p, c->raw_d.p, c->raw_e.p,
+                                                    c->raw_mode.p, c->locr.p, c->vels.p, c->wp.p, c->mode.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    plan_ped_grid(c, n, loc);
+    SFM_CUDA(cudaStreamSynchronize(c->stream));      // host arrays may be released by the caller on return
+    return 0;
+}
+
+int sfm_update_kinematics(sfm_ctx* c, int64_t n, const double* loc, const double* vel) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    if (!loc || !vel) return fail("null state array");
+    SFM_CUDA(cudaMemcpyAsync(c->raw_a.p, loc, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_b.p, vel, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    pack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->raw_a.p, c->raw_b.p, nullptr, nullptr, nullptr, nullptr,
+                                                    c->locr.p, c->vels.p, c->wp.p, c->mode.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->staged = false;
+    c->perm_valid = false;
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_update_targets(sfm_ctx* c, int64_t n, const double* wp3, const double* speed, const uint8_t* mode) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    if (wp3) SFM_CUDA(cudaMemcpyAsync(c->raw_c.p, wp3, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (speed) SFM_CUDA(cudaMemcpyAsync(c->raw_e.p, speed, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    if (mode) SFM_CUDA(cudaMemcpyAsync(c->raw_mode.p, mode, n, cudaMemcpyHostToDevice, c->stream));
+    pack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, nullptr, nullptr, wp3 ? c->raw_c.p : nullptr, nullptr,
+                                                    speed ? c->raw_e.p : nullptr, mode ? c->raw_mode.p : nullptr,
+                                                    c->locr.p, c->vels.p, c->wp.p, c->mode.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_download_state(sfm_ctx* c, int64_t n, double* loc, double* vel) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    unpack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->locr.p, c->vels.p, loc ? c->raw_a.p : nullptr,
+                                                      vel ? c->raw_b.p : nullptr);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    if (loc) SFM_CUDA(cudaMemcpyAsync(loc, c->raw_a.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (vel) SFM_CUDA(cudaMemcpyAsync(vel, c->raw_b.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_set_borders(sfm_ctx* c, int64_t n_sections, const double* center, const double* length, const int64_t* offsets,
+                    const double* points) {
+    SFM_TRY(check_ctx(c));
+    if (n_sections > 0 && !length) return fail("null section_length");
+    return upload_set(c, c->borders, n_sections, center, length, 0.0, nullptr, offsets, points);
+}
+
+int sfm_set_obstacles(sfm_ctx* c, int which, int64_t n_obstacles, const double* centers, const double* velocities,
+                      const int64_t* offsets, const double* points) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (which != SFM_FORCE_STATIC_OBSTACLE && which != SFM_FORCE_DYNAMIC_OBSTACLE) return fail("bad obstacle class");
+    const bool dynamic = which == SFM_FORCE_DYNAMIC_OBSTACLE;
+    const double thr = dynamic ? c->params.dynamic_obs.perception_threshold : c->params.static_obs.perception_threshold;
+    return upload_set(c, dynamic ? c->dyn : c->stat, n_obstacles, centers, nullptr, thr, velocities, offsets, points);
+}
+
+int sfm_force(sfm_ctx* c, int cls, int64_t n, double* out) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (cls < 0 || cls >= SFM_FORCE_COUNT) return fail("bad force class");
+    if (n == 0) return 0;
+    if (!out) return fail("null output");
+    SFM_TRY(ensure_force_buffers(c));
+    if (cls == SFM_FORCE_ACCELERATION || cls == SFM_FORCE_PEDESTRIAN) {
+        if (cls == SFM_FORCE_PEDESTRIAN) SFM_TRY(launch_pairs(c));
+        StepArgs a = step_args(c);
+        a.enable_accel = cls == SFM_FORCE_ACCELERATION;
+        a.enable_ped = cls == SFM_FORCE_PEDESTRIAN;
+        a.update_velocity = 0;
+        a.f_accel = c->f_accel.p;
+        a.f_ped = c->f_ped.p;
+        {
+            SpanGuard g(c, ST_INTEGRATE);
+            k3_integrate<<<cdiv(n, 256), 256, 0, c->stream>>>(a);
+            c->launches += 1;
+            SFM_CUDA(cudaGetLastError());
+        }
+        return download3(c, cls == SFM_FORCE_ACCELERATION ? c->f_accel.p : c->f_ped.p, n, out);
+    }
+    SFM_TRY(launch_segments(c, cls, false, 0));
+    DevBuf<double2>& f = (cls == SFM_FORCE_BORDER) ? c->f_border
+                                                   : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->f_static : c->f_dynamic);
+    SFM_TRY(c->raw_a.ensure(3 * n));
+    expand_xy<<<cdiv(n, 256), 256, 0, c->stream>>>(n, f.p, c->raw_a.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    return download3(c, c->raw_a.p, n, out);
+}
+
+int sfm_enumerate_pairs(sfm_ctx* c, int cls, int64_t capacity, int64_t* triplets, int64_t* count) {
+    SFM_TRY(check_ctx(c));
+    if (cls != SFM_FORCE_BORDER && cls != SFM_FORCE_STATIC_OBSTACLE && cls != SFM_FORCE_DYNAMIC_OBSTACLE)
+        return fail("only the cutoff-limited classes enumerate pairs");
+    if (!count || capacity < 0 || (capacity > 0 && !triplets)) return fail("bad enumeration buffer");
+    *count = 0;
+    if (c->n == 0) return 0;
+    SFM_TRY(c->emit.ensure((size_t)3 * std::max<int64_t>(capacity, 1)));
+    SFM_TRY(c->emit_count.ensure(1));
+    SFM_CUDA(cudaMemsetAsync(c->emit_count.p, 0, sizeof(unsigned long long), c->stream));
+    SFM_TRY(launch_segments(c, cls, true, capacity));
+    unsigned long long total = 0;
+    SFM_CUDA(cudaMemcpyAsync(&total, c->emit_count.p, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    *count = (int64_t)total;
+    const int64_t got = std::min<int64_t>((int64_t)total, capacity);
+    if (got > 0) SFM_CUDA(cudaMemcpy(triplets, c->emit.p, sizeof(long long) * 3 * got, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int sfm_step(sfm_ctx* c, int n_steps, int integrate_positions) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (n_steps < 0) return fail("negative step count");
+    if (c->n == 0) return 0;                       // pedestrian_simulation.py:60 early-out
+    if (c->world > 1 && n_steps > 1) return fail("multi-rank contexts step once per all-gather");
+    for (int s = 0; s < n_steps; ++s) SFM_TRY(step_once(c, true, integrate_positions != 0, false));
+    return 0;
+}
+
+int sfm_tick_host(sfm_ctx* c, int64_t n, const double* loc, const double* vel, double* new_vel, double* new_loc) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    if (!loc || !vel || !new_vel) return fail("null array");
+    SFM_CUDA(cudaMemcpyAsync(c->raw_a.p, loc, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_b.p, vel, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    pack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->raw_a.p, c->raw_b.p, nullptr, nullptr, nullptr, nullptr,
+                                                    c->locr.p, c->vels.p, c->wp.p, c->mode.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->staged = false;
+    c->perm_valid = false;
+    SFM_TRY(step_once(c, true, new_loc != nullptr, false));
+    unpack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->locr.p, c->vels.p, new_loc ? c->raw_a.p : nullptr,
+                                                      c->raw_b.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    if (new_loc)
+        SFM_CUDA(cudaMemcpyAsync(new_loc, c->raw_a.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaMemcpyAsync(new_vel, c->raw_b.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_download_force(sfm_ctx* c, int64_t n, double* out) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    if (!out || !c->f_total.p) return fail("no force available");
+    return download3(c, c->f_total.p, n, out);
+}
+
+int sfm_download_class_force(sfm_ctx* c, int cls, int64_t n, double* out) {
+    // Per-class arrays are produced on demand from the current state (Force.get_force semantics).
+    return sfm_force(c, cls, n, out);
+}
+
+int sfm_gather_buffer(sfm_ctx* c, void** device_ptr, size_t* bytes_per_rank) {
+    SFM_TRY(check_ctx(c));
+    if (!device_ptr || !bytes_per_rank) return fail("null pointer");
+    if (!c->planes.p) return fail("no state uploaded yet");
+    *device_ptr = c->planes.p;
+    *bytes_per_rank = sizeof(float) * NPLANES * (size_t)c->rows_pad;
+    return 0;
+}
+
+int sfm_set_profiling(sfm_ctx* c, int enabled) {
+    SFM_TRY(check_ctx(c));
+    SFM_TRY(drain_spans(c));
+    c->profiling = enabled != 0;
+    return 0;
+}
+
+int sfm_reset_stats(sfm_ctx* c) {
+    SFM_TRY(check_ctx(c));
+    SFM_TRY(drain_spans(c));
+    c->launches = c->steps = c->pair_launches = 0;
+    for (double& m : c->ms) m = 0.0;
+    return 0;
+}
+
+int sfm_get_stats(sfm_ctx* c, sfm_stats* out) {
+    SFM_TRY(check_ctx(c));
+    if (!out) return fail("null pointer");
+    SFM_TRY(drain_spans(c));
+    out->launches = c->launches; out->steps = c->steps; out->pair_launches = c->pair_launches;
+    out->ms_pairs = c->ms[ST_PAIRS]; out->ms_cells = c->ms[ST_CELLS]; out->ms_segments = c->ms[ST_SEGMENTS];
+    out->ms_integrate = c->ms[ST_INTEGRATE];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Shared definitions of the sfm_b200 CUDA translation unit (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sfm_b200.h"
+
+namespace sfm {
+
+// ---- staged float32 planes read by the all-pairs kernel -------------------------------------------------------------
+// Gather buffer layout: [world][NPLANES][rows_pad] float32.  One rank block is what a rank contributes to the per-step
+// all-gather (32 B per pedestrian row).  Planes: position relative to the origin, radius, lambda * velocity.
+constexpr int NPLANES = 8;
+enum Plane { PX = 0, PY = 1, PZ = 2, PR = 3, PVX = 4, PVY = 5, PVZ = 6, PSPARE = 7 };
+constexpr int ROW_ALIGN = 256;              // rows_pad granularity == j-tile length of the pair kernel
+constexpr float PAD_POS = 1.0e15f;          // padded rows sit this far away: exp(-dist/B) underflows to exactly 0
+
+// Parameters of the float32 Moussaid evaluation, pre-folded on the host (see k1_ped_pairs.cuh for the algebra).
+struct PairParams {
+    float lambda;          // lambda_weight (applied when staging velocities)
+    float eps_gamma;       // epsilon * gamma
+    float neg_l2e_over_gamma;   // -log2(e) / gamma
+    float c_nprime;        // (n' * gamma)^2 * log2(e)
+    float c_n;             // (n  * gamma)^2 * log2(e)
+    float log2A;           // log2(A)
+};
+
+// Parameters of the float64 Moussaid evaluation used by the obstacle kernels (reference operation order).
+struct MoussaidD {
+    double lambda, A, gamma, n, n_prime, epsilon, threshold;
+};
+
+// Uniform grid over the centres of a point set (sections or obstacles); cell edge >= the largest cutoff of the set.
+struct CellGrid {
+    double x0, y0, cell, inv_cell;
+    int nx, ny;
+};
+
+// A CSR point set on the device.
+struct SegmentSet {
+    int64_t count = 0;          // sections / obstacles
+    int64_t n_points = 0;
+    double2* center = nullptr;  // [count]
+    double* cutoff = nullptr;   // [count]  per-section length, or the perception threshold replicated
+    double2* velocity = nullptr;// [count]  obstacle velocity (zeros for borders / static)
+    int* offset = nullptr;      // [count + 1]
+    double2* point = nullptr;   // [n_points]
+    CellGrid grid{};
+    int* cell_start = nullptr;  // [nx * ny + 1]
+    int* cell_item = nullptr;   // [count]  set items ordered by (cell, index)
+    int64_t cap_count = 0, cap_points = 0, cap_cells = 0;
+};
+
+}  // namespace sfm

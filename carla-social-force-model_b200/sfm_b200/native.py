@@ -1,0 +1,329 @@
+"""ctypes binding of ``libsfm_b200.so`` (C ABI in ``include/sfm_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  Loading it needs the CUDA runtime but no
+GPU; *using* it needs a B200: ``Context()`` raises ``SfmError`` otherwise -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
+LIB_PATH = os.path.join(HERE, 'libsfm_b200.so')
+
+FORCE_CLASSES = ('acceleration_force', 'pedestrian_force', 'border_force', 'static_obstacle_force',
+                 'dynamic_obstacle_force')                      # pedestrian_simulation.py:37-48 dict order
+ACCELERATION, PEDESTRIAN, BORDER, STATIC_OBSTACLE, DYNAMIC_OBSTACLE = range(5)
+
+# every symbol include/sfm_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
+SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create', 'sfm_destroy', 'sfm_set_stream',
+           'sfm_synchronize', 'sfm_set_params', 'sfm_set_origin', 'sfm_set_partition', 'sfm_upload_state',
+           'sfm_update_kinematics', 'sfm_update_targets', 'sfm_download_state', 'sfm_set_borders', 'sfm_set_obstacles',
+           'sfm_force', 'sfm_enumerate_pairs', 'sfm_step', 'sfm_tick_host', 'sfm_download_force',
+           'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats')
+
+
+class SfmError(RuntimeError):
+    pass
+
+
+class MoussaidParams(C.Structure):
+    _fields_ = [('lambda_weight', C.c_double), ('A', C.c_double), ('gamma', C.c_double), ('n', C.c_double),
+                ('n_prime', C.c_double), ('epsilon', C.c_double), ('perception_threshold', C.c_double)]
+
+
+class Params(C.Structure):
+    _fields_ = [('step_length', C.c_double), ('tau', C.c_double), ('max_speed_factor', C.c_double),
+                ('border_a', C.c_double), ('border_b', C.c_double),
+                ('ped', MoussaidParams), ('static_obs', MoussaidParams), ('dynamic_obs', MoussaidParams),
+                ('use_ped_radius', C.c_int32), ('enable', C.c_int32 * 5)]
+
+
+class Stats(C.Structure):
+    _fields_ = [('launches', C.c_int64), ('steps', C.c_int64), ('ms_pairs', C.c_double), ('ms_cells', C.c_double),
+                ('ms_segments', C.c_double), ('ms_integrate', C.c_double), ('pair_launches', C.c_int64)]
+
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
+              '-shared']
+
+
+def build(force=False, verbose=False):
+    """Compile ``csrc/sfm_api.cu`` into ``libsfm_b200.so`` next to this file (nvcc cross-compiles without a GPU)."""
+    sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cu', '.cuh'))]
+    sources.append(os.path.join(os.path.dirname(os.path.dirname(HERE)), 'include', 'sfm_b200.h'))
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in sources):
+            return LIB_PATH
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH,
+                                                                            os.path.join(CSRC, 'sfm_api.cu')]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise SfmError('nvcc failed:\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once) and declare the prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SfmError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` first; '
+                       'there is no CPU fallback')
+    L = C.CDLL(LIB_PATH)
+    p_ctx, p_d, p_u8, p_i64 = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
+    i64 = C.c_int64
+    sig = {
+        'sfm_abi_version': (C.c_int, []),
+        'sfm_last_error': (C.c_char_p, []),
+        'sfm_device_count': (C.c_int, [C.POINTER(C.c_int)]),
+        'sfm_create': (C.c_int, [C.c_int, C.POINTER(p_ctx)]),
+        'sfm_destroy': (C.c_int, [p_ctx]),
+        'sfm_set_stream': (C.c_int, [p_ctx, C.c_void_p]),
+        'sfm_synchronize': (C.c_int, [p_ctx]),
+        'sfm_set_params': (C.c_int, [p_ctx, C.POINTER(Params)]),
+        'sfm_set_origin': (C.c_int, [p_ctx, C.c_double, C.c_double, C.c_double]),
+        'sfm_set_partition': (C.c_int, [p_ctx, C.c_int, C.c_int, i64]),
+        'sfm_upload_state': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d, p_d, p_u8]),
+        'sfm_update_kinematics': (C.c_int, [p_ctx, i64, p_d, p_d]),
+        'sfm_update_targets': (C.c_int, [p_ctx, i64, p_d, p_d, p_u8]),
+        'sfm_download_state': (C.c_int, [p_ctx, i64, p_d, p_d]),
+        'sfm_set_borders': (C.c_int, [p_ctx, i64, p_d, p_d, p_i64, p_d]),
+        'sfm_set_obstacles': (C.c_int, [p_ctx, C.c_int, i64, p_d, p_d, p_i64, p_d]),
+        'sfm_force': (C.c_int, [p_ctx, C.c_int, i64, p_d]),
+        'sfm_enumerate_pairs': (C.c_int, [p_ctx, C.c_int, i64, p_i64, p_i64]),
+        'sfm_step': (C.c_int, [p_ctx, C.c_int, C.c_int]),
+        'sfm_tick_host': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d]),
+        'sfm_download_force': (C.c_int, [p_ctx, i64, p_d]),
+        'sfm_download_class_force': (C.c_int, [p_ctx, C.c_int, i64, p_d]),
+        'sfm_gather_buffer': (C.c_int, [p_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+        'sfm_set_profiling': (C.c_int, [p_ctx, C.c_int]),
+        'sfm_reset_stats': (C.c_int, [p_ctx]),
+        'sfm_get_stats': (C.c_int, [p_ctx, C.POINTER(Stats)]),
+    }
+    assert set(sig) == set(SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    if L.sfm_abi_version() != 1:
+        raise SfmError('libsfm_b200.so ABI version mismatch; rebuild')
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise SfmError(lib().sfm_last_error().decode(errors='replace'))
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f'expected shape {shape}, got {a.shape}')
+    return a
+
+
+def _ptr(a, ctype=C.c_double):
+    return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+def pack_point_set(rings):
+    """list of (P_k, 2) arrays -> (offsets int64 [K+1], points float64 [sum P_k, 2])  -- the CSR wire format."""
+    sizes = np.fromiter((len(r) for r in rings), dtype=np.int64, count=len(rings))
+    offsets = np.zeros(len(rings) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    if len(rings):
+        points = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, 2) for r in rings]))
+    else:
+        points = np.zeros((0, 2))
+    return offsets, points
+
+
+def moussaid_from_config(section, defaults):
+    """Read one Moussaid section exactly like forces.py:66-72 / :200-206 (missing keys fall back to the code defaults)."""
+    m = MoussaidParams()
+    m.lambda_weight = section.get('lambda', defaults[0])
+    m.A = section.get('A', defaults[1])
+    m.gamma = section.get('gamma', defaults[2])
+    m.n = section.get('n', defaults[3])
+    m.n_prime = section.get('n_prime', defaults[4])
+    m.epsilon = section.get('epsilon', defaults[5])
+    m.perception_threshold = section.get('perception_threshold', defaults[6])
+    return m
+
+
+_MOUSSAID_DEFAULTS = (2.0, 4.5, 0.35, 2.0, 3.0, 0.005, 20)
+
+
+def params_from_config(sfm_config, step_length, enable=None, strict=False):
+    """Translate the parsed sfm_config.toml into ``Params``, reading the keys the reference's code reads.
+
+    Bug-compatible by default: ``max_speed_factor`` (not the shipped ``max_speed_multiplier``)
+    and ``[goal_force].tau`` (not the shipped ``[acceleration_force].tau``) are honoured, both defaulting to the shipped
+    values.  With ``strict=True`` missing mandatory sections raise ``KeyError`` like forces.py:66,134,197,199 do.
+    """
+    p = Params()
+    p.step_length = step_length
+    p.tau = sfm_config.get('goal_force', {}).get('tau', 0.5)
+    p.max_speed_factor = sfm_config.get('max_speed_factor', 1.3)
+    border = sfm_config['border_force'] if strict else sfm_config.get('border_force', {})
+    p.border_a, p.border_b = border.get('a', 3.0), border.get('b', 0.1)
+    get = (lambda k: sfm_config[k]) if strict else (lambda k: sfm_config.get(k, {}))
+    p.ped = moussaid_from_config(get('pedestrian_force'), _MOUSSAID_DEFAULTS)
+    p.static_obs = moussaid_from_config(get('static_obstacle_force'), _MOUSSAID_DEFAULTS)
+    p.dynamic_obs = moussaid_from_config(get('dynamic_obstacle_force'), _MOUSSAID_DEFAULTS)
+    p.use_ped_radius = int(bool(sfm_config.get('use_ped_radius', False)))
+    switches = sfm_config.get('forces', {}) if enable is None else enable
+    for k, name in enumerate(FORCE_CLASSES):
+        p.enable[k] = int(bool(switches.get(name, False)))
+    return p
+
+
+class Context:
+    """One device context = one rank's pedestrians + the replicated point sets."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._lib = lib()
+        _check(self._lib.sfm_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+        self.n = 0
+
+    def close(self):
+        if self._h:
+            self._lib.sfm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration
+    def set_params(self, params):
+        self.params = params
+        _check(self._lib.sfm_set_params(self._h, C.byref(params)))
+
+    def set_stream(self, cuda_stream):
+        _check(self._lib.sfm_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def set_origin(self, ox, oy, oz=0.0):
+        _check(self._lib.sfm_set_origin(self._h, ox, oy, oz))
+
+    def set_partition(self, world, rank, rows_pad):
+        _check(self._lib.sfm_set_partition(self._h, world, rank, rows_pad))
+
+    def synchronize(self):
+        _check(self._lib.sfm_synchronize(self._h))
+
+    # -- state
+    def upload_state(self, loc, vel, next_waypoint, radius, target_speed, mode):
+        n = len(loc)
+        loc, vel, wp = _f64(loc, (n, 3)), _f64(vel, (n, 3)), _f64(next_waypoint, (n, 3))
+        radius, speed = _f64(radius, (n,)), _f64(target_speed, (n,))
+        mode = np.ascontiguousarray(mode, dtype=np.uint8)
+        _check(self._lib.sfm_upload_state(self._h, n, _ptr(loc), _ptr(vel), _ptr(wp), _ptr(radius), _ptr(speed),
+                                          _ptr(mode, C.c_uint8)))
+        self.n = n
+
+    def update_kinematics(self, loc, vel):
+        loc, vel = _f64(loc, (self.n, 3)), _f64(vel, (self.n, 3))
+        _check(self._lib.sfm_update_kinematics(self._h, self.n, _ptr(loc), _ptr(vel)))
+
+    def update_targets(self, next_waypoint=None, target_speed=None, mode=None):
+        wp = _f64(next_waypoint, (self.n, 3)) if next_waypoint is not None else None
+        sp = _f64(target_speed, (self.n,)) if target_speed is not None else None
+        md = np.ascontiguousarray(mode, dtype=np.uint8) if mode is not None else None
+        _check(self._lib.sfm_update_targets(self._h, self.n, _ptr(wp), _ptr(sp), _ptr(md, C.c_uint8)))
+
+    def download_state(self, loc=None, vel=None):
+        loc = np.empty((self.n, 3)) if loc is None else loc
+        vel = np.empty((self.n, 3)) if vel is None else vel
+        _check(self._lib.sfm_download_state(self._h, self.n, _ptr(loc), _ptr(vel)))
+        return loc, vel
+
+    # -- point sets
+    def set_borders(self, borders, section_center, section_length):
+        n = len(borders)
+        if n == 0:
+            _check(self._lib.sfm_set_borders(self._h, 0, None, None, None, None))
+            return
+        offsets, points = pack_point_set(borders)
+        center = _f64(np.asarray(section_center, dtype=np.float64).reshape(-1, 2), (n, 2))
+        length = _f64(np.asarray(section_length, dtype=np.float64).reshape(-1), (n,))
+        _check(self._lib.sfm_set_borders(self._h, n, _ptr(center), _ptr(length), _ptr(offsets, C.c_int64), _ptr(points)))
+
+    def set_obstacles(self, which, centers, rings, velocities=None):
+        n = len(rings)
+        if n == 0:
+            _check(self._lib.sfm_set_obstacles(self._h, which, 0, None, None, None, None))
+            return
+        offsets, points = pack_point_set(rings)
+        centers = _f64(np.asarray(centers, dtype=np.float64).reshape(-1, 2), (n, 2))
+        vel = _f64(np.asarray(velocities, dtype=np.float64).reshape(-1, 2), (n, 2)) if velocities is not None else None
+        _check(self._lib.sfm_set_obstacles(self._h, which, n, _ptr(centers), _ptr(vel), _ptr(offsets, C.c_int64),
+                                           _ptr(points)))
+
+    def set_obstacles_csr(self, which, centers, velocities, offsets, points):
+        n = len(centers)
+        centers, points = _f64(centers, (n, 2)), _f64(points)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        vel = _f64(velocities, (n, 2)) if velocities is not None else None
+        _check(self._lib.sfm_set_obstacles(self._h, which, n, _ptr(centers), _ptr(vel), _ptr(offsets, C.c_int64),
+                                           _ptr(points)))
+
+    # -- forces and stepping
+    def force(self, force_class, out=None):
+        out = np.empty((self.n, 3)) if out is None else out
+        _check(self._lib.sfm_force(self._h, force_class, self.n, _ptr(out)))
+        return out
+
+    def enumerate_pairs(self, force_class, capacity=1 << 22):
+        buf = np.empty((capacity, 3), dtype=np.int64)
+        count = C.c_int64()
+        _check(self._lib.sfm_enumerate_pairs(self._h, force_class, capacity, _ptr(buf, C.c_int64), C.byref(count)))
+        if count.value > capacity:
+            return self.enumerate_pairs(force_class, int(count.value))
+        t = buf[:count.value]
+        return t[np.lexsort((t[:, 1], t[:, 0]))]
+
+    def step(self, n_steps=1, integrate_positions=True):
+        _check(self._lib.sfm_step(self._h, int(n_steps), int(bool(integrate_positions))))
+
+    def tick_host(self, loc, vel, new_vel, new_loc=None):
+        """Host-buffer tick; arrays must be C-contiguous float64 [n, 3] (pinned memory makes the copies asynchronous)."""
+        _check(self._lib.sfm_tick_host(self._h, self.n, _ptr(loc), _ptr(vel), _ptr(new_vel), _ptr(new_loc)))
+
+    def download_force(self, out=None):
+        out = np.empty((self.n, 3)) if out is None else out
+        _check(self._lib.sfm_download_force(self._h, self.n, _ptr(out)))
+        return out
+
+    # -- multi-GPU plumbing and accounting
+    def gather_buffer(self):
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        _check(self._lib.sfm_gather_buffer(self._h, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def set_profiling(self, enabled):
+        _check(self._lib.sfm_set_profiling(self._h, int(bool(enabled))))
+
+    def reset_stats(self):
+        _check(self._lib.sfm_reset_stats(self._h))
+
+    def stats(self):
+        s = Stats()
+        _check(self._lib.sfm_get_stats(self._h, C.byref(s)))
+        return {name: getattr(s, name) for name, _ in Stats._fields_}

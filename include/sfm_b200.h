@@ -1,0 +1,141 @@
+/*
+ * sfm_b200 -- C ABI of the B200-native Social Force Model step.
+ *
+ * The reference (felixlutz/carla-social-force-model) is pure Python and has no FFI of its own: its seam is the Python
+ * object protocol of forces.py / pedestrian_state.py / pedestrian_simulation.py.  This header is the boundary a
+ * maintainer binds from that Python layer (ctypes); every entry point names the reference code it
+ * replaces.  Plain pointers and sizes only.  All calls on one context must come from one host thread; all device work
+ * is enqueued on the context's stream (sfm_set_stream), and calls that return host data synchronise that stream.
+ *
+ * Return value: 0 on success, non-zero on failure; sfm_last_error() returns the message of the calling thread's last
+ * failure.  There is no CPU fallback: sfm_create fails when no sm_100 device is present.
+ *
+ * Host arrays are C-contiguous float64 unless stated otherwise, exactly the dtypes of the reference's PedState
+ * (pedestrian_state.py:17-19).
+ */
+#ifndef SFM_B200_H
+#define SFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_ABI_VERSION 1
+
+typedef struct sfm_ctx sfm_ctx;
+
+/* Force classes in the order pedestrian_simulation.py:37-48 inserts them into its dict (= summation order, :81). */
+enum sfm_force_class {
+    SFM_FORCE_ACCELERATION = 0,     /* forces.py:35-53   AccelerationForce */
+    SFM_FORCE_PEDESTRIAN = 1,       /* forces.py:56-117  PedestrianForce   */
+    SFM_FORCE_BORDER = 2,           /* forces.py:120-179 BorderForce       */
+    SFM_FORCE_STATIC_OBSTACLE = 3,  /* forces.py:182-283 ObstacleForce(dynamic=False) */
+    SFM_FORCE_DYNAMIC_OBSTACLE = 4, /* forces.py:182-283 ObstacleForce(dynamic=True)  */
+    SFM_FORCE_COUNT = 5
+};
+
+/* Pedestrian modes, ped_mode_manager.py:4-9.  Modes 2 and 3 switch the border force off (forces.py:176-177). */
+enum sfm_ped_mode {
+    SFM_IDLE = 0, SFM_WALKING_SIDEWALK = 1, SFM_CROSSING_ROAD = 2, SFM_ROAD_TO_SIDEWALK = 3, SFM_CHECKING_TRAFFIC = 4
+};
+
+/* One Moussaid parameter set: [pedestrian_force] forces.py:66-72, [static_/dynamic_obstacle_force] forces.py:196-206. */
+typedef struct {
+    double lambda_weight, A, gamma, n, n_prime, epsilon;
+    double perception_threshold;          /* obstacle sets only (forces.py:206); ignored for pedestrians */
+} sfm_moussaid_params;
+
+/* Everything sfm_config.toml + the scenario's step_length configure on the hot path. */
+typedef struct {
+    double step_length;                   /* pedestrian_simulation.py:120 */
+    double tau;                           /* forces.py:44  sfm_config['goal_force']['tau'], default 0.5 */
+    double max_speed_factor;              /* pedestrian_state.py:15,72-73, default 1.3 */
+    double border_a, border_b;            /* forces.py:135-136 */
+    sfm_moussaid_params ped, static_obs, dynamic_obs;
+    int32_t use_ped_radius;               /* forces.py:18 */
+    int32_t enable[SFM_FORCE_COUNT];      /* [forces] switches, pedestrian_simulation.py:33-48 */
+} sfm_params;
+
+/* Device-time accounting of the kernels launched since the last sfm_reset_stats (CUDA events on the launch stream). */
+typedef struct {
+    int64_t launches;                     /* kernels of this library launched (all classes) */
+    int64_t steps;                        /* fused steps executed */
+    double ms_pairs;                      /* K1 all-pairs pedestrian force (incl. its partial-sum layout) */
+    double ms_cells;                      /* K2a binning / cell-list builds */
+    double ms_segments;                   /* K2b/K2c border + obstacle kernels */
+    double ms_integrate;                  /* K3 acceleration + sum + clamp + Euler + restaging */
+    int64_t pair_launches;                /* number of K1 launches inside ms_pairs */
+} sfm_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------- */
+int sfm_abi_version(void);
+const char* sfm_last_error(void);
+int sfm_device_count(int* count);
+/* Creates a context on CUDA device `device`; fails unless its compute capability is 10.x. */
+int sfm_create(int device, sfm_ctx** out);
+int sfm_destroy(sfm_ctx* ctx);
+/* `cuda_stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL selects the context's own stream. */
+int sfm_set_stream(sfm_ctx* ctx, void* cuda_stream);
+int sfm_synchronize(sfm_ctx* ctx);
+
+/* ---- configuration: replaces Force.__init__ (forces.py:14-18,41-44,62-72,127-136,189-206) ----------------------- */
+int sfm_set_params(sfm_ctx* ctx, const sfm_params* params);
+/* Origin subtracted (in float64) before positions are rounded to the float32 staging copies the pair kernel reads. */
+int sfm_set_origin(sfm_ctx* ctx, double ox, double oy, double oz);
+/* Row partition for multi-GPU runs: this context owns one of `world` equal blocks of `rows_pad` staged rows
+ * (rows_pad a multiple of 256, >= the largest per-rank row count).  Default: world 1, rows_pad chosen by upload. */
+int sfm_set_partition(sfm_ctx* ctx, int world, int rank, int64_t rows_pad);
+
+/* ---- pedestrian state: replaces the PedState.state columns (pedestrian_state.py:17-19,45-77) -------------------- */
+/* Uploads this context's rows.  loc, vel, next_waypoint: [n][3]; radius, target_speed: [n]; mode: uint8 [n]. */
+int sfm_upload_state(sfm_ctx* ctx, int64_t n, const double* loc, const double* vel, const double* next_waypoint,
+                     const double* radius, const double* target_speed, const uint8_t* mode);
+/* Per-tick refresh of loc/vel from the simulator (PedState.update_state, pedestrian_state.py:79-81, batched). */
+int sfm_update_kinematics(sfm_ctx* ctx, int64_t n, const double* loc, const double* vel);
+/* Per-tick refresh of waypoint / target speed / mode (pedestrian_state.py:83-95).  NULL pointers leave a column as is. */
+int sfm_update_targets(sfm_ctx* ctx, int64_t n, const double* next_waypoint, const double* target_speed,
+                       const uint8_t* mode);
+int sfm_download_state(sfm_ctx* ctx, int64_t n, double* loc, double* vel);
+
+/* ---- point sets (CSR): replaces BorderForce.__init__ (forces.py:127-132) and ObstacleForce.update_obstacles /
+ *      update_obstacle_velocities (forces.py:285-291).  offsets: int64 [count+1] into points [offsets[count]][2]. ---- */
+int sfm_set_borders(sfm_ctx* ctx, int64_t n_sections, const double* section_center, const double* section_length,
+                    const int64_t* offsets, const double* points);
+/* which: SFM_FORCE_STATIC_OBSTACLE or SFM_FORCE_DYNAMIC_OBSTACLE.  velocities may be NULL (zeros, forces.py:212-213). */
+int sfm_set_obstacles(sfm_ctx* ctx, int which, int64_t n_obstacles, const double* centers, const double* velocities,
+                      const int64_t* offsets, const double* points);
+
+/* ---- forces: replaces Force.get_force (forces.py:28-32) for each class --------------------------------------- */
+/* Evaluates one force class on the current device state and copies it to out[n][3]. */
+int sfm_force(sfm_ctx* ctx, int force_class, int64_t n, double* out);
+/* Neighbour enumeration of a cutoff-limited class (border / static / dynamic): writes up to `capacity` triplets
+ * (pedestrian row, section-or-obstacle index, nearest point index) in unspecified order and the total count. */
+int sfm_enumerate_pairs(sfm_ctx* ctx, int force_class, int64_t capacity, int64_t* triplets, int64_t* count);
+
+/* ---- the fused tick: replaces PedestrianSimulation.tick's force sum and calculate_new_velocities
+ *      (pedestrian_simulation.py:81-83,117-124; stateutils.py:18-23) plus, optionally, the position update the
+ *      reference leaves to the CARLA server (run_simulation.py:77-87): x+ = x + dt * v+. --------------------------- */
+int sfm_step(sfm_ctx* ctx, int n_steps, int integrate_positions);
+/* Host-buffer tick: upload loc/vel, one step, download the new velocities (and positions when new_loc != NULL). */
+int sfm_tick_host(sfm_ctx* ctx, int64_t n, const double* loc, const double* vel, double* new_vel, double* new_loc);
+/* Total force / one class's force of the most recent step, [n][3]. */
+int sfm_download_force(sfm_ctx* ctx, int64_t n, double* out);
+int sfm_download_class_force(sfm_ctx* ctx, int force_class, int64_t n, double* out);
+
+/* ---- multi-GPU plumbing: the staged (pos, lambda*vel, radius) planes every rank all-gathers once per step -------- */
+/* Device pointer of the gather buffer [world][8][rows_pad] float32, and the size of one rank's block in bytes.
+ * After each sfm_step the caller all-gathers block `rank` into every rank's buffer (NCCL, in place). */
+int sfm_gather_buffer(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_rank);
+
+/* ---- accounting -------------------------------------------------------------------------------------------------- */
+int sfm_set_profiling(sfm_ctx* ctx, int enabled);
+int sfm_reset_stats(sfm_ctx* ctx);
+int sfm_get_stats(sfm_ctx* ctx, sfm_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFM_B200_H */

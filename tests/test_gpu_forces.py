@@ -1,0 +1,103 @@
+"""GPU parity of every force class against the float64 oracle and the reference's golden vectors (through the C ABI).
+
+Tolerances: the float32 all-pairs kernel must meet BASELINE.json's 1e-4 relative / 1e-5 m/s^2 absolute per component;
+the float64 cell-list kernels and the integrate kernel are held to 1e-11 (they follow numpy's operation order).
+"""
+import numpy as np
+import pytest
+
+from oracle import sfm_oracle as O
+from sfm_b200 import native, synth
+from tests import golden_util as G
+from tests.gpu_util import assert_forces_close, make_context
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_classes(w, cfg, step=0, rows=None):
+    scene = G.scene_for(w, cfg)
+    dyn, dyn_vel = G.dyn_for(w, step)
+    return O.forces_by_class(scene, w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode, dyn, dyn_vel,
+                             rows=rows)
+
+
+@pytest.mark.parametrize('use_radius', [False, True])
+def test_cfg1_all_classes(sfm_config, use_radius):
+    cfg = dict(sfm_config, use_ped_radius=use_radius)
+    w = synth.make_config(1)
+    ctx = make_context(w, cfg)
+    want = _oracle_classes(w, cfg)
+    _, risk = O.pedestrian_force(w.loc, w.vel, w.radius, G.scene_for(w, cfg).ped, use_radius, return_risk=True)
+    for k, name in enumerate(native.FORCE_CLASSES):
+        got = ctx.force(k)
+        if name == 'pedestrian_force':
+            assert_forces_close(got, want[name], risk=risk, name=name)
+        else:
+            np.testing.assert_allclose(got, want[name], rtol=1e-11, atol=1e-11, err_msg=name)
+
+
+@pytest.mark.parametrize('use_radius,z', [(False, 0), (True, 0), (False, 1), (True, 1)])
+def test_cfg2_against_reference_golden(sfm_config, use_radius, z):
+    """N = 4096, all five classes, vs arrays the imported reference produced (tests/golden)."""
+    cfg = dict(sfm_config, use_ped_radius=use_radius)
+    w = synth.make_config(2, z_spread=0.2 if z else 0.0)
+    g = G.load(f'cfg2_forces_r{int(use_radius)}_z{z}.npz', w)
+    ctx = make_context(w, cfg)
+    rows = np.arange(0, w.n, 4)
+    _, risk = O.pedestrian_force(w.loc, w.vel, w.radius, G.scene_for(w, cfg).ped, use_radius, rows=rows,
+                                 return_risk=True)
+    for k, name in enumerate(native.FORCE_CLASSES):
+        got, want = ctx.force(k), g[f'F_{name}']
+        if name == 'pedestrian_force':
+            assert np.isfinite(got).all()                   # unsampled rows are only checked for finiteness
+            assert_forces_close(got[rows], want[rows], risk=risk, name=name)
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11, err_msg=name)
+
+
+@pytest.mark.parametrize('cls,name', [(native.BORDER, 'border'), (native.STATIC_OBSTACLE, 'static'),
+                                      (native.DYNAMIC_OBSTACLE, 'dynamic')])
+def test_neighbour_enumeration_bit_exact(sfm_config, cls, name):
+    """The cell-list kernels must visit exactly the reference's (pedestrian, item, nearest point) triplets."""
+    w = synth.make_config(2)
+    ctx = make_context(w, sfm_config)
+    scene = G.scene_for(w, sfm_config)
+    if cls == native.BORDER:
+        _, want = O.border_force(w.loc, w.radius, w.mode, scene.borders, scene.section_center, scene.section_length,
+                                 scene.border, False, return_pairs=True)
+    elif cls == native.STATIC_OBSTACLE:
+        _, want = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in w.static_obstacles],
+                                   [r for _, r in w.static_obstacles], None, scene.static, False, return_pairs=True)
+    else:
+        dyn, dyn_vel = G.dyn_for(w, 0)
+        _, want = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in dyn], [r for _, r in dyn], dyn_vel,
+                                   scene.dynamic, False, return_pairs=True)
+    got = ctx.enumerate_pairs(cls)
+    assert len(want) > 1000
+    np.testing.assert_array_equal(got, want)
+
+
+def test_force_switches_and_empty_sets(sfm_config):
+    w = synth.make_config(1)
+    w.borders, w.static_obstacles, w.veh_center = [], [], None
+    ctx = make_context(w, sfm_config)
+    for cls in (native.BORDER, native.STATIC_OBSTACLE, native.DYNAMIC_OBSTACLE):
+        assert not ctx.force(cls).any()                      # forces.py:140-141, :209-210
+
+
+def test_coincident_and_degenerate_pairs(sfm_config):
+    """Zero distance, equal velocities, |D| = 0 -- same values as numpy wherever numpy is finite."""
+    loc = np.array([[0, 0, 0], [0, 0, 0], [2, 0, 0], [2, 0, 0.5], [5, 5, 0], [7, 5, 0]], dtype=np.float64)
+    vel = np.array([[1, 0, 0], [0, 1, 0], [0.5, 0, 0], [0.5, 0, 0], [0, 0, 0], [0.5, 0, 0]], dtype=np.float64)
+    n = len(loc)
+    w = synth.make_config(1)
+    w.loc, w.vel = loc, vel
+    w.next_waypoint, w.radius = np.zeros((n, 3)), np.full(n, 0.25)
+    w.target_speed, w.mode = np.full(n, 1.3), np.ones(n, dtype=np.uint8)
+    ctx = make_context(w, sfm_config)
+    with np.errstate(all='ignore'):
+        want = O.pedestrian_force(loc, vel, w.radius, G.scene_for(w, sfm_config).ped, False)
+    got = ctx.force(native.PEDESTRIAN)
+    finite = np.isfinite(want).all(axis=1)
+    assert finite.sum() >= 4
+    assert_forces_close(got[finite], want[finite], name='degenerate')
