@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the per-tick Social Force Model step (BASELINE.json metric) -- prints ONE JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4|cfg5] [--n N]
+
+A step = one tick of the hot path over the whole synthetic crowd: all enabled force classes (all-pairs pedestrian force,
+border / static-obstacle / dynamic-obstacle cell-list forces, acceleration force) + force sum + speed clamp + Euler
+position/velocity update, followed on N > 1 ranks by the all-gather of the staged rows.
+
+  value     pair-interactions/s of the whole job = N (N - 1) K / t, t = sum of the K per-step device times (CUDA events
+            on the launch stream, max over ranks), state resident in HBM.  agent-steps/s = value / (N - 1) is reported
+            beside it (`agent_steps_per_s`).
+  e2e       the same metric through the host-buffer tick (sfm_tick_host): every step copies this rank's positions and
+            velocities from pinned host memory to the device and the new positions / velocities back.
+  roofline  the all-pairs kernel (K1) against the FP32 issue peak, plus the HBM-bound integrate kernel (K3) in `roofline_hbm`.
+  workload  1 GPU: BASELINE.json configs[2] (N = 65,536 + 1M border points + 50k obstacle points).  N GPUs: the
+            constant-pair-work weak ladder anchored there, N_G = 65,536 sqrt(G) (sets scaled by area).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import tomllib
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'carla-social-force-model_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np                     # noqa: E402
+
+K1_INSTR_PER_PAIR = 58                 # FP32-pipe instructions per ordered pair (81 FLOP, 5 MUFU)
+# K3 algorithmic bytes per agent-step: read loc+r 32, vel+speed 32, waypoint 16, pair force 12, three
+# cell-list forces 3 x 16; write loc 32, vel 32, float32 staging planes 28, total force 24
+K3_BYTES_PER_AGENT = 32 + 32 + 16 + 12 + 48 + 32 + 32 + 28 + 24
+SMS, LANES = 148, 128
+
+
+def load_config():
+    with open(os.path.join(PKG, 'config', 'sfm_config.toml'), 'rb') as f:
+        return tomllib.load(f)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return {'hbm_gbs': 6650.0, 'sm_max_mhz': 1965.0}, 'fallback'
+
+
+def build_workload(args, world):
+    from sfm_b200 import synth
+    if args.workload == 'cfg3':
+        n = args.n or int(round(65536 * math.sqrt(world) / 256.0)) * 256
+        w = synth.make_config(3, n=n)
+        name = 'cfg3: N=65,536 + 1,050,000 border points (5,000 sections) + 50,000 static-obstacle points' if n == 65536 \
+            else f'cfg3 weak ladder: N={n} (65,536*sqrt({world})), border/obstacle sets scaled by area'
+    elif args.workload == 'cfg4':
+        w = synth.make_config(4, n=args.n)
+        name = f'cfg4: N={w.n} x {len(w.veh_center)} vehicles (68-point rings, cutoff 50 m)'
+    elif args.workload == 'cfg5':
+        w = synth.make_config(5, n=args.n)
+        name = f'cfg5: N={w.n} synthetic city-scale crowd'
+    else:
+        raise SystemExit(f'unknown workload {args.workload}')
+    return w, name
+
+
+class ClockSampler:
+    """nvidia-smi samples (SM clock, throttle reasons) taken DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.file = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(device), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.file,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        clocks, reasons, mx, power = [], set(), None, []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.file.read().splitlines():
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                clocks.append(float(parts[0]))
+                mx = float(parts[1])
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.file.name)
+        if clocks:
+            busy = sorted(clocks)[len(clocks) // 2:]            # upper half = samples under load
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(clocks),
+                       power_w_max=max(power))
+        return out
+
+
+def run_reference(args, world, rank):
+    """The reference arm: the path's CPU implementation on this box's host cores (oracle port, all cores)."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    cfg = load_config()
+    w, name = build_workload(args, world)
+    cores = os.cpu_count() or 1
+    rows_per_core = args.cpu_rows_per_core
+    for _ in range(args.warmup):
+        cpu_baseline.time_sample(w, cfg, rows_per_core=max(1, rows_per_core // 8), cores=cores)
+    times, rows = [], 0
+    for k in range(args.steps):
+        r = cpu_baseline.time_sample(w, cfg, rows_per_core=rows_per_core, cores=cores, seed=k)
+        times.append(r['seconds'])
+        rows = r['rows']
+    sec = float(np.mean(times))
+    value = rows * (w.n - 1) / sec
+    sample = f'{rows} of {w.n} rows per step (full tick for those rows against all {w.n} pedestrians), {cores} forked workers'
+    line = {
+        'impl': 'reference', 'metric': 'pair_interactions_per_s', 'value': value, 'unit': 'pair-interactions/s',
+        'agent_steps_per_s': value / (w.n - 1), 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': sec * 1e3 * w.n / rows, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': name, 'n_pedestrians': w.n, 'note': 'ms_per_step extrapolated from the row sample'},
+        'cpu_baseline': {'value': value, 'unit': 'pair-interactions/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'pair-interactions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, world, rank, local_rank):
+    import torch
+    from sfm_b200 import engine as eng
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dist = torch.distributed
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    cfg = load_config()
+    w, name = build_workload(args, world)
+    n = w.n
+    e = eng.Engine(cfg, w.step_length, device=local_rank)
+    e.load(w)
+    ctx = e.ctx
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')       # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        e.step(1, True)
+    barrier()
+    ctx.reset_stats()
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)                                             # L2 flush, outside the timed span
+        starts[k].record(stream)
+        e.step(1, True)
+        stops[k].record(stream)
+    barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if sampler else None
+    ms_total = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+    stats = ctx.stats()
+    ctx.set_profiling(False)
+    t = torch.tensor([ms_total, stats['ms_pairs'], stats['ms_integrate'], stats['ms_segments'] + stats['ms_cells']],
+                     dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_pairs, ms_integrate, ms_sets = t.tolist()
+    ms_per_step = ms_total / args.steps
+    value = n * (n - 1) / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through host buffers --------------------------------------------------------------------------
+    rows = e.hi - e.lo
+    pin = lambda: torch.empty((max(rows, 1), 3), dtype=torch.float64).pin_memory()      # noqa: E731
+    h_loc, h_vel, h_nloc, h_nvel = pin(), pin(), pin(), pin()
+    loc0, vel0 = e.local_state()
+    h_loc.numpy()[:rows], h_vel.numpy()[:rows] = loc0, vel0
+    a_loc, a_vel, a_nloc, a_nvel = (x.numpy()[:rows] for x in (h_loc, h_vel, h_nloc, h_nvel))
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = 0.0
+    for k in range(args.warmup + e2e_steps):
+        flush.fill_(k & 0xff)
+        barrier()
+        t0 = time.perf_counter()
+        e.tick_host(a_loc, a_vel, a_nvel, a_nloc)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if k >= args.warmup:
+            e2e_ms += dt * 1e3
+        a_loc[...] = a_nloc                       # next tick's input = this tick's output (the co-simulation loop)
+        a_vel[...] = a_nvel
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = t.item() / e2e_steps
+    e2e_value = n * (n - 1) / (e2e_ms_per_step * 1e-3)
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        sm_max_hz = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
+        fp32_peak = SMS * LANES * sm_max_hz / 1e12                      # T FP32-pipe lane-instructions / s
+        k1_ms = ms_pairs / max(stats['pair_launches'], 1)
+        k1_pairs = (e.hi - e.lo) * (n - 1)                              # ordered pairs this rank's launch evaluates
+        k1_rate = k1_pairs / (k1_ms * 1e-3)
+        achieved = k1_rate * K1_INSTR_PER_PAIR / 1e12
+        traffic = None
+        prof = os.path.join(ROOT, 'profiles', 'k1_ncu_summary.json')
+        if os.path.exists(prof):
+            with open(prof) as f:
+                traffic = json.load(f).get('dram_bytes_per_launch')
+        k3_ms = ms_integrate / max(stats['steps'], 1)
+        k3_gbs = rows * K3_BYTES_PER_AGENT / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else None
+        line = {
+            'metric': 'pair_interactions_per_s', 'value': value, 'unit': 'pair-interactions/s',
+            'agent_steps_per_s': value / (n - 1), 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 pair forces / f64 state, cell-list forces and integration', 'data': 'synthetic',
+            'config': {'workload': name, 'n_pedestrians': n, 'rows_per_gpu': rows, 'step_length': w.step_length,
+                       'forces': 'all five on', 'l2': 'flushed between timed steps (256 MiB fill, outside the timed spans)',
+                       'partition': f'row blocks over {world} rank(s), all-gather of 32 B/pedestrian per step'},
+            'e2e': {'value': e2e_value, 'unit': 'pair-interactions/s', 'ms_per_step': e2e_ms_per_step,
+                    'h2d_bytes_per_step': int(rows * 48), 'd2h_bytes_per_step': int(rows * 48), 'steps': e2e_steps,
+                    'api': 'sfm_tick_host (pinned host loc/vel in, new loc/vel out)'},
+            'gpu_launches': int(stats['launches']),
+            'kernel_ms_per_step': {'pairs_k1': ms_pairs / args.steps, 'segments_cells_k2': ms_sets / args.steps,
+                                   'integrate_k3': ms_integrate / args.steps},
+            'roofline': {'bound': 'fp32_issue', 'achieved': achieved, 'peak': fp32_peak,
+                         'unit': 'T FP32-pipe instr/s', 'frac': achieved / fp32_peak, 'traffic': traffic,
+                         'kernel': 'k1_ped_pairs', 'ms_per_launch': k1_ms, 'pairs_per_s': k1_rate,
+                         'algorithmic': f'{K1_INSTR_PER_PAIR} FP32-pipe instr (81 FLOP, 5 MUFU) per ordered pair',
+                         'peak_source': f'148 SM x 128 lanes x sm_max_mhz ({peak_kind} MEASURED_PEAKS.json clock); '
+                                        'FFMA microbenchmark on this pool: 33.2 T/s (profiles/microbench)'},
+            'roofline_hbm': {'bound': 'hbm', 'kernel': 'k3_integrate', 'achieved': k3_gbs,
+                             'peak': float(peaks.get('hbm_gbs', 6650.0)), 'unit': 'GB/s',
+                             'frac': (k3_gbs / float(peaks.get('hbm_gbs', 6650.0))) if k3_gbs else None,
+                             'ms_per_launch': k3_ms, 'peak_kind': peak_kind},
+            'clocks': clocks, 'wall_s_timed_loop': wall,
+        }
+        if clocks and clocks.get('sm_mhz'):
+            line['roofline']['frac_at_sampled_clock'] = achieved / (SMS * LANES * clocks['sm_mhz'] * 1e6 / 1e12)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_baseline
+            cores = os.cpu_count() or 1
+            r = cpu_baseline.time_sample(w, cfg, rows_per_core=args.cpu_rows_per_core, cores=cores)
+            line['cpu_baseline'] = {
+                'value': r['pairs_per_s'], 'unit': 'pair-interactions/s', 'cores': r['cores'], 'kind': 'port',
+                'agent_steps_per_s': r['agent_steps_per_s'], 'seconds': r['seconds'],
+                'sample': f"one full tick for {r['rows']} of {n} rows (each against all {n} pedestrians + the border/"
+                          f"obstacle sets), float64 numpy oracle, {r['cores']} forked workers"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg4', 'cfg5'])
+    ap.add_argument('--n', type=int, default=None, help='override the pedestrian count')
+    ap.add_argument('--cpu-rows-per-core', type=int, default=48)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ and args.impl == 'ours':
+        import socket                     # launched without torchrun: start one rank per GPU ourselves
+        with socket.socket() as sk:
+            sk.bind(('127.0.0.1', 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args, args.gpus, rank)
+    else:
+        run_ours(args, world, rank, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -800,6 +800,14 @@ int sfm_gather_buffer(sfm_ctx* c, void** device_ptr, size_t* bytes_per_rank) {
     return 0;
 }
 
+int sfm_stage(sfm_ctx* c) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (!c->planes.p) return fail("no state uploaded yet");
+    if (!c->staged) SFM_TRY(launch_stage(c));
+    return 0;
+}
+
 int sfm_set_profiling(sfm_ctx* c, int enabled) {
     SFM_TRY(check_ctx(c));
     SFM_TRY(drain_spans(c));

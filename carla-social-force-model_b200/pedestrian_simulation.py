@@ -1,0 +1,166 @@
+"""Per-tick Social Force Model driver with the call surface of the reference's ``pedestrian_simulation.py``.
+
+``tick`` keeps the reference sequence (pedestrian_simulation.py:57-83): mode bookkeeping -> gap acceptance -> recording
+-> force sum -> new velocities.  The arithmetic (all enabled forces, their sum in dict order, the Euler velocity update
+and the speed clamp) is one fused device pass (``sfm_step`` with ``integrate_positions = 0``); as in the reference,
+positions are left to the simulator that consumes the velocities (run_simulation.py:77-87).
+"""
+import numpy as np
+
+import forces
+from check_traffic import check_traffic
+from ped_mode_manager import PedMode
+from pedestrian_state import PedState
+from sfm_b200 import native
+from sfm_b200.session import get_session
+from stateutils import cap_velocity
+
+_NATIVE_ORDER = {name: k for k, name in enumerate(native.FORCE_CLASSES)}
+
+
+class PedestrianSimulation:
+    def __init__(self, borders, border_section_info, obstacles, sfm_config, step_length, record_states=True):
+        self.sfm_config = sfm_config
+        self.borders = borders
+        self.section_info = border_section_info
+        self.static_obstacles = obstacles
+        self.dyn_obs_ids = []
+        self.dyn_obstacles = []
+        self.dyn_obs_heading = []
+        self.dyn_obs_vel = []
+        self.dyn_obs_extent = []
+        self.all_dyn_obs_states = {}
+        self.record_states = record_states          # False skips the O(N) per-tick snapshots (unbounded memory)
+        self.peds = PedState(sfm_config)
+        self.step_length = step_length
+        self.forces = self.init_forces()
+        self.new_velocities = None
+
+    def init_forces(self):
+        """Ordered dict of the enabled force objects (pedestrian_simulation.py:32-55); order = summation order."""
+        switches = self.sfm_config['forces']
+        out = {}
+        if switches.get('acceleration_force', False):
+            out['acceleration_force'] = forces.AccelerationForce(self.step_length, self.sfm_config)
+        if switches.get('pedestrian_force', False):
+            out['pedestrian_force'] = forces.PedestrianForce(self.step_length, self.sfm_config)
+        if switches.get('border_force', False):
+            out['border_force'] = forces.BorderForce(self.step_length, self.sfm_config, self.borders, self.section_info)
+        if switches.get('static_obstacle_force', False):
+            out['static_obstacle_force'] = forces.ObstacleForce(self.step_length, self.sfm_config)
+            if self.static_obstacles:
+                out['static_obstacle_force'].update_obstacles(self.static_obstacles)
+        if switches.get('dynamic_obstacle_force', False):
+            out['dynamic_obstacle_force'] = forces.ObstacleForce(self.step_length, self.sfm_config, True)
+        for dead in ('ped_repulsive_force', 'space_repulsive_force'):
+            if switches.get(dead, False):     # the reference would raise AttributeError here
+                raise AttributeError(f"module 'forces' has no class for '{dead}' (dead switch in the reference too)")
+        return out
+
+    # ---- the tick ---------------------------------------------------------------------------------------------------
+    def tick(self, sim_time):
+        """Do one step in the simulation."""
+        if self.peds.state is None or self.peds.size() == 0:
+            return
+        self.peds.apply_current_mode()
+        for mode in self.peds.state['mode']:
+            if hasattr(mode, 'tick'):
+                mode.tick(sim_time)
+        codes = self.peds.mode_codes()
+        for row in np.nonzero(codes == PedMode.CHECKING_TRAFFIC)[0]:
+            ped = self.peds.state[row]
+            ready = True
+            if self.dyn_obstacles:
+                ready = check_traffic(ped, self.dyn_obstacles, self.dyn_obs_vel, self.dyn_obs_extent)
+            if ready:
+                ped['mode'].set_mode(PedMode.CROSSING_ROAD)
+        if self.record_states:
+            self.peds.record_current_state(sim_time)
+            if self.dyn_obstacles:
+                self.record_dyn_obstacle_states(sim_time)
+        if self._fusable():
+            self._fused_velocities()
+        else:                                  # hand-composed force dicts: per-class device forces, summed on the host
+            self.calculate_new_velocities(sum(f.get_force(self.peds) for f in self.forces.values()))
+
+    def _fusable(self):
+        names = list(self.forces)
+        return all(n in _NATIVE_ORDER and isinstance(f, forces.Force) and f.force_class == _NATIVE_ORDER[n]
+                   for n, f in self.forces.items()) and names == sorted(names, key=_NATIVE_ORDER.get)
+
+    def _fused_velocities(self):
+        session = get_session()
+        params = native.params_from_config(self.sfm_config, self.step_length,
+                                           enable={name: name in self.forces for name in native.FORCE_CLASSES})
+        session.ctx.set_params(params)
+        session.params_key = None                  # the per-class objects re-bind their (all-enabled) view on next use
+        for f in self.forces.values():
+            empty_set = (isinstance(f, forces.ObstacleForce) and (f.obstacle_locs is None or f.obstacle_locs.size == 0)) \
+                or (isinstance(f, forces.BorderForce) and len(f.borders) == 0)
+            if isinstance(f, forces.ObstacleForce) and not empty_set and f.obstacle_velocities is None:
+                f.obstacle_velocities = np.zeros((len(f.obstacle_locs), 2))
+            if empty_set:
+                self._clear_set(session, f.force_class)
+            else:
+                f._bind(session)
+        session.upload_peds(self.peds)
+        session.ctx.step(1, integrate_positions=False)
+        _, vel = session.ctx.download_state()
+        self.new_velocities = self.peds.state[['id', 'vel']]     # a view: writes through to state['vel']
+        self.new_velocities['vel'] = vel
+
+    @staticmethod
+    def _clear_set(session, which):
+        if session.owner[which] is not None or session.set_version[which] != 'empty':
+            if which == native.BORDER:
+                session.ctx.set_borders([], None, None)
+            else:
+                session.ctx.set_obstacles(which, None, [])
+            session.owner[which], session.set_version[which] = None, 'empty'
+
+    def calculate_new_velocities(self, force):
+        """New desired velocities from a force array (pedestrian_simulation.py:117-124)."""
+        desired_velocity = cap_velocity(self.peds.vel() + self.step_length * force, self.peds.max_speed())
+        self.new_velocities = self.peds.state[['id', 'vel']]
+        self.new_velocities['vel'] = desired_velocity
+
+    def get_new_velocities(self):
+        return self.new_velocities
+
+    # ---- bookkeeping (pedestrian_simulation.py:85-115,126-143) ------------------------------------------------------
+    def close(self):
+        pass
+
+    def get_arrived_peds(self, distance_threshold):
+        if self.peds.state is None:
+            return []
+        to_goal = self.peds.next_waypoint()[:, :2] - self.peds.loc()[:, :2]
+        return self.peds.name()[np.linalg.norm(to_goal, axis=-1) < distance_threshold]
+
+    def spawn_pedestrian(self, initial_ped_state):
+        self.peds.add_pedestrian(initial_ped_state)
+
+    def destroy_pedestrian(self, ped_name):
+        self.peds.remove_pedestrian(ped_name)
+
+    def update_ped_info(self, walker_id, location, velocity):
+        self.peds.update_state(walker_id, location, velocity)
+
+    def update_dynamic_obstacles(self, dynamic_obstacles):
+        (self.dyn_obs_ids, obstacle_pos, self.dyn_obs_heading, self.dyn_obs_vel, self.dyn_obs_extent,
+         borders) = dynamic_obstacles
+        self.dyn_obstacles = list(zip(obstacle_pos, borders))
+        if 'dynamic_obstacle_force' in self.forces and self.dyn_obstacles:
+            self.forces['dynamic_obstacle_force'].update_obstacles(self.dyn_obstacles)
+            self.forces['dynamic_obstacle_force'].update_obstacle_velocities(self.dyn_obs_vel)
+
+    def record_dyn_obstacle_states(self, sim_time):
+        centres = [c for c, _ in self.dyn_obstacles]
+        veh_state = np.empty(len(self.dyn_obs_ids), dtype=[('id', 'i4'), ('loc', 'f8', (2,)), ('heading', 'f8'),
+                                                           ('vel', 'f8', (2,)), ('extent', 'f8', (2,))])
+        veh_state['id'], veh_state['loc'], veh_state['heading'] = self.dyn_obs_ids, centres, self.dyn_obs_heading
+        veh_state['vel'], veh_state['extent'] = self.dyn_obs_vel, self.dyn_obs_extent
+        self.all_dyn_obs_states[sim_time] = veh_state
+
+    def get_states(self):
+        return self.peds.get_all_states()

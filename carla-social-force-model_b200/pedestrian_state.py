@@ -1,0 +1,118 @@
+"""Pedestrian state table with the call surface of the reference's ``pedestrian_state.py``.
+
+``PedState.state`` is the same structured numpy array the reference keeps (dtype pedestrian_state.py:17-19) because
+its callers index it directly (pedestrian_simulation.py:64,67,123; check_traffic.py:18-21; run_simulation.py via
+``update_state``).  It is the *host mirror*: the device keeps its own SoA copy (float64 master + float32 staging, see
+DESIGN.md) that ``device_columns()`` feeds.
+"""
+import numpy as np
+
+import stateutils
+from ped_mode_manager import PedMode
+
+
+class PedState:
+    def __init__(self, sfm_config):
+        self.max_speed_factor = sfm_config.get('max_speed_factor', 1.3)      # sic: not `max_speed_multiplier`
+        self.ped_state_dtype = [('name', 'U8'), ('id', 'i4'), ('loc', 'f8', (3,)), ('vel', 'f8', (3,)),
+                                ('next_waypoint', 'f8', (3,)), ('mode', 'O'), ('radius', 'f8'), ('target_speed', 'f8')]
+        self.state = None
+        self.all_states = {}            # sim_time -> snapshot, filled by record_current_state
+
+    # ---- rows in / out (pedestrian_state.py:26-43) ------------------------------------------------------------------
+    def add_pedestrian(self, initial_ped_state):
+        row = np.array([tuple(initial_ped_state)], dtype=self.ped_state_dtype)
+        self.state = row if self.state is None else np.concatenate((self.state, row))
+
+    def add_pedestrians(self, names, ids, loc, vel, next_waypoint, modes, radius, target_speed):
+        """Bulk insert (not in the reference): one allocation instead of one ``np.append`` per pedestrian."""
+        block = np.zeros(len(ids), dtype=self.ped_state_dtype)
+        block['name'], block['id'] = names, ids
+        block['loc'], block['vel'], block['next_waypoint'] = loc, vel, next_waypoint
+        block['radius'], block['target_speed'] = radius, target_speed
+        block['mode'] = list(modes)
+        self.state = block if self.state is None else np.concatenate((self.state, block))
+
+    def remove_pedestrian(self, ped_name):
+        self.state = self.state[self.state['name'] != ped_name]
+
+    # ---- column accessors (pedestrian_state.py:45-77) ---------------------------------------------------------------
+    def size(self):
+        return self.state.shape[0]
+
+    def name(self):
+        return self.state['name']
+
+    def walker_id(self):
+        return self.state['id']
+
+    def loc(self):
+        return self.state['loc']
+
+    def vel(self):
+        return self.state['vel']
+
+    def next_waypoint(self):
+        return self.state['next_waypoint']
+
+    def mode(self):
+        return self.state['mode']
+
+    def radius(self):
+        return self.state['radius']
+
+    def target_speed(self):
+        return self.state['target_speed']
+
+    def max_speed(self):
+        return self.target_speed() * self.max_speed_factor
+
+    def speeds(self):
+        return stateutils.speeds(self.state)
+
+    def desired_directions(self):
+        return stateutils.desired_directions(self.state)
+
+    # ---- per-tick updates (pedestrian_state.py:79-95) ---------------------------------------------------------------
+    def update_state(self, walker_id, location, velocity):
+        rows = self.state['id'] == walker_id
+        self.state['loc'][rows] = location
+        self.state['vel'][rows] = velocity
+
+    def update_states(self, walker_ids, locations, velocities):
+        """Batched ``update_state`` (not in the reference): one id->row lookup instead of an O(N) mask per walker."""
+        order = np.argsort(self.state['id'], kind='stable')
+        rows = order[np.searchsorted(self.state['id'], walker_ids, sorter=order)]
+        self.state['loc'][rows] = locations
+        self.state['vel'][rows] = velocities
+
+    def update_next_waypoint(self, ped_name, next_waypoint_tuple):
+        next_waypoint, crossing_road = next_waypoint_tuple
+        rows = self.state['name'] == ped_name
+        self.state['next_waypoint'][rows] = next_waypoint
+        wanted = PedMode.CROSSING_ROAD if crossing_road else PedMode.WALKING_SIDEWALK
+        self.state['mode'][rows][0].set_mode(wanted)
+
+    def apply_current_mode(self):
+        self.state['target_speed'] = [getattr(m, 'target_speed', s)
+                                      for m, s in zip(self.state['mode'], self.state['target_speed'])]
+
+    def mode_codes(self):
+        """``uint8`` mode per pedestrian; the ``mode`` column may hold ``PedModeManager`` objects or plain ``PedMode`` ints."""
+        return np.fromiter((int(getattr(m, 'current_mode', m)) for m in self.state['mode']), dtype=np.uint8,
+                           count=self.size())
+
+    def device_columns(self):
+        """Contiguous float64 / uint8 columns in the order ``sfm_upload_state`` takes them."""
+        s = self.state
+        return (np.ascontiguousarray(s['loc']), np.ascontiguousarray(s['vel']), np.ascontiguousarray(s['next_waypoint']),
+                np.ascontiguousarray(s['radius']), np.ascontiguousarray(s['target_speed']), self.mode_codes())
+
+    # ---- recording (pedestrian_state.py:100-107) --------------------------------------------------------------------
+    def record_current_state(self, sim_time):
+        snapshot = self.state.copy()
+        snapshot['mode'] = [getattr(m, 'current_mode', m) for m in snapshot['mode']]
+        self.all_states[sim_time] = snapshot
+
+    def get_all_states(self):
+        return self.all_states

@@ -1,0 +1,128 @@
+"""Device-resident crowd engine: one process per GPU, pedestrians row-partitioned across the ranks of one box.
+
+Every force on pedestrian i needs i's own row plus read-only global data (all pedestrians' positions / velocities /
+radii, the replicated border and obstacle sets), so rows shard with exactly one exchange per step: an all-gather of
+each rank's staged block (32 B per pedestrian) through ``torch.distributed`` (NCCL over NVLink; gloo in the CPU
+tests).  torch is plumbing only -- streams, the process group and a tensor view of the library's gather buffer; all
+arithmetic runs in ``libsfm_b200.so``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import native
+
+ROW_ALIGN = 256
+
+
+def partition_rows(n, world):
+    """Contiguous row blocks, sizes differing by at most one: returns int64 [world + 1] boundaries."""
+    base, extra = divmod(int(n), int(world))
+    sizes = np.full(world, base, dtype=np.int64)
+    sizes[:extra] += 1
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    np.cumsum(sizes, out=bounds[1:])
+    return bounds
+
+
+def padded_rows(bounds):
+    """Staged rows per rank block: the largest block rounded up to the pair kernel's tile (256 rows)."""
+    largest = int(np.max(np.diff(bounds))) if len(bounds) > 1 else 0
+    return max(ROW_ALIGN, (largest + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN)
+
+
+class _DeviceView:
+    """Minimal ``__cuda_array_interface__`` holder so torch can alias memory owned by the library."""
+
+    def __init__(self, ptr, n_float32):
+        self.__cuda_array_interface__ = {'shape': (n_float32,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+
+
+class Engine:
+    def __init__(self, sfm_config, step_length, device=None, group=None, use_torch_stream=True):
+        import torch                                   # plumbing only
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise native.SfmError('no CUDA device: the Social Force Model step has no CPU fallback')
+        self.dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) \
+            else None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.ctx = native.Context(self.device)
+        self.sfm_config, self.step_length = sfm_config, step_length
+        self.ctx.set_params(native.params_from_config(sfm_config, step_length))
+        if use_torch_stream:
+            self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.n_global = 0
+        self.bounds = None
+        self._gather = None
+
+    # ---- set-up ---------------------------------------------------------------------------------------------------
+    def load(self, w):
+        """Take a ``synth.Workload`` (or anything with the same attributes): this rank keeps its row block."""
+        self.n_global = w.n
+        self.bounds = partition_rows(w.n, self.world)
+        lo, hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        if self.world > 1:
+            self.ctx.set_partition(self.world, self.rank, padded_rows(self.bounds))
+        self.ctx.upload_state(w.loc[lo:hi], w.vel[lo:hi], w.next_waypoint[lo:hi], w.radius[lo:hi],
+                              w.target_speed[lo:hi], w.mode[lo:hi])
+        self.lo, self.hi = lo, hi
+        if len(w.borders):
+            self.ctx.set_borders(w.borders, w.section_center, w.section_length)
+        if len(w.static_obstacles):
+            self.ctx.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles],
+                                   [r for _, r in w.static_obstacles])
+        self.set_vehicles(w.vehicles_at(0))
+        self.ctx.stage()
+        self._bind_gather()
+        self.exchange()
+
+    def set_vehicles(self, dyn_tuple):
+        """The 6-tuple of pedestrian_simulation.py:108-115 (ids, centres, headings, velocities, extents, rings)."""
+        if dyn_tuple is not None:
+            self.ctx.set_obstacles(native.DYNAMIC_OBSTACLE, dyn_tuple[1], dyn_tuple[5], dyn_tuple[3])
+
+    def _bind_gather(self):
+        if self.world == 1:
+            return
+        ptr, per_rank = self.ctx.gather_buffer()
+        view = _DeviceView(ptr, per_rank // 4 * self.world)
+        self._gather = self.torch.as_tensor(view, device=f'cuda:{self.device}')
+        self._per_rank = per_rank // 4
+
+    def exchange(self):
+        """All-gather every rank's staged block (in place: block r of the buffer is rank r's contribution)."""
+        if self.world == 1:
+            return
+        mine = self._gather[self.rank * self._per_rank:(self.rank + 1) * self._per_rank]
+        self.dist.all_gather_into_tensor(self._gather, mine, group=self.group)
+
+    # ---- stepping -------------------------------------------------------------------------------------------------
+    def step(self, n_steps=1, integrate_positions=True):
+        if self.world == 1:
+            self.ctx.step(n_steps, integrate_positions)
+            return
+        for _ in range(n_steps):
+            self.ctx.step(1, integrate_positions)
+            self.exchange()
+
+    def tick_host(self, loc, vel, new_vel, new_loc=None):
+        """One tick with host buffers for this rank's rows (H2D, kernels, D2H inside the call)."""
+        if self.world == 1:
+            self.ctx.tick_host(loc, vel, new_vel, new_loc)
+            return
+        self.ctx.update_kinematics(loc, vel)        # refresh -> restage -> exchange -> step, so every rank sees the
+        self.ctx.stage()                            # other ranks' refreshed rows
+        self.exchange()
+        self.ctx.step(1, new_loc is not None)
+        self.ctx.download_state(new_loc if new_loc is not None else np.empty_like(new_vel), new_vel)
+        self.exchange()
+
+    def local_state(self):
+        return self.ctx.download_state()
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)

@@ -24,7 +24,7 @@ SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create'
            'sfm_synchronize', 'sfm_set_params', 'sfm_set_origin', 'sfm_set_partition', 'sfm_upload_state',
            'sfm_update_kinematics', 'sfm_update_targets', 'sfm_download_state', 'sfm_set_borders', 'sfm_set_obstacles',
            'sfm_force', 'sfm_enumerate_pairs', 'sfm_step', 'sfm_tick_host', 'sfm_download_force',
-           'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats')
+           'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_stage', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats')
 
 
 class SfmError(RuntimeError):
@@ -108,6 +108,7 @@ def lib():
         'sfm_download_force': (C.c_int, [p_ctx, i64, p_d]),
         'sfm_download_class_force': (C.c_int, [p_ctx, C.c_int, i64, p_d]),
         'sfm_gather_buffer': (C.c_int, [p_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+        'sfm_stage': (C.c_int, [p_ctx]),
         'sfm_set_profiling': (C.c_int, [p_ctx, C.c_int]),
         'sfm_reset_stats': (C.c_int, [p_ctx]),
         'sfm_get_stats': (C.c_int, [p_ctx, C.POINTER(Stats)]),
@@ -316,6 +317,9 @@ class Context:
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         _check(self._lib.sfm_gather_buffer(self._h, C.byref(ptr), C.byref(nbytes)))
         return ptr.value, nbytes.value
+
+    def stage(self):
+        _check(self._lib.sfm_stage(self._h))
 
     def set_profiling(self, enabled):
         _check(self._lib.sfm_set_profiling(self._h, int(bool(enabled))))

@@ -129,6 +129,9 @@ int sfm_download_class_force(sfm_ctx* ctx, int force_class, int64_t n, double* o
 /* Device pointer of the gather buffer [world][8][rows_pad] float32, and the size of one rank's block in bytes.
  * After each sfm_step the caller all-gathers block `rank` into every rank's buffer (NCCL, in place). */
 int sfm_gather_buffer(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_rank);
+/* Makes this rank's block of the gather buffer reflect the current master state (after an upload or refresh), so the
+ * first all-gather can run before the first step. */
+int sfm_stage(sfm_ctx* ctx);
 
 /* ---- accounting -------------------------------------------------------------------------------------------------- */
 int sfm_set_profiling(sfm_ctx* ctx, int enabled);
