@@ -273,6 +273,21 @@ __device__ __forceinline__ double2 segment_force(const SegArgs& a, double px, do
     }
 }
 
+// np.argmin(np.linalg.norm(loc - points, axis=-1)) with numpy's arithmetic (rare tie path of the scan below).
+__device__ __noinline__ int exact_argmin(const double2* __restrict__ point, int o0, int o1, double px, double py) {
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int best_q = o0;
+    for (int q = o0; q < o1; ++q) {
+        const double2 P = point[q];
+        const double d = norm2_np(__dsub_rn(px, P.x), __dsub_rn(py, P.y));
+        if (d < best) {
+            best = d;
+            best_q = q;
+        }
+    }
+    return best_q;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
     __shared__ double2 sp[K2_CHUNK];
@@ -326,7 +341,12 @@ __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
                 const bool pass = active && (norm2_np(__dsub_rn(px, cen.x), __dsub_rn(py, cen.y)) < cut);
                 const bool warp_pass = __any_sync(0xffffffffu, pass);
                 const int o0 = a.offset[s], o1 = a.offset[s + 1];
-                double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+                // Nearest point = np.argmin over the *rounded square roots* (forces.py:154, :228), first index on ties.
+                // The scan tracks the smallest squared distance m1 (first index q1, strict <) and the runner-up m2;
+                // sqrt is monotone, so q1 is numpy's answer unless another point's d2 lies within rounding distance
+                // of m1 -- then (rare) the section is rescanned with numpy's exact arithmetic.
+                const double INF = __longlong_as_double(0x7ff0000000000000LL);
+                double m1 = INF, m2 = INF;
                 int best_q = o0;
                 for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
                     const int m = min(K2_CHUNK, o1 - c0);
@@ -334,21 +354,19 @@ __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
                     for (int q = tid; q < m; q += K2_THREADS) sp[q] = a.point[c0 + q];
                     __syncthreads();
                     if (warp_pass) {
+#pragma unroll 4
                         for (int q = 0; q < m; ++q) {
                             const double2 P = sp[q];
                             const double dx = __dsub_rn(px, P.x), dy = __dsub_rn(py, P.y);
                             const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                            if (d2 < best) {
-                                // np.argmin runs on the rounded square roots: a smaller d2 whose sqrt rounds to the
-                                // same double is a tie and keeps the earlier index (forces.py:154, :228)
-                                if (d2 < best * 0.99999999999999 || __dsqrt_rn(d2) < __dsqrt_rn(best)) {
-                                    best = d2;
-                                    best_q = c0 + q;
-                                }
-                            }
+                            const bool lt1 = d2 < m1, lt2 = d2 < m2;
+                            m2 = lt1 ? m1 : (lt2 ? d2 : m2);
+                            m1 = lt1 ? d2 : m1;
+                            best_q = lt1 ? (c0 + q) : best_q;
                         }
                     }
                 }
+                if (pass && m2 <= m1 * 1.00000000000001) best_q = exact_argmin(a.point, o0, o1, px, py);
                 if (pass) {
                     const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
                                                           KIND ? a.velocity[s] : make_double2(0.0, 0.0));

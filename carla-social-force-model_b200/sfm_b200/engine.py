@@ -53,8 +53,11 @@ class Engine:
         self.ctx = native.Context(self.device)
         self.sfm_config, self.step_length = sfm_config, step_length
         self.ctx.set_params(native.params_from_config(sfm_config, step_length))
-        if use_torch_stream:
-            self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # A dedicated (non-default) torch stream carries both the library's kernels and the NCCL all-gather, so the
+        # two are ordered without host synchronisation; CUDA events recorded on it time the whole step.
+        self.stream = torch.cuda.Stream(self.device) if use_torch_stream else None
+        if self.stream is not None:
+            self.ctx.set_stream(self.stream.cuda_stream)
         self.n_global = 0
         self.bounds = None
         self._gather = None
@@ -98,7 +101,8 @@ class Engine:
         if self.world == 1:
             return
         mine = self._gather[self.rank * self._per_rank:(self.rank + 1) * self._per_rank]
-        self.dist.all_gather_into_tensor(self._gather, mine, group=self.group)
+        with self.torch.cuda.stream(self.stream):
+            self.dist.all_gather_into_tensor(self._gather, mine, group=self.group)
 
     # ---- stepping -------------------------------------------------------------------------------------------------
     def step(self, n_steps=1, integrate_positions=True):
