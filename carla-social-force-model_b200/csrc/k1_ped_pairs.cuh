@@ -22,7 +22,7 @@
 // that TMA bulk copies (cp.async.bulk + mbarrier, two stages) bring into shared memory; every lane reads the same j
 // (LDS.128 broadcast of 4 consecutive j per plane) and keeps its rows' partial force in registers.  grid.y splits the
 // j range so the grid is many waves deep on 148 SMs; the per-split partial sums are written once (no atomics) and
-// reduced in a fixed order by K3, which makes the result deterministic for a given launch geometry.
+// reduced in a fixed order by k1_reduce_fixup, which makes the result deterministic for a given launch geometry.
 #pragma once
 
 #include "sfm_common.cuh"
@@ -184,6 +184,169 @@ __device__ __forceinline__ void tile_pairs(const float (*__restrict__ tl)[K1_TJ]
     }
 }
 
+// ---- packed float32x2 fast path (Blackwell FFMA2 / FMUL2 / FADD2) --------------------------------------------------
+// The kernel is bound by instruction issue, and sm_100 can retire two FP32 operations per lane per issued instruction
+// when they are packed in a 64-bit register pair.  One packed value holds the same quantity for two consecutive j
+// (an LDS.128 of a staged plane yields two such pairs for free); MUFU and the few compare/select steps stay scalar on
+// the halves.  This path carries NO zero guards: a degenerate pair (|d| = 0, |D| = 0, d_xy = 0) produces a NaN that
+// poisons the row's partial sum, and k1_reduce_fixup recomputes exactly those rows with the guarded scalar code above.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 neg2(f32x2 a) { return a ^ 0x8000000080000000ULL; }
+__device__ __forceinline__ f32x2 rsqrt2(f32x2 a) {
+    float lo, hi;
+    unpack2(a, lo, hi);
+    return pack2(rsqrt_approx(lo), rsqrt_approx(hi));
+}
+__device__ __forceinline__ f32x2 ex2_2(f32x2 a) {
+    float lo, hi;
+    unpack2(a, lo, hi);
+    return pack2(ex2_approx(lo), ex2_approx(hi));
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+
+// octant bookkeeping of atan2 on one half: p = atan(min/max) in [0, pi/4] -> angle of (x, y) in (-pi, pi]
+__device__ __forceinline__ float octant_fix(float p, float ax, float ay, float x, float y) {
+    if (ay > ax) p = 1.57079632679489662f - p;
+    if (x < 0.0f) p = 3.14159265358979324f - p;
+    return copysignf(p, y);
+}
+
+struct PackedConst {
+    f32x2 eps_gamma_neg, k_exp, log2A, c_nprime_neg, c_n_neg;
+    f32x2 a7, a6, a5, a4, a3, a2, a1, a0;
+};
+
+__device__ __forceinline__ PackedConst make_packed_const(const PairParams& pp) {
+    PackedConst c;
+    c.eps_gamma_neg = splat2(-pp.eps_gamma);
+    c.k_exp = splat2(pp.neg_l2e_over_gamma);
+    c.log2A = splat2(pp.log2A);
+    c.c_nprime_neg = splat2(-pp.c_nprime);
+    c.c_n_neg = splat2(-pp.c_n);
+    c.a7 = splat2(-4.693274875e-03f);
+    c.a6 = splat2(2.425239913e-02f);
+    c.a5 = splat2(-5.948638773e-02f);
+    c.a4 = splat2(9.914292465e-02f);
+    c.a3 = splat2(-1.401948078e-01f);
+    c.a2 = splat2(1.996972388e-01f);
+    c.a1 = splat2(-3.333199075e-01f);
+    c.a0 = splat2(9.999999010e-01f);
+    return c;
+}
+
+struct PackedAcc {
+    f32x2 ax, bx, ay, az;     // sum a*Dx, sum b*Dy, sum (a*Dy + b*Dx), sum a*Dz   (-F = (ax - bx, ay, az))
+};
+
+// Two ordered pairs (i <- j0) and (i <- j1) at once.
+template <bool RADIUS>
+__device__ __forceinline__ void pair_force2(const f32x2 xi, const f32x2 yi, const f32x2 zi, const f32x2 ri,
+                                            const f32x2 vxi, const f32x2 vyi, const f32x2 vzi, const f32x2 xj,
+                                            const f32x2 yj, const f32x2 zj, const f32x2 rj, const f32x2 vxj,
+                                            const f32x2 vyj, const f32x2 vzj, const PackedConst& c, PackedAcc& acc) {
+    const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi), dz = sub2(zj, zi);
+    const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const f32x2 rinv = rsqrt2(d2);
+    const f32x2 dist = mul2(d2, rinv);
+    const f32x2 wx = sub2(vxi, vxj), wy = sub2(vyi, vyj), wz = sub2(vzi, vzj);
+    const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy), Dz = fma2(dz, rinv, wz);
+    const f32x2 D2 = fma2(Dz, Dz, fma2(Dy, Dy, mul2(Dx, Dx)));
+    const f32x2 Dinv = rsqrt2(D2);
+    const f32x2 Dn = mul2(D2, Dinv);
+    const f32x2 cross = fma2(wx, dy, neg2(mul2(wy, dx)));
+    const f32x2 dot = fma2(Dx, dx, mul2(Dy, dy));
+    // atan2(cross, dot): scalar octant reduction on the halves, packed polynomial
+    float cl, ch, tl, th;
+    unpack2(cross, cl, ch);
+    unpack2(dot, tl, th);
+    const float axl = fabsf(tl), ayl = fabsf(cl), axh = fabsf(th), ayh = fabsf(ch);
+    const f32x2 mn = pack2(fminf(axl, ayl), fminf(axh, ayh));
+    const f32x2 mxr = pack2(rcp_approx(fmaxf(axl, ayl)), rcp_approx(fmaxf(axh, ayh)));
+    const f32x2 q = mul2(mn, mxr);
+    const f32x2 s = mul2(q, q);
+    f32x2 p = fma2(c.a7, s, c.a6);
+    p = fma2(p, s, c.a5);
+    p = fma2(p, s, c.a4);
+    p = fma2(p, s, c.a3);
+    p = fma2(p, s, c.a2);
+    p = fma2(p, s, c.a1);
+    p = fma2(p, s, c.a0);
+    p = mul2(p, q);
+    float pl, ph;
+    unpack2(p, pl, ph);
+    const f32x2 theta = pack2(octant_fix(pl, axl, ayl, tl, cl), octant_fix(ph, axh, ayh, th, ch));
+    const f32x2 thp = fma2(c.eps_gamma_neg, Dn, theta);
+    const f32x2 u = mul2(Dn, thp);
+    const f32x2 u2 = mul2(u, u);
+    f32x2 dl = dist;
+    if (RADIUS) dl = sub2(sub2(dist, ri), rj);
+    const f32x2 y = fma2(mul2(dl, Dinv), c.k_exp, c.log2A);
+    const f32x2 e1 = ex2_2(fma2(c.c_nprime_neg, u2, y));
+    const f32x2 e2 = ex2_2(fma2(c.c_n_neg, u2, y));
+    const f32x2 a = mul2(e1, Dinv);
+    // b carries sign(theta'): e2 * Dinv >= 0, so OR-ing theta's sign bits in is copysign (NaNs stay NaNs)
+    const f32x2 b = mul2(e2, Dinv) | (thp & 0x8000000080000000ULL);
+    acc.ax = fma2(a, Dx, acc.ax);
+    acc.bx = fma2(b, Dy, acc.bx);
+    acc.ay = fma2(a, Dy, acc.ay);
+    acc.ay = fma2(b, Dx, acc.ay);
+    acc.az = fma2(a, Dz, acc.az);
+}
+
+template <int IR, bool RADIUS>
+__device__ __forceinline__ void tile_pairs_packed(const float (*__restrict__ tl)[K1_TJ], const f32x2 (&xi)[IR],
+                                                  const f32x2 (&yi)[IR], const f32x2 (&zi)[IR], const f32x2 (&ri)[IR],
+                                                  const f32x2 (&vxi)[IR], const f32x2 (&vyi)[IR],
+                                                  const f32x2 (&vzi)[IR], const PackedConst& c, PackedAcc (&acc)[IR]) {
+#pragma unroll 1
+    for (int j = 0; j < K1_TJ; j += 4) {
+        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tl[PX][j]);
+        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&tl[PY][j]);
+        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&tl[PZ][j]);
+        ulonglong2 R = make_ulonglong2(0ull, 0ull);
+        if (RADIUS) R = *reinterpret_cast<const ulonglong2*>(&tl[PR][j]);
+        const ulonglong2 VX = *reinterpret_cast<const ulonglong2*>(&tl[PVX][j]);
+        const ulonglong2 VY = *reinterpret_cast<const ulonglong2*>(&tl[PVY][j]);
+        const ulonglong2 VZ = *reinterpret_cast<const ulonglong2*>(&tl[PVZ][j]);
+#pragma unroll
+        for (int r = 0; r < IR; ++r) {
+            pair_force2<RADIUS>(xi[r], yi[r], zi[r], ri[r], vxi[r], vyi[r], vzi[r], X.x, Y.x, Z.x, R.x, VX.x, VY.x, VZ.x,
+                                c, acc[r]);
+            pair_force2<RADIUS>(xi[r], yi[r], zi[r], ri[r], vxi[r], vyi[r], vzi[r], X.y, Y.y, Z.y, R.y, VX.y, VY.y, VZ.y,
+                                c, acc[r]);
+        }
+    }
+}
+
 // planes:      [world][NPLANES][rows_pad] staged rows of all ranks (after the all-gather)
 // own_block:   index of the rank block whose rows this launch computes forces for
 // partial:     [gridDim.y][partial_stride] float4, (-> K3 sums over the splits)
@@ -237,6 +400,16 @@ __global__ void __launch_bounds__(K1_THREADS) k1_ped_pairs(const float* __restri
         vzi[r] = own[(size_t)PVZ * rows_pad + row];
         acc[r].gx = acc[r].gy = acc[r].gz = 0.0f;
     }
+    // packed duplicates of the row data and the packed accumulators of the fast path
+    const PackedConst pc = make_packed_const(pp);
+    f32x2 xi2[IR], yi2[IR], zi2[IR], ri2[IR], vxi2[IR], vyi2[IR], vzi2[IR];
+    PackedAcc acc2[IR];
+#pragma unroll
+    for (int r = 0; r < IR; ++r) {
+        xi2[r] = splat2(xi[r]); yi2[r] = splat2(yi[r]); zi2[r] = splat2(zi[r]); ri2[r] = splat2(ri[r]);
+        vxi2[r] = splat2(vxi[r]); vyi2[r] = splat2(vyi[r]); vzi2[r] = splat2(vzi[r]);
+        acc2[r].ax = acc2[r].bx = acc2[r].ay = acc2[r].az = 0ull;
+    }
     // the CTA's rows are K1_TJ-aligned blocks, so they meet the j range in rows_per_cta / K1_TJ diagonal tiles
     const int diag_first = (own_block * rows_pad + i_base) / K1_TJ;
     const int diag_last = (own_block * rows_pad + i_base + rows_per_cta - 1) / K1_TJ;
@@ -252,16 +425,96 @@ __global__ void __launch_bounds__(K1_THREADS) k1_ped_pairs(const float* __restri
                 self_j[r] = own_block * rows_pad + i_base + r * K1_THREADS + tid - t * K1_TJ;   // slot inside this tile
             tile_pairs<IR, RADIUS, true>(tile[stage], xi, yi, zi, ri, vxi, vyi, vzi, self_j, pp, acc);
         } else {
-#pragma unroll
-            for (int r = 0; r < IR; ++r) self_j[r] = -1;
-            tile_pairs<IR, RADIUS, false>(tile[stage], xi, yi, zi, ri, vxi, vyi, vzi, self_j, pp, acc);
+            tile_pairs_packed<IR, RADIUS>(tile[stage], xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, acc2);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int r = 0; r < IR; ++r) {
         const int row = i_base + r * K1_THREADS + tid;
-        partial[(size_t)split * partial_stride + row] = make_float4(-acc[r].gx, -acc[r].gy, -acc[r].gz, 0.0f);
+        float axl, axh, bxl, bxh, ayl, ayh, azl, azh;
+        unpack2(acc2[r].ax, axl, axh);
+        unpack2(acc2[r].bx, bxl, bxh);
+        unpack2(acc2[r].ay, ayl, ayh);
+        unpack2(acc2[r].az, azl, azh);
+        const float gx = acc[r].gx + ((axl + axh) - (bxl + bxh));
+        const float gy = acc[r].gy + (ayl + ayh);
+        const float gz = acc[r].gz + (azl + azh);
+        partial[(size_t)split * partial_stride + row] = make_float4(-gx, -gy, -gz, 0.0f);
+    }
+}
+
+// K1r -- reduce the per-split partial sums (fixed order, float64) and repair poisoned rows.
+//
+// A row whose sum is not finite met a degenerate pair in the unguarded packed path (or genuinely overflows); its warp
+// recomputes it cooperatively with the guarded scalar pair_force, lanes striding over every staged slot.  Healthy crowds
+// never take that branch, so the kernel is a plain N x nsplit x 16 B read.
+struct ReduceArgs {
+    const float* planes;
+    int rows_pad, world, own_block, n_local;
+    const float4* partial;
+    int nsplit;
+    double* f_ped;                  // [n_local][3]
+    unsigned long long* fixup_rows; // running count of repaired rows (statistics)
+    PairParams pp;
+};
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(256) k1_reduce_fixup(const ReduceArgs a) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = row < a.n_local;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    if (live) {
+        for (int s = 0; s < a.nsplit; ++s) {
+            const float4 p = a.partial[(size_t)s * a.rows_pad + row];
+            sx += (double)p.x;
+            sy += (double)p.y;
+            sz += (double)p.z;
+        }
+    }
+    const bool bad = live && !(isfinite(sx) && isfinite(sy) && isfinite(sz));
+    unsigned mask = __ballot_sync(0xffffffffu, bad);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int r = __shfl_sync(0xffffffffu, row, src);
+        const float* own = a.planes + ((size_t)a.own_block * NPLANES) * a.rows_pad;
+        const float xi = own[(size_t)PX * a.rows_pad + r], yi = own[(size_t)PY * a.rows_pad + r];
+        const float zi = own[(size_t)PZ * a.rows_pad + r], ri = own[(size_t)PR * a.rows_pad + r];
+        const float vxi = own[(size_t)PVX * a.rows_pad + r], vyi = own[(size_t)PVY * a.rows_pad + r];
+        const float vzi = own[(size_t)PVZ * a.rows_pad + r];
+        const int islot = a.own_block * a.rows_pad + r;
+        const int total = a.world * a.rows_pad;
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+        for (int j = lane; j < total; j += 32) {
+            const int q = j / a.rows_pad;
+            const float* b = a.planes + ((size_t)q * NPLANES) * a.rows_pad + (j - q * a.rows_pad);
+            PairAcc acc = {0.0f, 0.0f, 0.0f};
+            pair_force<RADIUS, true>(xi, yi, zi, ri, vxi, vyi, vzi, b[(size_t)PX * a.rows_pad], b[(size_t)PY * a.rows_pad],
+                                     b[(size_t)PZ * a.rows_pad], b[(size_t)PR * a.rows_pad], b[(size_t)PVX * a.rows_pad],
+                                     b[(size_t)PVY * a.rows_pad], b[(size_t)PVZ * a.rows_pad], j == islot, a.pp, acc);
+            gx += (double)acc.gx;
+            gy += (double)acc.gy;
+            gz += (double)acc.gz;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            gz += __shfl_xor_sync(0xffffffffu, gz, o);
+        }
+        if (lane == src) {
+            sx = -gx;
+            sy = -gy;
+            sz = -gz;
+            atomicAdd(a.fixup_rows, 1ull);
+        }
+    }
+    if (live) {
+        a.f_ped[3 * (size_t)row + 0] = sx;
+        a.f_ped[3 * (size_t)row + 1] = sy;
+        a.f_ped[3 * (size_t)row + 2] = sz;
     }
 }
 

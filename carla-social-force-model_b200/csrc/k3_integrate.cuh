@@ -24,15 +24,13 @@ struct StepArgs {
     int64_t n;                   // live local rows
     int64_t rows_pad;            // staged rows of one rank block
     // force inputs
-    const float4* ped_partial;   // [nsplit][rows_pad]
-    int nsplit;
+    const double* ped_force;     // [n][3] reduced pair force (k1_reduce_fixup)
     const double2* f_border;     // [n] or nullptr
     const double2* f_static;
     const double2* f_dynamic;
     // outputs
     double* f_total;             // [n][3]
     double* f_accel;             // [n][3] or nullptr (kept only when class forces are requested)
-    double* f_ped;               // [n][3] or nullptr
     float* planes_own;           // this rank's block of the gather buffer: [NPLANES][rows_pad]
     // parameters
     double dt, tau, max_speed_factor, lambda_ped;
@@ -101,21 +99,9 @@ __global__ void __launch_bounds__(256) k3_integrate(StepArgs a) {
         fz = __dadd_rn(fz, az);
     }
     if (a.enable_ped) {
-        double px = 0.0, py = 0.0, pz = 0.0;
-        for (int s = 0; s < a.nsplit; ++s) {                              // fixed order: deterministic
-            const float4 p = a.ped_partial[(size_t)s * a.rows_pad + i];
-            px += (double)p.x;
-            py += (double)p.y;
-            pz += (double)p.z;
-        }
-        if (a.f_ped) {
-            a.f_ped[3 * i + 0] = px;
-            a.f_ped[3 * i + 1] = py;
-            a.f_ped[3 * i + 2] = pz;
-        }
-        fx = __dadd_rn(fx, px);
-        fy = __dadd_rn(fy, py);
-        fz = __dadd_rn(fz, pz);
+        fx = __dadd_rn(fx, a.ped_force[3 * i + 0]);
+        fy = __dadd_rn(fy, a.ped_force[3 * i + 1]);
+        fz = __dadd_rn(fz, a.ped_force[3 * i + 2]);
     }
     if (a.f_border) {
         const double2 f = a.f_border[i];

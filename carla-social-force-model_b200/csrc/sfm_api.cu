@@ -111,6 +111,8 @@ struct sfm_ctx {
     // enumeration scratch
     DevBuf<long long> emit;
     DevBuf<unsigned long long> emit_count;
+    DevBuf<unsigned long long> fixup_rows;
+    bool fixup_zeroed = false;
     // accounting
     bool profiling = false;
     int64_t launches = 0, steps = 0, pair_launches = 0;
@@ -244,7 +246,7 @@ StepArgs step_args(sfm_ctx* c) {
     StepArgs a{};
     a.locr = c->locr.p; a.vels = c->vels.p; a.wp = c->wp.p; a.mode = c->mode.p;
     a.n = c->n; a.rows_pad = c->rows_pad;
-    a.ped_partial = c->partial.p; a.nsplit = c->nsplit;
+    a.ped_force = c->f_ped.p;
     a.f_total = c->f_total.p;
     a.planes_own = c->planes.p + (size_t)c->rank * NPLANES * c->rows_pad;
     a.dt = c->params.step_length; a.tau = c->params.tau; a.max_speed_factor = c->params.max_speed_factor;
@@ -284,6 +286,21 @@ int launch_pairs(sfm_ctx* c) {
                                                                    c->partial.p, (int)c->rows_pad, pp);
     c->launches += 1;
     c->pair_launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    // reduce the split partials (and repair rows the unguarded fast path poisoned)
+    SFM_TRY(c->f_ped.ensure((size_t)3 * std::max<int64_t>(c->n, 1)));
+    SFM_TRY(c->fixup_rows.ensure(1));
+    if (!c->fixup_zeroed) {
+        SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, sizeof(unsigned long long), c->stream));
+        c->fixup_zeroed = true;
+    }
+    ReduceArgs ra{};
+    ra.planes = c->planes.p; ra.rows_pad = (int)c->rows_pad; ra.world = c->world; ra.own_block = c->rank;
+    ra.n_local = (int)c->n; ra.partial = c->partial.p; ra.nsplit = nsplit; ra.f_ped = c->f_ped.p;
+    ra.fixup_rows = c->fixup_rows.p; ra.pp = pp;
+    if (c->params.use_ped_radius) k1_reduce_fixup<true><<<cdiv(c->n, 256), 256, 0, c->stream>>>(ra);
+    else k1_reduce_fixup<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(ra);
+    c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -473,11 +490,9 @@ int step_once(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool k
     }
     a.enable_accel = P.enable[SFM_FORCE_ACCELERATION];
     a.enable_ped = P.enable[SFM_FORCE_PEDESTRIAN];
-    a.ped_partial = c->partial.p;
-    a.nsplit = c->nsplit;
     a.update_velocity = update_velocity;
     a.integrate_positions = integrate_positions;
-    if (keep_class_forces) { a.f_accel = c->f_accel.p; a.f_ped = c->f_ped.p; }
+    if (keep_class_forces) a.f_accel = c->f_accel.p;
     {
         SpanGuard g(c, ST_INTEGRATE);
         k3_integrate<<<cdiv(std::max<int64_t>(c->n, 1), 256), 256, 0, c->stream>>>(a);
@@ -544,7 +559,7 @@ int sfm_destroy(sfm_ctx* c) {
     c->f_total.release(); c->f_accel.release(); c->f_ped.release();
     c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
-    c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release();
+    c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release();
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -704,7 +719,6 @@ int sfm_force(sfm_ctx* c, int cls, int64_t n, double* out) {
         a.enable_ped = cls == SFM_FORCE_PEDESTRIAN;
         a.update_velocity = 0;
         a.f_accel = c->f_accel.p;
-        a.f_ped = c->f_ped.p;
         {
             SpanGuard g(c, ST_INTEGRATE);
             k3_integrate<<<cdiv(n, 256), 256, 0, c->stream>>>(a);
@@ -820,6 +834,7 @@ int sfm_reset_stats(sfm_ctx* c) {
     SFM_TRY(drain_spans(c));
     c->launches = c->steps = c->pair_launches = 0;
     for (double& m : c->ms) m = 0.0;
+    c->fixup_zeroed = false;
     return 0;
 }
 
@@ -830,6 +845,13 @@ int sfm_get_stats(sfm_ctx* c, sfm_stats* out) {
     out->launches = c->launches; out->steps = c->steps; out->pair_launches = c->pair_launches;
     out->ms_pairs = c->ms[ST_PAIRS]; out->ms_cells = c->ms[ST_CELLS]; out->ms_segments = c->ms[ST_SEGMENTS];
     out->ms_integrate = c->ms[ST_INTEGRATE];
+    out->fixup_rows = 0;
+    if (c->fixup_rows.p && c->fixup_zeroed) {
+        unsigned long long v = 0;
+        SFM_CUDA(cudaMemcpyAsync(&v, c->fixup_rows.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+        SFM_CUDA(cudaStreamSynchronize(c->stream));
+        out->fixup_rows = (int64_t)v;
+    }
     return 0;
 }
 

@@ -68,6 +68,7 @@ typedef struct {
     double ms_segments;                   /* K2b/K2c border + obstacle kernels */
     double ms_integrate;                  /* K3 acceleration + sum + clamp + Euler + restaging */
     int64_t pair_launches;                /* number of K1 launches inside ms_pairs */
+    int64_t fixup_rows;                   /* rows the degenerate-pair repair path recomputed (0 for healthy crowds) */
 } sfm_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
