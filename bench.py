@@ -75,51 +75,51 @@ def build_workload(args, world):
 
 
 class ClockSampler:
-    """nvidia-smi samples (SM clock, throttle reasons) taken DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a background thread, 10 ms period)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, device):
-        self.file = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-        self.proc = None
+        import threading
+        self.samples, self.reasons, self.power, self.max_mhz = [], set(), [], None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(device), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.file,
-                                         stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            index = int(visible.split(',')[device]) if visible and visible.split(',')[device].isdigit() else device
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._thread = None
+
+    def _run(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if self.proc is None:
+        out = {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'samples': 0}
+        if self._thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.file.flush()
-        self.file.seek(0)
-        clocks, reasons, mx, power = [], set(), None, []
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.file.read().splitlines():
-            parts = [x.strip() for x in line.split(',')]
-            if len(parts) < 7:
-                continue
-            try:
-                clocks.append(float(parts[0]))
-                mx = float(parts[1])
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[3:7]):
-                if flag.lower().startswith('active'):
-                    reasons.add(name)
-        os.unlink(self.file.name)
-        if clocks:
-            busy = sorted(clocks)[len(clocks) // 2:]            # upper half = samples under load
-            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(clocks),
-                       power_w_max=max(power))
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.samples:
+            out.update(sm_mhz=float(np.median(self.samples)), reasons=sorted(self.reasons), samples=len(self.samples),
+                       power_w_max=max(self.power) if self.power else None)
         return out
 
 

@@ -8,9 +8,10 @@
 //       pedestrian visits its candidate items in one fixed order.  The cell edge is >= the largest cutoff of the set,
 //       hence every item within the cutoff of a pedestrian lies in the 3x3 cells around it.  Pedestrians are binned
 //       too (Morton-ordered counting sort) purely for locality: a CTA then owns pedestrians that share candidates.
-//  K2b/c  one CTA = 128 spatially adjacent pedestrians, one per thread.  The CTA walks the cells overlapping its
-//       bounding box (+1 ring), rejects items whose cutoff disc misses the box, stages the item's points in shared
-//       memory and lets every thread that passes the reference's exact filter scan them.
+//  K2b/c  one CTA = 32 spatially adjacent pedestrians (one per lane) x 4 warps that split the candidate items.  The
+//       warps walk the cells overlapping the pedestrians' bounding box (+1 ring), reject items whose cutoff disc misses
+//       the box, stage an item's points in shared memory and let every lane that passes the reference's exact filter
+//       scan them.
 //
 // Bit-exact enumeration: the filter sqrt(dx*dx + dy*dy) < cutoff and the nearest-point argmin are evaluated in float64
 // with numpy's operation order (np.linalg.norm = sqrt(add.reduce(x*x)), unfused), np.argmin's first-index tie rule
@@ -22,8 +23,9 @@
 
 namespace sfm {
 
-constexpr int K2_THREADS = 128;
-constexpr int K2_CHUNK = 256;           // points staged per pass
+constexpr int K2_WARPS = 4;             // warps sharing one group of 32 pedestrians
+constexpr int K2_THREADS = 32 * K2_WARPS;
+constexpr int K2_CHUNK = 128;           // points one warp stages per pass
 constexpr int SORT_THREADS = 512;
 constexpr int SORT_RADIX_BITS = 4;
 
@@ -288,12 +290,17 @@ __device__ __noinline__ int exact_argmin(const double2* __restrict__ point, int 
     return best_q;
 }
 
+// One CTA = 32 spatially adjacent pedestrians (lane = pedestrian) x K2_WARPS warps.  All warps walk the same candidate
+// list -- metadata of 32 items is fetched lane-parallel and broadcast by shuffles -- and share it by item index: warp k
+// takes the items with index % K2_WARPS == k that survive the bounding-box test.  Each warp stages its item's points in its own
+// shared-memory slice (warp-level barriers only), scans them, and keeps a partial force per pedestrian; the partials
+// are combined in warp order at the end, so the summation order is fixed.
 template <int KIND>
 __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
-    __shared__ double2 sp[K2_CHUNK];
-    __shared__ double red[4][K2_THREADS / 32];
+    __shared__ double2 sp[K2_WARPS][K2_CHUNK];
+    __shared__ double2 part[K2_WARPS][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int slot = blockIdx.x * K2_THREADS + tid;
+    const int slot = blockIdx.x * 32 + lane;
     const bool active = slot < a.n;
     const int i = active ? a.perm[slot] : -1;
     double px = 0.0, py = 0.0, radius = 0.0, vx = 0.0, vy = 0.0;
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
         const double4 V = a.vels[i];
         px = L.x; py = L.y; radius = L.w; vx = V.x; vy = V.y;
     }
-    // CTA bounding box of the live pedestrians
+    // bounding box of the warp's live pedestrians
     const double BIG = 1.0e300;
     double x0 = active ? px : BIG, x1 = active ? px : -BIG, y0 = active ? py : BIG, y1 = active ? py : -BIG;
 #pragma unroll
@@ -312,62 +319,72 @@ __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
         y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
         y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
     }
-    if (lane == 0) { red[0][wid] = x0; red[1][wid] = x1; red[2][wid] = y0; red[3][wid] = y1; }
-    __syncthreads();
-    x0 = red[0][0]; x1 = red[1][0]; y0 = red[2][0]; y1 = red[3][0];
-#pragma unroll
-    for (int w = 1; w < K2_THREADS / 32; ++w) {
-        x0 = fmin(x0, red[0][w]); x1 = fmax(x1, red[1][w]); y0 = fmin(y0, red[2][w]); y1 = fmax(y1, red[3][w]);
-    }
     const CellGrid g = a.grid;
     const int cx0 = max(cell_coord(x0, g.x0, g.inv_cell, g.nx) - 1, 0);
     const int cx1 = min(cell_coord(x1, g.x0, g.inv_cell, g.nx) + 1, g.nx - 1);
     const int cy0 = max(cell_coord(y0, g.y0, g.inv_cell, g.ny) - 1, 0);
     const int cy1 = min(cell_coord(y1, g.y0, g.inv_cell, g.ny) + 1, g.ny - 1);
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
     double fx = 0.0, fy = 0.0;
     for (int cy = cy0; cy <= cy1; ++cy) {
-        for (int cx = cx0; cx <= cx1; ++cx) {
-            const int c = cy * g.nx + cx;
-            const int k_end = a.cell_start[c + 1];
-            for (int k = a.cell_start[c]; k < k_end; ++k) {
-                const int s = a.cell_item[k];
-                const double2 cen = a.center[s];
-                const double cut = a.cutoff[s];
-                // CTA-uniform conservative reject: the cutoff disc misses the bounding box (with slack for rounding)
-                const double gx = fmax(fmax(x0 - cen.x, cen.x - x1), 0.0), gy = fmax(fmax(y0 - cen.y, cen.y - y1), 0.0);
-                if (gx * gx + gy * gy > cut * cut * 1.000000001) continue;
+        // cells of one grid row are contiguous in the (cell, index) order: one item range per row
+        const int k_begin = a.cell_start[cy * g.nx + cx0], k_end = a.cell_start[cy * g.nx + cx1 + 1];
+        for (int k0 = k_begin; k0 < k_end; k0 += 32) {
+            const int kk = k0 + lane;
+            int s_l = -1, o0_l = 0, o1_l = 0;
+            double2 cen_l = make_double2(0.0, 0.0);
+            double cut_l = 0.0;
+            bool accept_l = false;
+            if (kk < k_end) {
+                s_l = a.cell_item[kk];
+                cen_l = a.center[s_l];
+                cut_l = a.cutoff[s_l];
+                o0_l = a.offset[s_l];
+                o1_l = a.offset[s_l + 1];
+                // conservative reject: the cutoff disc misses the warp's bounding box (slack covers rounding)
+                const double gx = fmax(fmax(x0 - cen_l.x, cen_l.x - x1), 0.0);
+                const double gy = fmax(fmax(y0 - cen_l.y, cen_l.y - y1), 0.0);
+                accept_l = !(gx * gx + gy * gy > cut_l * cut_l * 1.000000001);
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, accept_l);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                // item -> warp by the item's own index, so a pedestrian's summation order does not depend on which
+                // other pedestrians share its group (results are reproducible under any pedestrian ordering)
+                const int s = __shfl_sync(0xffffffffu, s_l, src);
+                if ((s % K2_WARPS) != wid) continue;
+                const double cxs = __shfl_sync(0xffffffffu, cen_l.x, src), cys = __shfl_sync(0xffffffffu, cen_l.y, src);
+                const double cut = __shfl_sync(0xffffffffu, cut_l, src);
+                const int o0 = __shfl_sync(0xffffffffu, o0_l, src), o1 = __shfl_sync(0xffffffffu, o1_l, src);
                 // the reference's filter, bit for bit: norm(loc - centre) < cutoff  (forces.py:149-150, :222-223)
-                const bool pass = active && (norm2_np(__dsub_rn(px, cen.x), __dsub_rn(py, cen.y)) < cut);
-                const bool warp_pass = __any_sync(0xffffffffu, pass);
-                const int o0 = a.offset[s], o1 = a.offset[s + 1];
-                // Nearest point = np.argmin over the *rounded square roots* (forces.py:154, :228), first index on ties.
-                // The scan tracks the smallest squared distance m1 (first index q1, strict <) and the runner-up m2;
-                // sqrt is monotone, so q1 is numpy's answer unless another point's d2 lies within rounding distance
-                // of m1 -- then (rare) the section is rescanned with numpy's exact arithmetic.
-                const double INF = __longlong_as_double(0x7ff0000000000000LL);
+                const bool pass = active && (norm2_np(__dsub_rn(px, cxs), __dsub_rn(py, cys)) < cut);
+                if (!__any_sync(0xffffffffu, pass)) continue;
+                // Nearest point = np.argmin over the *rounded square roots* (forces.py:154, :228), first index on
+                // ties.  The scan tracks the smallest squared distance m1 (first index, strict <) and the runner-up
+                // m2; sqrt is monotone, so that index is numpy's answer unless another point's d2 lies within
+                // rounding distance of m1 -- then (rare) the item is rescanned with numpy's exact arithmetic.
                 double m1 = INF, m2 = INF;
                 int best_q = o0;
                 for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
                     const int m = min(K2_CHUNK, o1 - c0);
-                    __syncthreads();
-                    for (int q = tid; q < m; q += K2_THREADS) sp[q] = a.point[c0 + q];
-                    __syncthreads();
-                    if (warp_pass) {
+                    __syncwarp();
+                    for (int q = lane; q < m; q += 32) sp[wid][q] = a.point[c0 + q];
+                    __syncwarp();
 #pragma unroll 4
-                        for (int q = 0; q < m; ++q) {
-                            const double2 P = sp[q];
-                            const double dx = __dsub_rn(px, P.x), dy = __dsub_rn(py, P.y);
-                            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                            const bool lt1 = d2 < m1, lt2 = d2 < m2;
-                            m2 = lt1 ? m1 : (lt2 ? d2 : m2);
-                            m1 = lt1 ? d2 : m1;
-                            best_q = lt1 ? (c0 + q) : best_q;
-                        }
+                    for (int q = 0; q < m; ++q) {
+                        const double2 P = sp[wid][q];
+                        const double dx = px - P.x, dy = py - P.y;
+                        const double d2 = fma(dx, dx, dy * dy);          // argmin only; ties go to exact_argmin
+                        const bool lt1 = d2 < m1, lt2 = d2 < m2;
+                        m2 = lt1 ? m1 : (lt2 ? d2 : m2);
+                        m1 = lt1 ? d2 : m1;
+                        best_q = lt1 ? (c0 + q) : best_q;
                     }
                 }
-                if (pass && m2 <= m1 * 1.00000000000001) best_q = exact_argmin(a.point, o0, o1, px, py);
                 if (pass) {
+                    if (m2 <= m1 * 1.00000000000001) best_q = exact_argmin(a.point, o0, o1, px, py);
                     const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
                                                           KIND ? a.velocity[s] : make_double2(0.0, 0.0));
                     fx = __dadd_rn(fx, f.x);
@@ -384,12 +401,20 @@ __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
             }
         }
     }
-    if (active) {
+    part[wid][lane] = make_double2(fx, fy);
+    __syncthreads();
+    if (wid == 0 && active) {
+        double sx = part[0][lane].x, sy = part[0][lane].y;
+#pragma unroll
+        for (int w = 1; w < K2_WARPS; ++w) {
+            sx = __dadd_rn(sx, part[w][lane].x);
+            sy = __dadd_rn(sy, part[w][lane].y);
+        }
         if (KIND == 0) {
             const uint8_t md = a.mode[i];                   // forces.py:176-177
-            if (md == SFM_CROSSING_ROAD || md == SFM_ROAD_TO_SIDEWALK) { fx = __dmul_rn(fx, 0.0); fy = __dmul_rn(fy, 0.0); }
+            if (md == SFM_CROSSING_ROAD || md == SFM_ROAD_TO_SIDEWALK) { sx = __dmul_rn(sx, 0.0); sy = __dmul_rn(sy, 0.0); }
         }
-        a.f_out[i] = make_double2(fx, fy);
+        a.f_out[i] = make_double2(sx, sy);
     }
 }
 

@@ -452,8 +452,8 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity) {
         a.emit = c->emit.p; a.emit_count = c->emit_count.p; a.emit_capacity = emit_capacity;
     }
     SpanGuard g(c, ST_SEGMENTS);
-    if (cls == SFM_FORCE_BORDER) k2_segments<0><<<cdiv(n, K2_THREADS), K2_THREADS, 0, c->stream>>>(a);
-    else k2_segments<1><<<cdiv(n, K2_THREADS), K2_THREADS, 0, c->stream>>>(a);
+    if (cls == SFM_FORCE_BORDER) k2_segments<0><<<cdiv(n, 32), K2_THREADS, 0, c->stream>>>(a);
+    else k2_segments<1><<<cdiv(n, 32), K2_THREADS, 0, c->stream>>>(a);
     c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     return 0;

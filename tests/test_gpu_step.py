@@ -68,3 +68,51 @@ def test_zero_target_speed_stops(sfm_config):
     ctx.step(1)
     _, vel = ctx.download_state()
     assert not vel.any()                                      # stateutils.py:20-23 with s = 0
+
+
+def test_two_rank_partition_emulated_on_one_gpu(sfm_config):
+    """Row partition + all-gather layout, emulated with two contexts on one GPU (the exchange is a device copy of each
+    rank's staged block into the other's gather buffer -- what NCCL's all-gather does across GPUs)."""
+    import torch
+    from sfm_b200 import engine
+    w = synth.make_config(2, n=3000)                                   # ragged: 1500 + 1500 rows in 1536-row blocks
+    whole = make_context(w, sfm_config)
+    bounds = engine.partition_rows(w.n, 2)
+    rows_pad = engine.padded_rows(bounds)
+    ranks = []
+    for r in range(2):
+        lo, hi = int(bounds[r]), int(bounds[r + 1])
+        ctx = native.Context(0)
+        ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+        ctx.set_partition(2, r, rows_pad)
+        ctx.upload_state(w.loc[lo:hi], w.vel[lo:hi], w.next_waypoint[lo:hi], w.radius[lo:hi], w.target_speed[lo:hi],
+                         w.mode[lo:hi])
+        ctx.set_borders(w.borders, w.section_center, w.section_length)
+        ctx.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles], [r_ for _, r_ in w.static_obstacles])
+        veh = w.vehicles_at(0)
+        ctx.set_obstacles(native.DYNAMIC_OBSTACLE, veh[1], veh[5], veh[3])
+        ctx.stage()
+        ctx.synchronize()
+        ptr, per_rank = ctx.gather_buffer()
+        view = torch.as_tensor(engine._DeviceView(ptr, per_rank // 4 * 2), device='cuda:0')
+        ranks.append((ctx, view, per_rank // 4))
+
+    def exchange():
+        for r, (ctx, view, per) in enumerate(ranks):
+            ctx.synchronize()
+        for r, (_, view, per) in enumerate(ranks):
+            other = ranks[1 - r][1]
+            other[r * per:(r + 1) * per].copy_(view[r * per:(r + 1) * per])
+        torch.cuda.synchronize()
+
+    exchange()
+    for step in range(3):
+        whole.step(1, True)
+        for ctx, _, _ in ranks:
+            ctx.step(1, True)
+        exchange()
+    loc_w, vel_w = whole.download_state()
+    loc_p = np.concatenate([ranks[r][0].download_state()[0] for r in range(2)])
+    vel_p = np.concatenate([ranks[r][0].download_state()[1] for r in range(2)])
+    np.testing.assert_allclose(loc_p, loc_w, rtol=0, atol=1e-6)       # split geometry differs -> float32 sum order differs
+    np.testing.assert_allclose(vel_p, vel_w, rtol=0, atol=2e-5)
