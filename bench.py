@@ -162,6 +162,7 @@ def run_ours(args, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     dist = torch.distributed
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('SFM_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     cfg = load_config()
     w, name = build_workload(args, world)

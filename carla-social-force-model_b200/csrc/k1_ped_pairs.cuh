@@ -350,8 +350,8 @@ __device__ __forceinline__ void tile_pairs_packed(const float (*__restrict__ tl)
 // planes:      [world][NPLANES][rows_pad] staged rows of all ranks (after the all-gather)
 // own_block:   index of the rank block whose rows this launch computes forces for
 // partial:     [gridDim.y][partial_stride] float4, (-> K3 sums over the splits)
-template <int IR, bool RADIUS>
-__global__ void __launch_bounds__(K1_THREADS) k1_ped_pairs(const float* __restrict__ planes, const int rows_pad,
+template <int IR, bool RADIUS, int MINB>
+__global__ void __launch_bounds__(K1_THREADS, MINB) k1_ped_pairs(const float* __restrict__ planes, const int rows_pad,
                                                            const int total_tiles, const int own_block,
                                                            float4* __restrict__ partial, const int partial_stride,
                                                            const PairParams pp) {

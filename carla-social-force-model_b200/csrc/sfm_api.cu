@@ -120,6 +120,7 @@ struct sfm_ctx {
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> event_pool;
     int k1_target_ctas = 148 * 4 * 16;
+    int k1_ir = 2, k1_minb = 5;     // tuning knobs (SFM_K1_IR, SFM_K1_MINB)
 };
 
 namespace {
@@ -267,7 +268,7 @@ int launch_stage(sfm_ctx* c) {
 
 int launch_pairs(sfm_ctx* c) {
     if (!c->staged) SFM_TRY(launch_stage(c));
-    constexpr int IR = 2;
+    const int IR = c->k1_ir;
     const int rows_per_cta = K1_THREADS * IR;
     const int itiles = (int)(c->rows_pad / rows_per_cta);
     const int total_tiles = (int)((int64_t)c->world * c->rows_pad / K1_TJ);
@@ -278,12 +279,22 @@ int launch_pairs(sfm_ctx* c) {
     const PairParams pp = make_pair_params(c->params.ped);
     SpanGuard g(c, ST_PAIRS);
     dim3 grid(itiles, nsplit);
-    if (c->params.use_ped_radius)
-        k1_ped_pairs<IR, true><<<grid, K1_THREADS, 0, c->stream>>>(c->planes.p, (int)c->rows_pad, total_tiles, c->rank,
-                                                                  c->partial.p, (int)c->rows_pad, pp);
-    else
-        k1_ped_pairs<IR, false><<<grid, K1_THREADS, 0, c->stream>>>(c->planes.p, (int)c->rows_pad, total_tiles, c->rank,
-                                                                   c->partial.p, (int)c->rows_pad, pp);
+    const bool rad = c->params.use_ped_radius != 0;
+#define SFM_K1_LAUNCH(IRV, MINBV)                                                                                      \
+    do {                                                                                                               \
+        if (rad)                                                                                                       \
+            k1_ped_pairs<IRV, true, MINBV><<<grid, K1_THREADS, 0, c->stream>>>(                                         \
+                c->planes.p, (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
+        else                                                                                                           \
+            k1_ped_pairs<IRV, false, MINBV><<<grid, K1_THREADS, 0, c->stream>>>(                                        \
+                c->planes.p, (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
+    } while (0)
+    if (IR == 2 && c->k1_minb <= 5) SFM_K1_LAUNCH(2, 5);
+    else if (IR == 2 && c->k1_minb == 6) SFM_K1_LAUNCH(2, 6);
+    else if (IR == 2) SFM_K1_LAUNCH(2, 8);
+    else if (c->k1_minb <= 8) SFM_K1_LAUNCH(1, 8);
+    else SFM_K1_LAUNCH(1, 10);
+#undef SFM_K1_LAUNCH
     c->launches += 1;
     c->pair_launches += 1;
     SFM_CUDA(cudaGetLastError());
@@ -544,6 +555,8 @@ int sfm_create(int device, sfm_ctx** out) {
     c->stream = c->own_stream;
     if (const char* env = std::getenv("SFM_K1_TARGET_CTAS")) c->k1_target_ctas = std::max(1, std::atoi(env));
     else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
+    if (const char* env = std::getenv("SFM_K1_IR")) c->k1_ir = std::atoi(env) == 1 ? 1 : 2;
+    if (const char* env = std::getenv("SFM_K1_MINB")) c->k1_minb = std::atoi(env);
     *out = c;
     return 0;
 }
