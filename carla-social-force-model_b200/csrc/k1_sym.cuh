@@ -1,0 +1,340 @@
+// K1s -- all-pairs pedestrian force evaluated once per UNORDERED pair (Newton's third law), float32 packed, sm_100a.
+//
+// The reference's pair force (forces.py:74-117) is exactly antisymmetric: swapping i and j negates d = p_j - p_i and
+// w = lambda (v_i - v_j), hence D = d/|d| + w -> -D, while |d|, |D|, B = gamma |D|, the radius term r_i + r_j and the
+// interaction angle theta = atan2(D_xy x d_xy, D_xy . d_xy) are unchanged; so f_ji = -f_ij.  Each tile pair {I, J} of
+// 256-row tiles is therefore visited once ("half shell": tile I takes the partners I+1 .. I+T/2 cyclically) and the
+// result is added to the rows of I and subtracted from the rows of J.
+//
+// * Thread t of the CTA owns 2 rows of tile I (registers).  Lanes are STAGGERED over the partner tile: at step k lane l
+//   works on j-quad (k + l) mod 64, so the J-side accumulation (a per-warp shared-memory array, read-modify-write of 3
+//   float4 per step) never sees two lanes of a warp on the same j; no shared-memory atomics.
+// * Tile partials (256 terms per row, float32) are converted to 64-bit fixed point (2^-32 m/s^2) and accumulated with
+//   integer atomics: integer addition is associative, so the result does not depend on CTA scheduling, on the launch
+//   geometry or on how many GPUs share the crowd -- and the multi-GPU exchange is an integer reduce-scatter.
+// * The diagonal tile {I, I} runs the guarded asymmetric code (self pairs removed).  A non-finite or out-of-range tile
+//   partial (degenerate pair) bumps the row's poison counter instead; k1_sym_finish recomputes
+//   poisoned rows with the guarded scalar path.
+#pragma once
+
+#include "k1_ped_pairs.cuh"
+
+namespace sfm {
+
+constexpr int KS_THREADS = 128;
+constexpr int KS_IR = 2;
+constexpr int KS_QUADS = K1_TJ / 4;
+constexpr float KS_FIXED_SCALE = 4294967296.0f;          // 2^32 counts per m/s^2
+constexpr float KS_FIXED_LIMIT = 1.0e9f;                 // |partial| beyond this goes to the repair path
+
+struct SymArgs {
+    const float* planes;       // [world][NPLANES][rows_pad]
+    int rows_pad;
+    int total_tiles;           // world * rows_pad / 256
+    int own_first_tile;        // first tile of this rank's rows
+    long long* facc;           // [total_slots][4]: fixed-point force x, y, z and the poison counter
+    PairParams pp;
+};
+
+// -f_ij for two consecutive j at once: g = (a Dx - b Dy, a Dy + b Dx, a Dz); F_i -= g, F_j += g.
+template <bool RADIUS>
+__device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, const f32x2 zi, const f32x2 ri,
+                                            const f32x2 vxi, const f32x2 vyi, const f32x2 vzi, const f32x2 xj,
+                                            const f32x2 yj, const f32x2 zj, const f32x2 rj, const f32x2 vxj,
+                                            const f32x2 vyj, const f32x2 vzj, const PackedConst& c, f32x2& gx, f32x2& gy,
+                                            f32x2& gz) {
+    const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi), dz = sub2(zj, zi);
+    const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const f32x2 rinv = rsqrt2(d2);
+    const f32x2 dist = mul2(d2, rinv);
+    const f32x2 wx = sub2(vxi, vxj), wy = sub2(vyi, vyj), wz = sub2(vzi, vzj);
+    const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy), Dz = fma2(dz, rinv, wz);
+    const f32x2 D2 = fma2(Dz, Dz, fma2(Dy, Dy, mul2(Dx, Dx)));
+    const f32x2 Dinv = rsqrt2(D2);
+    const f32x2 Dn = mul2(D2, Dinv);
+    const f32x2 cross = fma2(wx, dy, neg2(mul2(wy, dx)));
+    const f32x2 dot = fma2(Dx, dx, mul2(Dy, dy));
+    float cl, ch, tl, th;
+    unpack2(cross, cl, ch);
+    unpack2(dot, tl, th);
+    const float axl = fabsf(tl), ayl = fabsf(cl), axh = fabsf(th), ayh = fabsf(ch);
+    const f32x2 mn = pack2(fminf(axl, ayl), fminf(axh, ayh));
+    const f32x2 mxr = pack2(rcp_approx(fmaxf(axl, ayl)), rcp_approx(fmaxf(axh, ayh)));
+    const f32x2 q = mul2(mn, mxr);
+    const f32x2 s = mul2(q, q);
+    f32x2 p = fma2(c.a7, s, c.a6);
+    p = fma2(p, s, c.a5);
+    p = fma2(p, s, c.a4);
+    p = fma2(p, s, c.a3);
+    p = fma2(p, s, c.a2);
+    p = fma2(p, s, c.a1);
+    p = fma2(p, s, c.a0);
+    p = mul2(p, q);
+    float pl, ph;
+    unpack2(p, pl, ph);
+    const f32x2 theta = pack2(octant_fix(pl, axl, ayl, tl, cl), octant_fix(ph, axh, ayh, th, ch));
+    const f32x2 thp = fma2(c.eps_gamma_neg, Dn, theta);
+    const f32x2 u = mul2(Dn, thp);
+    const f32x2 u2 = mul2(u, u);
+    f32x2 dl = dist;
+    if (RADIUS) dl = sub2(sub2(dist, ri), rj);
+    const f32x2 y = fma2(mul2(dl, Dinv), c.k_exp, c.log2A);
+    const f32x2 e1 = ex2_2(fma2(c.c_nprime_neg, u2, y));
+    const f32x2 e2 = ex2_2(fma2(c.c_n_neg, u2, y));
+    const f32x2 a = mul2(e1, Dinv);
+    const f32x2 b = mul2(e2, Dinv) | (thp & 0x8000000080000000ULL);      // copysign(e2 / |D|, theta')
+    gx = fma2(a, Dx, mul2(neg2(b), Dy));
+    gy = fma2(a, Dy, mul2(b, Dx));
+    gz = mul2(a, Dz);
+}
+
+__device__ __forceinline__ bool fixed_ok(float v) { return fabsf(v) < KS_FIXED_LIMIT; }     // false for NaN / inf too
+__device__ __forceinline__ long long to_fixed(float v) { return __float2ll_rn(v * KS_FIXED_SCALE); }
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
+    __shared__ __align__(128) float tile[K1_STAGES][K1_PLANES][K1_TJ];
+    __shared__ __align__(16) float accj[KS_THREADS / 32][3][K1_TJ];
+    __shared__ __align__(8) uint64_t bar[K1_STAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int T = a.total_tiles;
+    const int I = a.own_first_tile + blockIdx.x;
+    const int tiles_per_rank = a.rows_pad / K1_TJ;
+    // half shell: partners I+1 .. I+H (cyclic); for even T the opposite tile belongs to the lower half only
+    const int H = (T & 1) ? (T - 1) / 2 : ((I < T / 2) ? T / 2 : T / 2 - 1);
+    const int nsplit = gridDim.y, split = blockIdx.y;
+    const int m_begin = (int)(((long long)H * split) / nsplit), m_end = (int)(((long long)H * (split + 1)) / nsplit);
+    const int has_diag = (split == 0) ? 1 : 0;
+    const int n_items = has_diag + (m_end - m_begin);
+    if (n_items == 0) return;
+    auto item_tile = [&](int k) {
+        if (has_diag && k == 0) return I;
+        int j = I + 1 + m_begin + (k - has_diag);
+        return (j >= T) ? j - T : j;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    for (int e = tid; e < (KS_THREADS / 32) * 3 * K1_TJ; e += KS_THREADS) (&accj[0][0][0])[e] = 0.0f;
+    __syncthreads();
+
+    auto issue = [&](int t, int stage) {
+        const int q = t / tiles_per_rank;
+        const int off = (t - q * tiles_per_rank) * K1_TJ;
+        const float* src = a.planes + ((size_t)q * NPLANES) * a.rows_pad + off;
+        mbar_expect_tx(&bar[stage], K1_PLANES * K1_TJ * sizeof(float));
+#pragma unroll
+        for (int p = 0; p < K1_PLANES; ++p)
+            bulk_copy_g2s(&tile[stage][p][0], src + (size_t)p * a.rows_pad, K1_TJ * sizeof(float), &bar[stage]);
+    };
+    if (tid == 0) issue(item_tile(0), 0);
+
+    // this thread's rows of tile I
+    const int qi = I / tiles_per_rank;
+    const float* own = a.planes + ((size_t)qi * NPLANES) * a.rows_pad + (size_t)(I - qi * tiles_per_rank) * K1_TJ;
+    float xi[KS_IR], yi[KS_IR], zi[KS_IR], ri[KS_IR], vxi[KS_IR], vyi[KS_IR], vzi[KS_IR];
+    f32x2 xi2[KS_IR], yi2[KS_IR], zi2[KS_IR], ri2[KS_IR], vxi2[KS_IR], vyi2[KS_IR], vzi2[KS_IR];
+    long long fix[KS_IR][3];
+    int bad[KS_IR];
+#pragma unroll
+    for (int r = 0; r < KS_IR; ++r) {
+        const int row = r * KS_THREADS + tid;
+        xi[r] = own[(size_t)PX * a.rows_pad + row];
+        yi[r] = own[(size_t)PY * a.rows_pad + row];
+        zi[r] = own[(size_t)PZ * a.rows_pad + row];
+        ri[r] = own[(size_t)PR * a.rows_pad + row];
+        vxi[r] = own[(size_t)PVX * a.rows_pad + row];
+        vyi[r] = own[(size_t)PVY * a.rows_pad + row];
+        vzi[r] = own[(size_t)PVZ * a.rows_pad + row];
+        xi2[r] = splat2(xi[r]); yi2[r] = splat2(yi[r]); zi2[r] = splat2(zi[r]); ri2[r] = splat2(ri[r]);
+        vxi2[r] = splat2(vxi[r]); vyi2[r] = splat2(vyi[r]); vzi2[r] = splat2(vzi[r]);
+        fix[r][0] = fix[r][1] = fix[r][2] = 0;
+        bad[r] = 0;
+    }
+    const PackedConst pc = make_packed_const(a.pp);
+
+    for (int k = 0; k < n_items; ++k) {
+        const int stage = k & 1;
+        const int J = item_tile(k);
+        if (tid == 0 && k + 1 < n_items) issue(item_tile(k + 1), stage ^ 1);   // stage^1 was released by the barriers below
+        while (!mbar_try_wait(&bar[stage], (k >> 1) & 1)) {}
+        float gi[KS_IR][3];                                   // this tile's -F_i partial per row
+        if (J == I) {
+            // diagonal tile: guarded asymmetric evaluation with self pairs removed, rows of I only
+            PairAcc acc[KS_IR];
+            int self_j[KS_IR];
+#pragma unroll
+            for (int r = 0; r < KS_IR; ++r) {
+                acc[r].gx = acc[r].gy = acc[r].gz = 0.0f;
+                self_j[r] = r * KS_THREADS + tid;
+            }
+            tile_pairs<KS_IR, RADIUS, true>(tile[stage], xi, yi, zi, ri, vxi, vyi, vzi, self_j, a.pp, acc);
+#pragma unroll
+            for (int r = 0; r < KS_IR; ++r) { gi[r][0] = acc[r].gx; gi[r][1] = acc[r].gy; gi[r][2] = acc[r].gz; }
+            __syncthreads();
+        } else {
+            f32x2 Gx[KS_IR], Gy[KS_IR], Gz[KS_IR];
+#pragma unroll
+            for (int r = 0; r < KS_IR; ++r) Gx[r] = Gy[r] = Gz[r] = 0ull;
+            const float (*tl)[K1_TJ] = tile[stage];
+#pragma unroll 1
+            for (int step = 0; step < KS_QUADS; ++step) {
+                const int j = ((step + lane) & (KS_QUADS - 1)) * 4;          // staggered: distinct j per lane
+                const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tl[PX][j]);
+                const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&tl[PY][j]);
+                const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&tl[PZ][j]);
+                ulonglong2 R = make_ulonglong2(0ull, 0ull);
+                if (RADIUS) R = *reinterpret_cast<const ulonglong2*>(&tl[PR][j]);
+                const ulonglong2 VX = *reinterpret_cast<const ulonglong2*>(&tl[PVX][j]);
+                const ulonglong2 VY = *reinterpret_cast<const ulonglong2*>(&tl[PVY][j]);
+                const ulonglong2 VZ = *reinterpret_cast<const ulonglong2*>(&tl[PVZ][j]);
+                f32x2 jx0 = 0ull, jy0 = 0ull, jz0 = 0ull, jx1 = 0ull, jy1 = 0ull, jz1 = 0ull;   // sum over my rows
+#pragma unroll
+                for (int r = 0; r < KS_IR; ++r) {
+                    f32x2 gx, gy, gz;
+                    pair_terms2<RADIUS>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.x, Y.x, Z.x, R.x,
+                                        VX.x, VY.x, VZ.x, pc, gx, gy, gz);
+                    Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy); Gz[r] = add2(Gz[r], gz);
+                    jx0 = r ? add2(jx0, gx) : gx; jy0 = r ? add2(jy0, gy) : gy; jz0 = r ? add2(jz0, gz) : gz;
+                    pair_terms2<RADIUS>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.y, Y.y, Z.y, R.y,
+                                        VX.y, VY.y, VZ.y, pc, gx, gy, gz);
+                    Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy); Gz[r] = add2(Gz[r], gz);
+                    jx1 = r ? add2(jx1, gx) : gx; jy1 = r ? add2(jy1, gy) : gy; jz1 = r ? add2(jz1, gz) : gz;
+                }
+                // J side: F_j += g, into this warp's private slice (lanes hold distinct j, so plain read-modify-write)
+                ulonglong2* ax = reinterpret_cast<ulonglong2*>(&accj[wid][0][j]);
+                ulonglong2* ay = reinterpret_cast<ulonglong2*>(&accj[wid][1][j]);
+                ulonglong2* az = reinterpret_cast<ulonglong2*>(&accj[wid][2][j]);
+                ulonglong2 vx = *ax, vy = *ay, vz = *az;
+                vx.x = add2(vx.x, jx0); vx.y = add2(vx.y, jx1);
+                vy.x = add2(vy.x, jy0); vy.y = add2(vy.y, jy1);
+                vz.x = add2(vz.x, jz0); vz.y = add2(vz.y, jz1);
+                *ax = vx; *ay = vy; *az = vz;
+                __syncwarp();                                   // next step another lane owns this quad
+            }
+#pragma unroll
+            for (int r = 0; r < KS_IR; ++r) {
+                float lo, hi;
+                unpack2(Gx[r], lo, hi); gi[r][0] = lo + hi;
+                unpack2(Gy[r], lo, hi); gi[r][1] = lo + hi;
+                unpack2(Gz[r], lo, hi); gi[r][2] = lo + hi;
+            }
+            __syncthreads();                                    // every warp's J-side slice is complete
+            // flush the J side: sum the warps' slices in fixed order, fixed-point atomics into the global accumulator
+            for (int e = tid; e < K1_TJ; e += KS_THREADS) {
+                float v[3];
+                bool ok = true;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    v[c] = ((accj[0][c][e] + accj[1][c][e]) + accj[2][c][e]) + accj[3][c][e];
+                    accj[0][c][e] = accj[1][c][e] = accj[2][c][e] = accj[3][c][e] = 0.0f;
+                    ok = ok && fixed_ok(v[c]);
+                }
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.facc + ((size_t)J * K1_TJ + e) * 4);
+                if (ok) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (v[c] != 0.0f) atomicAdd(dst + c, (unsigned long long)to_fixed(v[c]));
+                } else {
+                    atomicAdd(dst + 3, 1ull);
+                }
+            }
+            __syncthreads();                                    // slices are zero again; the tile stage is free
+        }
+        // I side: this tile's partial into the thread's fixed-point registers (F_i -= g)
+#pragma unroll
+        for (int r = 0; r < KS_IR; ++r) {
+            if (fixed_ok(gi[r][0]) && fixed_ok(gi[r][1]) && fixed_ok(gi[r][2])) {
+                fix[r][0] -= to_fixed(gi[r][0]);
+                fix[r][1] -= to_fixed(gi[r][1]);
+                fix[r][2] -= to_fixed(gi[r][2]);
+            } else {
+                bad[r] += 1;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KS_IR; ++r) {
+        unsigned long long* dst =
+            reinterpret_cast<unsigned long long*>(a.facc + ((size_t)I * K1_TJ + r * KS_THREADS + tid) * 4);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (fix[r][c] != 0) atomicAdd(dst + c, (unsigned long long)fix[r][c]);
+        if (bad[r]) atomicAdd(dst + 3, (unsigned long long)bad[r]);
+    }
+}
+
+// Fixed-point accumulators -> float64 pair force of the local rows; poisoned rows are recomputed by their warp with the
+// guarded scalar code (numpy's zero-safe semantics), lanes striding over every staged slot.
+struct FinishArgs {
+    const float* planes;
+    int rows_pad, world, own_block, n_local;
+    const long long* facc_own;      // [rows_pad][4] this rank's block (after the reduce-scatter)
+    double* f_ped;                  // [n_local][3]
+    unsigned long long* fixup_rows;
+    PairParams pp;
+};
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(256) k1_sym_finish(const FinishArgs a) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = row < a.n_local;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    bool bad = false;
+    if (live) {
+        const long long* f = a.facc_own + (size_t)row * 4;
+        const double inv = 1.0 / 4294967296.0;
+        sx = (double)f[0] * inv;
+        sy = (double)f[1] * inv;
+        sz = (double)f[2] * inv;
+        bad = f[3] != 0;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, bad);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int r = __shfl_sync(0xffffffffu, row, src);
+        const float* own = a.planes + ((size_t)a.own_block * NPLANES) * a.rows_pad;
+        const float xi = own[(size_t)PX * a.rows_pad + r], yi = own[(size_t)PY * a.rows_pad + r];
+        const float zi = own[(size_t)PZ * a.rows_pad + r], ri = own[(size_t)PR * a.rows_pad + r];
+        const float vxi = own[(size_t)PVX * a.rows_pad + r], vyi = own[(size_t)PVY * a.rows_pad + r];
+        const float vzi = own[(size_t)PVZ * a.rows_pad + r];
+        const int islot = a.own_block * a.rows_pad + r;
+        const int total = a.world * a.rows_pad;
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+        for (int j = lane; j < total; j += 32) {
+            const int q = j / a.rows_pad;
+            const float* b = a.planes + ((size_t)q * NPLANES) * a.rows_pad + (j - q * a.rows_pad);
+            PairAcc acc = {0.0f, 0.0f, 0.0f};
+            pair_force<RADIUS, true>(xi, yi, zi, ri, vxi, vyi, vzi, b[(size_t)PX * a.rows_pad], b[(size_t)PY * a.rows_pad],
+                                     b[(size_t)PZ * a.rows_pad], b[(size_t)PR * a.rows_pad], b[(size_t)PVX * a.rows_pad],
+                                     b[(size_t)PVY * a.rows_pad], b[(size_t)PVZ * a.rows_pad], j == islot, a.pp, acc);
+            gx += (double)acc.gx;
+            gy += (double)acc.gy;
+            gz += (double)acc.gz;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            gz += __shfl_xor_sync(0xffffffffu, gz, o);
+        }
+        if (lane == src) {
+            sx = -gx;
+            sy = -gy;
+            sz = -gz;
+            atomicAdd(a.fixup_rows, 1ull);
+        }
+    }
+    if (live) {
+        a.f_ped[3 * (size_t)row + 0] = sx;
+        a.f_ped[3 * (size_t)row + 1] = sy;
+        a.f_ped[3 * (size_t)row + 2] = sz;
+    }
+}
+
+}  // namespace sfm

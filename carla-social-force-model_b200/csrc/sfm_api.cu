@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "k1_ped_pairs.cuh"
+#include "k1_sym.cuh"
 #include "k2_cells.cuh"
 #include "k3_integrate.cuh"
 
@@ -121,6 +122,10 @@ struct sfm_ctx {
     std::vector<cudaEvent_t> event_pool;
     int k1_target_ctas = 148 * 4 * 16;
     int k1_ir = 2, k1_minb = 5;     // tuning knobs (SFM_K1_IR, SFM_K1_MINB)
+    int k1_rows_mode = 0;           // SFM_K1_MODE=rows: ordered-pair row kernel instead of the symmetric one
+    DevBuf<long long> facc;         // [world * rows_pad][4] fixed-point force accumulators + poison counter
+    bool pairs_pending = false;
+    bool step_open = false;         // sfm_step_begin done, sfm_step_end outstanding     // symmetric accumulation launched, finish kernel not yet run
 };
 
 namespace {
@@ -266,7 +271,7 @@ int launch_stage(sfm_ctx* c) {
     return 0;
 }
 
-int launch_pairs(sfm_ctx* c) {
+int launch_pairs_rows(sfm_ctx* c) {
     if (!c->staged) SFM_TRY(launch_stage(c));
     const int IR = c->k1_ir;
     const int rows_per_cta = K1_THREADS * IR;
@@ -314,6 +319,60 @@ int launch_pairs(sfm_ctx* c) {
     c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     return 0;
+}
+
+// Symmetric pair kernel, phase 1: zero the fixed-point accumulators and add every tile pair this rank owns.
+int launch_pairs_accumulate(sfm_ctx* c) {
+    if (!c->staged) SFM_TRY(launch_stage(c));
+    const int own_tiles = (int)(c->rows_pad / K1_TJ);
+    const int total_tiles = own_tiles * c->world;
+    const size_t slots = (size_t)c->world * c->rows_pad;
+    SFM_TRY(c->facc.ensure(slots * 4));
+    const int half = std::max(1, total_tiles / 2);
+    int nsplit = std::max(1, cdiv(c->k1_target_ctas, own_tiles));
+    nsplit = std::min(nsplit, half);
+    c->nsplit = nsplit;
+    SymArgs a{};
+    a.planes = c->planes.p; a.rows_pad = (int)c->rows_pad; a.total_tiles = total_tiles;
+    a.own_first_tile = c->rank * own_tiles; a.facc = c->facc.p; a.pp = make_pair_params(c->params.ped);
+    SpanGuard g(c, ST_PAIRS);
+    SFM_CUDA(cudaMemsetAsync(c->facc.p, 0, slots * 4 * sizeof(long long), c->stream));
+    dim3 grid(own_tiles, nsplit);
+    if (c->params.use_ped_radius) k1_sym_pairs<true><<<grid, KS_THREADS, 0, c->stream>>>(a);
+    else k1_sym_pairs<false><<<grid, KS_THREADS, 0, c->stream>>>(a);
+    c->launches += 1;
+    c->pair_launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->pairs_pending = true;
+    return 0;
+}
+
+// Symmetric pair kernel, phase 2 (after the cross-rank reduce-scatter on multi-GPU runs): fixed point -> float64 force.
+int launch_pairs_finish(sfm_ctx* c) {
+    if (!c->pairs_pending) return 0;
+    SFM_TRY(c->f_ped.ensure((size_t)3 * std::max<int64_t>(c->n, 1)));
+    SFM_TRY(c->fixup_rows.ensure(1));
+    if (!c->fixup_zeroed) {
+        SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, sizeof(unsigned long long), c->stream));
+        c->fixup_zeroed = true;
+    }
+    FinishArgs f{};
+    f.planes = c->planes.p; f.rows_pad = (int)c->rows_pad; f.world = c->world; f.own_block = c->rank;
+    f.n_local = (int)c->n; f.facc_own = c->facc.p + (size_t)c->rank * c->rows_pad * 4; f.f_ped = c->f_ped.p;
+    f.fixup_rows = c->fixup_rows.p; f.pp = make_pair_params(c->params.ped);
+    SpanGuard g(c, ST_PAIRS);
+    if (c->params.use_ped_radius) k1_sym_finish<true><<<cdiv(c->n, 256), 256, 0, c->stream>>>(f);
+    else k1_sym_finish<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(f);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->pairs_pending = false;
+    return 0;
+}
+
+int launch_pairs(sfm_ctx* c) {
+    if (c->k1_rows_mode) return launch_pairs_rows(c);
+    SFM_TRY(launch_pairs_accumulate(c));
+    return launch_pairs_finish(c);
 }
 
 int rebin_peds(sfm_ctx* c) {
@@ -477,28 +536,36 @@ int ensure_force_buffers(sfm_ctx* c) {
     return 0;
 }
 
-// One tick on the device: all enabled forces, then K3.
-int step_once(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool keep_class_forces) {
+// First half of a tick: everything that does not need other ranks' force contributions -- the pair accumulation and
+// the three cell-list forces.
+int step_begin(sfm_ctx* c) {
     const sfm_params& P = c->params;
     SFM_TRY(ensure_force_buffers(c));
-    if (P.enable[SFM_FORCE_PEDESTRIAN]) SFM_TRY(launch_pairs(c));
+    if (P.enable[SFM_FORCE_PEDESTRIAN]) {
+        if (c->k1_rows_mode) SFM_TRY(launch_pairs_rows(c));
+        else SFM_TRY(launch_pairs_accumulate(c));
+    }
     const bool any_set = (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) ||
                          (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) ||
                          (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count);
     if (any_set && !c->perm_valid) SFM_TRY(rebin_peds(c));
-    StepArgs a = step_args(c);
-    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) {
-        SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0));
-        a.f_border = c->f_border.p;
-    }
-    if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) {
+    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0));
+    if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count)
         SFM_TRY(launch_segments(c, SFM_FORCE_STATIC_OBSTACLE, false, 0));
-        a.f_static = c->f_static.p;
-    }
-    if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count) {
+    if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count)
         SFM_TRY(launch_segments(c, SFM_FORCE_DYNAMIC_OBSTACLE, false, 0));
-        a.f_dynamic = c->f_dynamic.p;
-    }
+    c->step_open = true;
+    return 0;
+}
+
+// Second half: finish the pair force (after the reduce-scatter on multi-GPU runs), then K3.
+int step_end(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool keep_class_forces) {
+    const sfm_params& P = c->params;
+    if (P.enable[SFM_FORCE_PEDESTRIAN]) SFM_TRY(launch_pairs_finish(c));
+    StepArgs a = step_args(c);
+    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) a.f_border = c->f_border.p;
+    if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) a.f_static = c->f_static.p;
+    if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count) a.f_dynamic = c->f_dynamic.p;
     a.enable_accel = P.enable[SFM_FORCE_ACCELERATION];
     a.enable_ped = P.enable[SFM_FORCE_PEDESTRIAN];
     a.update_velocity = update_velocity;
@@ -514,7 +581,13 @@ int step_once(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool k
         c->steps += 1;
         c->perm_valid = false;      // positions moved; rebin before the next segment pass
     }
+    c->step_open = false;
     return 0;
+}
+
+int step_once(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool keep_class_forces) {
+    SFM_TRY(step_begin(c));
+    return step_end(c, update_velocity, integrate_positions, keep_class_forces);
 }
 
 int download3(sfm_ctx* c, const double* dev, int64_t n, double* out) {
@@ -557,6 +630,7 @@ int sfm_create(int device, sfm_ctx** out) {
     else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
     if (const char* env = std::getenv("SFM_K1_IR")) c->k1_ir = std::atoi(env) == 1 ? 1 : 2;
     if (const char* env = std::getenv("SFM_K1_MINB")) c->k1_minb = std::atoi(env);
+    if (const char* env = std::getenv("SFM_K1_MODE")) c->k1_rows_mode = std::strcmp(env, "rows") == 0;
     *out = c;
     return 0;
 }
@@ -572,7 +646,7 @@ int sfm_destroy(sfm_ctx* c) {
     c->f_total.release(); c->f_accel.release(); c->f_ped.release();
     c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
-    c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release();
+    c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release(); c->facc.release();
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -726,6 +800,8 @@ int sfm_force(sfm_ctx* c, int cls, int64_t n, double* out) {
     if (!out) return fail("null output");
     SFM_TRY(ensure_force_buffers(c));
     if (cls == SFM_FORCE_ACCELERATION || cls == SFM_FORCE_PEDESTRIAN) {
+        if (cls == SFM_FORCE_PEDESTRIAN && c->world > 1 && !c->k1_rows_mode)
+            return fail("the per-class pedestrian force of a multi-rank context needs the reduce-scatter; use the step API");
         if (cls == SFM_FORCE_PEDESTRIAN) SFM_TRY(launch_pairs(c));
         StepArgs a = step_args(c);
         a.enable_accel = cls == SFM_FORCE_ACCELERATION;
@@ -775,7 +851,8 @@ int sfm_step(sfm_ctx* c, int n_steps, int integrate_positions) {
     if (!c->have_params) return fail("sfm_set_params must be called first");
     if (n_steps < 0) return fail("negative step count");
     if (c->n == 0) return 0;                       // pedestrian_simulation.py:60 early-out
-    if (c->world > 1 && n_steps > 1) return fail("multi-rank contexts step once per all-gather");
+    if (c->world > 1)
+        return fail("multi-rank contexts step with sfm_step_begin / reduce-scatter / sfm_step_end / all-gather");
     for (int s = 0; s < n_steps; ++s) SFM_TRY(step_once(c, true, integrate_positions != 0, false));
     return 0;
 }
@@ -824,6 +901,31 @@ int sfm_gather_buffer(sfm_ctx* c, void** device_ptr, size_t* bytes_per_rank) {
     if (!c->planes.p) return fail("no state uploaded yet");
     *device_ptr = c->planes.p;
     *bytes_per_rank = sizeof(float) * NPLANES * (size_t)c->rows_pad;
+    return 0;
+}
+
+int sfm_step_begin(sfm_ctx* c) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (c->step_open) return fail("sfm_step_begin called twice without sfm_step_end");
+    if (c->n == 0 && c->world == 1) return 0;
+    return step_begin(c);
+}
+
+int sfm_step_end(sfm_ctx* c, int integrate_positions) {
+    SFM_TRY(check_ctx(c));
+    if (c->n == 0 && c->world == 1) return 0;
+    if (!c->step_open) return fail("sfm_step_end without sfm_step_begin");
+    return step_end(c, true, integrate_positions != 0, false);
+}
+
+int sfm_force_accumulator(sfm_ctx* c, void** device_ptr, size_t* bytes_per_rank) {
+    SFM_TRY(check_ctx(c));
+    if (!device_ptr || !bytes_per_rank) return fail("null pointer");
+    if (!c->planes.p) return fail("no state uploaded yet");
+    SFM_TRY(c->facc.ensure((size_t)c->world * c->rows_pad * 4));
+    *device_ptr = c->facc.p;
+    *bytes_per_rank = sizeof(long long) * 4 * (size_t)c->rows_pad;
     return 0;
 }
 

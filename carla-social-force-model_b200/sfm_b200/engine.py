@@ -1,9 +1,9 @@
 """Device-resident crowd engine: one process per GPU, pedestrians row-partitioned across the ranks of one box.
 
-Every force on pedestrian i needs i's own row plus read-only global data (all pedestrians' positions / velocities /
-radii, the replicated border and obstacle sets), so rows shard with exactly one exchange per step: an all-gather of
-each rank's staged block (32 B per pedestrian) through ``torch.distributed`` (NCCL over NVLink; gloo in the CPU
-tests).  torch is plumbing only -- streams, the process group and a tensor view of the library's gather buffer; all
+Rows shard: each rank owns the state, the cell-list forces and the integration of a contiguous row block.  The pair
+force is evaluated once per unordered pair by exactly one rank (half-shell over 256-row tiles), so a step has two
+exchanges through ``torch.distributed`` (NCCL over NVLink; gloo in the CPU tests): an integer reduce-scatter of the
+fixed-point force accumulators (32 B per pedestrian) and an all-gather of each rank's staged block (32 B per pedestrian).  torch is plumbing only -- streams, the process group and a tensor view of the library's gather buffer; all
 arithmetic runs in ``libsfm_b200.so``.
 """
 from __future__ import annotations
@@ -34,8 +34,8 @@ def padded_rows(bounds):
 class _DeviceView:
     """Minimal ``__cuda_array_interface__`` holder so torch can alias memory owned by the library."""
 
-    def __init__(self, ptr, n_float32):
-        self.__cuda_array_interface__ = {'shape': (n_float32,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+    def __init__(self, ptr, n_items, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': (n_items,), 'typestr': typestr, 'data': (ptr, False), 'version': 2}
 
 
 class Engine:
@@ -95,6 +95,10 @@ class Engine:
         view = _DeviceView(ptr, per_rank // 4 * self.world)
         self._gather = self.torch.as_tensor(view, device=f'cuda:{self.device}')
         self._per_rank = per_rank // 4
+        ptr, per_rank = self.ctx.force_accumulator()
+        view = _DeviceView(ptr, per_rank // 8 * self.world, '<i8')
+        self._facc = self.torch.as_tensor(view, device=f'cuda:{self.device}')
+        self._facc_per_rank = per_rank // 8
 
     def exchange(self):
         """All-gather every rank's staged block (in place: block r of the buffer is rank r's contribution)."""
@@ -104,13 +108,22 @@ class Engine:
         with self.torch.cuda.stream(self.stream):
             self.dist.all_gather_into_tensor(self._gather, mine, group=self.group)
 
+    def reduce_forces(self):
+        """Integer reduce-scatter of the fixed-point pair-force accumulators: every unordered pair was evaluated by
+        exactly one rank, which added it to both pedestrians' rows; block r of the sum belongs to rank r (in place)."""
+        mine = self._facc[self.rank * self._facc_per_rank:(self.rank + 1) * self._facc_per_rank]
+        with self.torch.cuda.stream(self.stream):
+            self.dist.reduce_scatter_tensor(mine, self._facc, group=self.group)
+
     # ---- stepping -------------------------------------------------------------------------------------------------
     def step(self, n_steps=1, integrate_positions=True):
         if self.world == 1:
             self.ctx.step(n_steps, integrate_positions)
             return
         for _ in range(n_steps):
-            self.ctx.step(1, integrate_positions)
+            self.ctx.step_begin()
+            self.reduce_forces()
+            self.ctx.step_end(integrate_positions)
             self.exchange()
 
     def tick_host(self, loc, vel, new_vel, new_loc=None):
@@ -121,7 +134,9 @@ class Engine:
         self.ctx.update_kinematics(loc, vel)        # refresh -> restage -> exchange -> step, so every rank sees the
         self.ctx.stage()                            # other ranks' refreshed rows
         self.exchange()
-        self.ctx.step(1, new_loc is not None)
+        self.ctx.step_begin()
+        self.reduce_forces()
+        self.ctx.step_end(new_loc is not None)
         self.ctx.download_state(new_loc if new_loc is not None else np.empty_like(new_vel), new_vel)
         self.exchange()
 

@@ -24,7 +24,8 @@ SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create'
            'sfm_synchronize', 'sfm_set_params', 'sfm_set_origin', 'sfm_set_partition', 'sfm_upload_state',
            'sfm_update_kinematics', 'sfm_update_targets', 'sfm_download_state', 'sfm_set_borders', 'sfm_set_obstacles',
            'sfm_force', 'sfm_enumerate_pairs', 'sfm_step', 'sfm_tick_host', 'sfm_download_force',
-           'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_stage', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats')
+           'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_stage', 'sfm_step_begin', 'sfm_step_end',
+           'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats')
 
 
 class SfmError(RuntimeError):
@@ -110,6 +111,9 @@ def lib():
         'sfm_download_class_force': (C.c_int, [p_ctx, C.c_int, i64, p_d]),
         'sfm_gather_buffer': (C.c_int, [p_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         'sfm_stage': (C.c_int, [p_ctx]),
+        'sfm_step_begin': (C.c_int, [p_ctx]),
+        'sfm_step_end': (C.c_int, [p_ctx, C.c_int]),
+        'sfm_force_accumulator': (C.c_int, [p_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         'sfm_set_profiling': (C.c_int, [p_ctx, C.c_int]),
         'sfm_reset_stats': (C.c_int, [p_ctx]),
         'sfm_get_stats': (C.c_int, [p_ctx, C.POINTER(Stats)]),
@@ -317,6 +321,17 @@ class Context:
     def gather_buffer(self):
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         _check(self._lib.sfm_gather_buffer(self._h, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def step_begin(self):
+        _check(self._lib.sfm_step_begin(self._h))
+
+    def step_end(self, integrate_positions=True):
+        _check(self._lib.sfm_step_end(self._h, int(bool(integrate_positions))))
+
+    def force_accumulator(self):
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        _check(self._lib.sfm_force_accumulator(self._h, C.byref(ptr), C.byref(nbytes)))
         return ptr.value, nbytes.value
 
     def stage(self):

@@ -130,6 +130,15 @@ int sfm_download_class_force(sfm_ctx* ctx, int force_class, int64_t n, double* o
 /* Device pointer of the gather buffer [world][8][rows_pad] float32, and the size of one rank's block in bytes.
  * After each sfm_step the caller all-gathers block `rank` into every rank's buffer (NCCL, in place). */
 int sfm_gather_buffer(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_rank);
+/* Multi-GPU tick in two halves.  sfm_step_begin enqueues the pair accumulation (each unordered pedestrian pair is
+ * evaluated once, by one rank, and contributes to both pedestrians' rows) and the cell-list forces; the caller then
+ * reduce-scatters (integer sum) the accumulator -- block `rank` of [world][rows_pad][4] int64 stays on rank `rank` -- and
+ * calls sfm_step_end (pair-force finish, K3), followed by the all-gather of the staged rows.  sfm_step == begin + end
+ * on single-rank contexts. */
+int sfm_step_begin(sfm_ctx* ctx);
+int sfm_step_end(sfm_ctx* ctx, int integrate_positions);
+/* Device pointer of the fixed-point force accumulator (int64 [world][rows_pad][4]) and the bytes of one rank block. */
+int sfm_force_accumulator(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_rank);
 /* Makes this rank's block of the gather buffer reflect the current master state (after an upload or refresh), so the
  * first all-gather can run before the first step. */
 int sfm_stage(sfm_ctx* ctx);

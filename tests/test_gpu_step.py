@@ -98,18 +98,32 @@ def test_two_rank_partition_emulated_on_one_gpu(sfm_config):
         ranks.append((ctx, view, per_rank // 4))
 
     def exchange():
-        for r, (ctx, view, per) in enumerate(ranks):
+        for ctx, _, _ in ranks:
             ctx.synchronize()
         for r, (_, view, per) in enumerate(ranks):
             other = ranks[1 - r][1]
             other[r * per:(r + 1) * per].copy_(view[r * per:(r + 1) * per])
         torch.cuda.synchronize()
 
+    def reduce_scatter():
+        views = []
+        for ctx, _, _ in ranks:
+            ctx.synchronize()
+            ptr, per = ctx.force_accumulator()
+            views.append((torch.as_tensor(engine._DeviceView(ptr, per // 8 * 2, '<i8'), device='cuda:0'), per // 8))
+        total = views[0][0] + views[1][0]
+        for r, (v, per) in enumerate(views):
+            v[r * per:(r + 1) * per].copy_(total[r * per:(r + 1) * per])
+        torch.cuda.synchronize()
+
     exchange()
     for step in range(3):
         whole.step(1, True)
         for ctx, _, _ in ranks:
-            ctx.step(1, True)
+            ctx.step_begin()
+        reduce_scatter()
+        for ctx, _, _ in ranks:
+            ctx.step_end(True)
         exchange()
     loc_w, vel_w = whole.download_state()
     loc_p = np.concatenate([ranks[r][0].download_state()[0] for r in range(2)])
