@@ -116,7 +116,7 @@ struct sfm_ctx {
     bool fixup_zeroed = false;
     // accounting
     bool profiling = false;
-    int64_t launches = 0, steps = 0, pair_launches = 0;
+    int64_t launches = 0, steps = 0, pair_launches = 0, pair_evals = 0;
     double ms[ST_COUNT] = {0, 0, 0, 0};
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -302,6 +302,7 @@ int launch_pairs_rows(sfm_ctx* c) {
 #undef SFM_K1_LAUNCH
     c->launches += 1;
     c->pair_launches += 1;
+    c->pair_evals += (int64_t)c->rows_pad * c->world * c->rows_pad;
     SFM_CUDA(cudaGetLastError());
     // reduce the split partials (and repair rows the unguarded fast path poisoned)
     SFM_TRY(c->f_ped.ensure((size_t)3 * std::max<int64_t>(c->n, 1)));
@@ -342,6 +343,11 @@ int launch_pairs_accumulate(sfm_ctx* c) {
     else k1_sym_pairs<false><<<grid, KS_THREADS, 0, c->stream>>>(a);
     c->launches += 1;
     c->pair_launches += 1;
+    for (int t = 0; t < own_tiles; ++t) {        // pair terms this launch evaluates: half shell + the diagonal tile
+        const int I = a.own_first_tile + t;
+        const int H = (total_tiles & 1) ? (total_tiles - 1) / 2 : ((I < total_tiles / 2) ? total_tiles / 2 : total_tiles / 2 - 1);
+        c->pair_evals += (int64_t)(H + 1) * K1_TJ * K1_TJ;
+    }
     SFM_CUDA(cudaGetLastError());
     c->pairs_pending = true;
     return 0;
@@ -947,7 +953,7 @@ int sfm_set_profiling(sfm_ctx* c, int enabled) {
 int sfm_reset_stats(sfm_ctx* c) {
     SFM_TRY(check_ctx(c));
     SFM_TRY(drain_spans(c));
-    c->launches = c->steps = c->pair_launches = 0;
+    c->launches = c->steps = c->pair_launches = c->pair_evals = 0;
     for (double& m : c->ms) m = 0.0;
     c->fixup_zeroed = false;
     return 0;
@@ -961,6 +967,7 @@ int sfm_get_stats(sfm_ctx* c, sfm_stats* out) {
     out->ms_pairs = c->ms[ST_PAIRS]; out->ms_cells = c->ms[ST_CELLS]; out->ms_segments = c->ms[ST_SEGMENTS];
     out->ms_integrate = c->ms[ST_INTEGRATE];
     out->fixup_rows = 0;
+    out->pair_evaluations = c->pair_evals;
     if (c->fixup_rows.p && c->fixup_zeroed) {
         unsigned long long v = 0;
         SFM_CUDA(cudaMemcpyAsync(&v, c->fixup_rows.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));

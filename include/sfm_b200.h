@@ -69,6 +69,7 @@ typedef struct {
     double ms_integrate;                  /* K3 acceleration + sum + clamp + Euler + restaging */
     int64_t pair_launches;                /* number of K1 launches inside ms_pairs */
     int64_t fixup_rows;                   /* rows the degenerate-pair repair path recomputed (0 for healthy crowds) */
+    int64_t pair_evaluations;             /* pair terms K1 evaluated (padded slots included; one per unordered pair) */
 } sfm_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
