@@ -37,6 +37,7 @@ for p in (ROOT, PKG):
 import numpy as np                     # noqa: E402
 
 K1_INSTR_PER_PAIR = 58                 # FP32-pipe instructions per ordered pair (81 FLOP, 5 MUFU)
+K1_INSTR_PER_PAIR_2D = 48              # same table: the 2-D / radius-off specialisation (what a flat crowd needs)
 # K3 algorithmic bytes per agent-step: read loc+r 32, vel+speed 32, waypoint 16, pair force 12, three
 # cell-list forces 3 x 16; write loc 32, vel 32, float32 staging planes 28, total force 24
 K3_BYTES_PER_AGENT = 32 + 32 + 16 + 12 + 48 + 32 + 32 + 28 + 24
@@ -181,7 +182,7 @@ def run_ours(args, world, rank, local_rank):
             torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------------------------------
-    for _ in range(args.warmup):
+    for _ in range(args.warmup + (3 if world > 1 else 0)):     # NCCL builds its channels lazily: a few extra untimed steps
         e.step(1, True)
     barrier()
     ctx.reset_stats()
@@ -241,13 +242,30 @@ def run_ours(args, world, rank, local_rank):
         peaks, peak_kind = measured_peaks()
         sm_max_hz = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
         fp32_peak = SMS * LANES * sm_max_hz / 1e12                      # T FP32-pipe lane-instructions / s
-        k1_ms = ms_pairs / max(stats['pair_launches'], 1)
+        k1_ms_in_step = ms_pairs / max(stats['pair_launches'], 1)       # overlapped with the cell-list kernels
+        k1_evals = stats['pair_evaluations'] / max(stats['pair_launches'], 1)
+        k1_ms = k1_ms_in_step
+        if world == 1:
+            # the pair kernel timed alone (CUDA events on the launch stream): inside the step it shares the SMs with
+            # the concurrently running FP64 cell-list kernels, which inflates its span
+            ctx.reset_stats()
+            ctx.set_profiling(True)
+            scratch = np.empty((rows, 3))
+            for _ in range(5):
+                with torch.cuda.stream(stream):
+                    flush.fill_(1)
+                ctx.force(1, scratch)
+            iso = ctx.stats()
+            ctx.set_profiling(False)
+            k1_ms = iso['ms_pairs'] / max(iso['pair_launches'], 1)
+            k1_evals = iso['pair_evaluations'] / max(iso['pair_launches'], 1)
         # pair terms the launch actually evaluates (the symmetric kernel visits every unordered pair once and applies it
         # to both rows; padded slots included) -- this is what occupies the pipes -- and the ordered pairs it covers
-        k1_evals = stats['pair_evaluations'] / max(stats['pair_launches'], 1)
+        flat = bool(np.all(w.loc[:, 2] == w.loc[0, 2]) and not np.any(w.vel[:, 2])) and not cfg.get('use_ped_radius', False)
+        instr = K1_INSTR_PER_PAIR_2D if flat else K1_INSTR_PER_PAIR
         k1_rate = k1_evals / (k1_ms * 1e-3)
         k1_ordered_rate = (e.hi - e.lo) * (n - 1) / (k1_ms * 1e-3)
-        achieved = k1_rate * K1_INSTR_PER_PAIR / 1e12
+        achieved = k1_rate * instr / 1e12
         traffic = None
         prof = os.path.join(ROOT, 'profiles', 'k1_ncu_summary.json')
         if os.path.exists(prof):
@@ -273,11 +291,13 @@ def run_ours(args, world, rank, local_rank):
                          'unit': 'T FP32-pipe instr/s', 'frac': achieved / fp32_peak, 'traffic': traffic,
                          'kernel': 'k1_sym_pairs (+ accumulator zero/finish)', 'ms_per_launch': k1_ms,
                          'pair_terms_evaluated_per_s': k1_rate, 'ordered_pairs_covered_per_s': k1_ordered_rate,
-                         'frac_ordered_equivalent': k1_ordered_rate * K1_INSTR_PER_PAIR / 1e12 / fp32_peak,
+                         'frac_ordered_equivalent': k1_ordered_rate * instr / 1e12 / fp32_peak,
+                         'ms_per_launch_inside_step': k1_ms_in_step, 'instr_per_pair': instr,
                          'note': 'f_ji = -f_ij exactly, so each unordered pair is evaluated once: achieved/frac count '
                                  'the evaluated pair terms (hardware utilisation); the ordered-pair figures are the '
                                  'useful work the metric counts',
-                         'algorithmic': f'{K1_INSTR_PER_PAIR} FP32-pipe instr (81 FLOP, 5 MUFU) per ordered pair',
+                         'algorithmic': (f'{instr} FP32-pipe instr per pair term (SURVEY 8d: 58 = 3-D radius-on, 81 FLOP, '
+                                         '5 MUFU; 48 = the 2-D radius-off specialisation a flat crowd takes)'),
                          'peak_source': f'148 SM x 128 lanes x sm_max_mhz ({peak_kind} MEASURED_PEAKS.json clock); '
                                         'FFMA microbenchmark on this pool: 33.2 T/s (profiles/microbench)'},
             'roofline_hbm': {'bound': 'hbm', 'kernel': 'k3_integrate', 'achieved': k3_gbs,

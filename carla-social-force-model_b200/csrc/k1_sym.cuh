@@ -24,6 +24,7 @@ namespace sfm {
 constexpr int KS_THREADS = 128;
 constexpr int KS_IR = 2;
 constexpr int KS_QUADS = K1_TJ / 4;
+constexpr int KS_PLANES = 8;                             // PX..PVZ + the per-row non-planar flag (PSPARE)
 constexpr float KS_FIXED_SCALE = 4294967296.0f;          // 2^32 counts per m/s^2
 constexpr float KS_FIXED_LIMIT = 1.0e9f;                 // |partial| beyond this goes to the repair path
 
@@ -37,19 +38,30 @@ struct SymArgs {
 };
 
 // -f_ij for two consecutive j at once: g = (a Dx - b Dy, a Dy + b Dx, a Dz); F_i -= g, F_j += g.
-template <bool RADIUS>
+template <bool RADIUS, bool PLANAR>
 __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, const f32x2 zi, const f32x2 ri,
                                             const f32x2 vxi, const f32x2 vyi, const f32x2 vzi, const f32x2 xj,
                                             const f32x2 yj, const f32x2 zj, const f32x2 rj, const f32x2 vxj,
                                             const f32x2 vyj, const f32x2 vzj, const PackedConst& c, f32x2& gx, f32x2& gy,
                                             f32x2& gz) {
-    const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi), dz = sub2(zj, zi);
-    const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    // PLANAR: every pedestrian of both tiles has the same z and no vertical velocity, so d_z = w_z = D_z = 0 exactly
+    const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi);
+    f32x2 dz = 0ull, wz = 0ull, Dz = 0ull;
+    f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
+    if (!PLANAR) {
+        dz = sub2(zj, zi);
+        d2 = fma2(dz, dz, d2);
+    }
     const f32x2 rinv = rsqrt2(d2);
     const f32x2 dist = mul2(d2, rinv);
-    const f32x2 wx = sub2(vxi, vxj), wy = sub2(vyi, vyj), wz = sub2(vzi, vzj);
-    const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy), Dz = fma2(dz, rinv, wz);
-    const f32x2 D2 = fma2(Dz, Dz, fma2(Dy, Dy, mul2(Dx, Dx)));
+    const f32x2 wx = sub2(vxi, vxj), wy = sub2(vyi, vyj);
+    const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy);
+    f32x2 D2 = fma2(Dy, Dy, mul2(Dx, Dx));
+    if (!PLANAR) {
+        wz = sub2(vzi, vzj);
+        Dz = fma2(dz, rinv, wz);
+        D2 = fma2(Dz, Dz, D2);
+    }
     const f32x2 Dinv = rsqrt2(D2);
     const f32x2 Dn = mul2(D2, Dinv);
     const f32x2 cross = fma2(wx, dy, neg2(mul2(wy, dx)));
@@ -85,15 +97,78 @@ __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, cons
     const f32x2 b = mul2(e2, Dinv) | (thp & 0x8000000080000000ULL);      // copysign(e2 / |D|, theta')
     gx = fma2(a, Dx, mul2(neg2(b), Dy));
     gy = fma2(a, Dy, mul2(b, Dx));
-    gz = mul2(a, Dz);
+    gz = PLANAR ? 0ull : mul2(a, Dz);
 }
 
 __device__ __forceinline__ bool fixed_ok(float v) { return fabsf(v) < KS_FIXED_LIMIT; }     // false for NaN / inf too
 __device__ __forceinline__ long long to_fixed(float v) { return __float2ll_rn(v * KS_FIXED_SCALE); }
 
+// One partner tile against this thread's rows: accumulates -F_i partials in registers (returned in gi) and +g into the
+// warp's private J-side slice.  Lanes are staggered over the j-quads so no two lanes of a warp touch the same j.
+template <bool RADIUS, bool PLANAR>
+__device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], float (*__restrict__ accw)[K1_TJ],
+                                         const int lane, const f32x2 (&xi2)[KS_IR], const f32x2 (&yi2)[KS_IR],
+                                         const f32x2 (&zi2)[KS_IR], const f32x2 (&ri2)[KS_IR],
+                                         const f32x2 (&vxi2)[KS_IR], const f32x2 (&vyi2)[KS_IR],
+                                         const f32x2 (&vzi2)[KS_IR], const PackedConst& pc, float (&gi)[KS_IR][3]) {
+    f32x2 Gx[KS_IR], Gy[KS_IR], Gz[KS_IR];
+#pragma unroll
+    for (int r = 0; r < KS_IR; ++r) Gx[r] = Gy[r] = Gz[r] = 0ull;
+#pragma unroll 1
+    for (int step = 0; step < KS_QUADS; ++step) {
+        const int j = ((step + lane) & (KS_QUADS - 1)) * 4;          // staggered: distinct j per lane
+        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tl[PX][j]);
+        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&tl[PY][j]);
+        ulonglong2 Z = make_ulonglong2(0ull, 0ull), VZ = make_ulonglong2(0ull, 0ull), R = make_ulonglong2(0ull, 0ull);
+        if (!PLANAR) {
+            Z = *reinterpret_cast<const ulonglong2*>(&tl[PZ][j]);
+            VZ = *reinterpret_cast<const ulonglong2*>(&tl[PVZ][j]);
+        }
+        if (RADIUS) R = *reinterpret_cast<const ulonglong2*>(&tl[PR][j]);
+        const ulonglong2 VX = *reinterpret_cast<const ulonglong2*>(&tl[PVX][j]);
+        const ulonglong2 VY = *reinterpret_cast<const ulonglong2*>(&tl[PVY][j]);
+        f32x2 jx0 = 0ull, jy0 = 0ull, jz0 = 0ull, jx1 = 0ull, jy1 = 0ull, jz1 = 0ull;   // sum over my rows
+#pragma unroll
+        for (int r = 0; r < KS_IR; ++r) {
+            f32x2 gx, gy, gz;
+            pair_terms2<RADIUS, PLANAR>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.x, Y.x, Z.x, R.x,
+                                        VX.x, VY.x, VZ.x, pc, gx, gy, gz);
+            Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
+            jx0 = r ? add2(jx0, gx) : gx; jy0 = r ? add2(jy0, gy) : gy;
+            if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz0 = r ? add2(jz0, gz) : gz; }
+            pair_terms2<RADIUS, PLANAR>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.y, Y.y, Z.y, R.y,
+                                        VX.y, VY.y, VZ.y, pc, gx, gy, gz);
+            Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
+            jx1 = r ? add2(jx1, gx) : gx; jy1 = r ? add2(jy1, gy) : gy;
+            if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz1 = r ? add2(jz1, gz) : gz; }
+        }
+        // J side: F_j += g, into this warp's private slice (lanes hold distinct j, so plain read-modify-write)
+        ulonglong2* ax = reinterpret_cast<ulonglong2*>(&accw[0][j]);
+        ulonglong2* ay = reinterpret_cast<ulonglong2*>(&accw[1][j]);
+        ulonglong2 vx = *ax, vy = *ay;
+        vx.x = add2(vx.x, jx0); vx.y = add2(vx.y, jx1);
+        vy.x = add2(vy.x, jy0); vy.y = add2(vy.y, jy1);
+        *ax = vx; *ay = vy;
+        if (!PLANAR) {
+            ulonglong2* az = reinterpret_cast<ulonglong2*>(&accw[2][j]);
+            ulonglong2 vz = *az;
+            vz.x = add2(vz.x, jz0); vz.y = add2(vz.y, jz1);
+            *az = vz;
+        }
+        __syncwarp();                                   // next step another lane owns this quad
+    }
+#pragma unroll
+    for (int r = 0; r < KS_IR; ++r) {
+        float lo, hi;
+        unpack2(Gx[r], lo, hi); gi[r][0] = lo + hi;
+        unpack2(Gy[r], lo, hi); gi[r][1] = lo + hi;
+        unpack2(Gz[r], lo, hi); gi[r][2] = lo + hi;
+    }
+}
+
 template <bool RADIUS>
 __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
-    __shared__ __align__(128) float tile[K1_STAGES][K1_PLANES][K1_TJ];
+    __shared__ __align__(128) float tile[K1_STAGES][KS_PLANES][K1_TJ];
     __shared__ __align__(16) float accj[KS_THREADS / 32][3][K1_TJ];
     __shared__ __align__(8) uint64_t bar[K1_STAGES];
 
@@ -125,9 +200,9 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
         const int q = t / tiles_per_rank;
         const int off = (t - q * tiles_per_rank) * K1_TJ;
         const float* src = a.planes + ((size_t)q * NPLANES) * a.rows_pad + off;
-        mbar_expect_tx(&bar[stage], K1_PLANES * K1_TJ * sizeof(float));
+        mbar_expect_tx(&bar[stage], KS_PLANES * K1_TJ * sizeof(float));
 #pragma unroll
-        for (int p = 0; p < K1_PLANES; ++p)
+        for (int p = 0; p < KS_PLANES; ++p)
             bulk_copy_g2s(&tile[stage][p][0], src + (size_t)p * a.rows_pad, K1_TJ * sizeof(float), &bar[stage]);
     };
     if (tid == 0) issue(item_tile(0), 0);
@@ -155,6 +230,11 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
         bad[r] = 0;
     }
     const PackedConst pc = make_packed_const(a.pp);
+    // planar fast path: K3 flags every staged row whose z (relative to the origin) or vertical velocity is non-zero
+    int own_flag = 0;
+#pragma unroll
+    for (int r = 0; r < KS_IR; ++r) own_flag |= (own[(size_t)PSPARE * a.rows_pad + r * KS_THREADS + tid] != 0.0f);
+    const bool planar_own = __syncthreads_or(own_flag) == 0;
 
     for (int k = 0; k < n_items; ++k) {
         const int stage = k & 1;
@@ -162,6 +242,8 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
         if (tid == 0 && k + 1 < n_items) issue(item_tile(k + 1), stage ^ 1);   // stage^1 was released by the barriers below
         while (!mbar_try_wait(&bar[stage], (k >> 1) & 1)) {}
         float gi[KS_IR][3];                                   // this tile's -F_i partial per row
+        const bool tile_nonplanar =
+            __syncthreads_or((tile[stage][PSPARE][tid] != 0.0f) | (tile[stage][PSPARE][tid + KS_THREADS] != 0.0f)) != 0;
         if (J == I) {
             // diagonal tile: guarded asymmetric evaluation with self pairs removed, rows of I only
             PairAcc acc[KS_IR];
@@ -171,57 +253,16 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
                 acc[r].gx = acc[r].gy = acc[r].gz = 0.0f;
                 self_j[r] = r * KS_THREADS + tid;
             }
-            tile_pairs<KS_IR, RADIUS, true>(tile[stage], xi, yi, zi, ri, vxi, vyi, vzi, self_j, a.pp, acc);
+            tile_pairs<KS_IR, RADIUS, true>(reinterpret_cast<const float (*)[K1_TJ]>(&tile[stage][0][0]), xi, yi, zi, ri, vxi,
+                                            vyi, vzi, self_j, a.pp, acc);
 #pragma unroll
             for (int r = 0; r < KS_IR; ++r) { gi[r][0] = acc[r].gx; gi[r][1] = acc[r].gy; gi[r][2] = acc[r].gz; }
             __syncthreads();
         } else {
-            f32x2 Gx[KS_IR], Gy[KS_IR], Gz[KS_IR];
-#pragma unroll
-            for (int r = 0; r < KS_IR; ++r) Gx[r] = Gy[r] = Gz[r] = 0ull;
-            const float (*tl)[K1_TJ] = tile[stage];
-#pragma unroll 1
-            for (int step = 0; step < KS_QUADS; ++step) {
-                const int j = ((step + lane) & (KS_QUADS - 1)) * 4;          // staggered: distinct j per lane
-                const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tl[PX][j]);
-                const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&tl[PY][j]);
-                const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&tl[PZ][j]);
-                ulonglong2 R = make_ulonglong2(0ull, 0ull);
-                if (RADIUS) R = *reinterpret_cast<const ulonglong2*>(&tl[PR][j]);
-                const ulonglong2 VX = *reinterpret_cast<const ulonglong2*>(&tl[PVX][j]);
-                const ulonglong2 VY = *reinterpret_cast<const ulonglong2*>(&tl[PVY][j]);
-                const ulonglong2 VZ = *reinterpret_cast<const ulonglong2*>(&tl[PVZ][j]);
-                f32x2 jx0 = 0ull, jy0 = 0ull, jz0 = 0ull, jx1 = 0ull, jy1 = 0ull, jz1 = 0ull;   // sum over my rows
-#pragma unroll
-                for (int r = 0; r < KS_IR; ++r) {
-                    f32x2 gx, gy, gz;
-                    pair_terms2<RADIUS>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.x, Y.x, Z.x, R.x,
-                                        VX.x, VY.x, VZ.x, pc, gx, gy, gz);
-                    Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy); Gz[r] = add2(Gz[r], gz);
-                    jx0 = r ? add2(jx0, gx) : gx; jy0 = r ? add2(jy0, gy) : gy; jz0 = r ? add2(jz0, gz) : gz;
-                    pair_terms2<RADIUS>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.y, Y.y, Z.y, R.y,
-                                        VX.y, VY.y, VZ.y, pc, gx, gy, gz);
-                    Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy); Gz[r] = add2(Gz[r], gz);
-                    jx1 = r ? add2(jx1, gx) : gx; jy1 = r ? add2(jy1, gy) : gy; jz1 = r ? add2(jz1, gz) : gz;
-                }
-                // J side: F_j += g, into this warp's private slice (lanes hold distinct j, so plain read-modify-write)
-                ulonglong2* ax = reinterpret_cast<ulonglong2*>(&accj[wid][0][j]);
-                ulonglong2* ay = reinterpret_cast<ulonglong2*>(&accj[wid][1][j]);
-                ulonglong2* az = reinterpret_cast<ulonglong2*>(&accj[wid][2][j]);
-                ulonglong2 vx = *ax, vy = *ay, vz = *az;
-                vx.x = add2(vx.x, jx0); vx.y = add2(vx.y, jx1);
-                vy.x = add2(vy.x, jy0); vy.y = add2(vy.y, jy1);
-                vz.x = add2(vz.x, jz0); vz.y = add2(vz.y, jz1);
-                *ax = vx; *ay = vy; *az = vz;
-                __syncwarp();                                   // next step another lane owns this quad
-            }
-#pragma unroll
-            for (int r = 0; r < KS_IR; ++r) {
-                float lo, hi;
-                unpack2(Gx[r], lo, hi); gi[r][0] = lo + hi;
-                unpack2(Gy[r], lo, hi); gi[r][1] = lo + hi;
-                unpack2(Gz[r], lo, hi); gi[r][2] = lo + hi;
-            }
+            if (planar_own && !tile_nonplanar)
+                sym_tile<RADIUS, true>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, gi);
+            else
+                sym_tile<RADIUS, false>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, gi);
             __syncthreads();                                    // every warp's J-side slice is complete
             // flush the J side: sum the warps' slices in fixed order, fixed-point atomics into the global accumulator
             for (int e = tid; e < K1_TJ; e += KS_THREADS) {

@@ -49,6 +49,8 @@ __device__ __forceinline__ void stage_row(float* planes, int64_t rows_pad, int64
     planes[PVX * rows_pad + i] = (float)(a.lambda_ped * vx);
     planes[PVY * rows_pad + i] = (float)(a.lambda_ped * vy);
     planes[PVZ * rows_pad + i] = (float)(a.lambda_ped * vz);
+    // non-planar flag read by the symmetric pair kernel (its z-free fast path needs z == origin and v_z == 0)
+    planes[PSPARE * rows_pad + i] = ((float)(z - a.oz) != 0.0f || (float)(a.lambda_ped * vz) != 0.0f) ? 1.0f : 0.0f;
 }
 
 __device__ __forceinline__ void stage_pad(float* planes, int64_t rows_pad, int64_t i) {
@@ -59,6 +61,7 @@ __device__ __forceinline__ void stage_pad(float* planes, int64_t rows_pad, int64
     planes[PVX * rows_pad + i] = 0.0f;
     planes[PVY * rows_pad + i] = 0.0f;
     planes[PVZ * rows_pad + i] = 0.0f;
+    planes[PSPARE * rows_pad + i] = 0.0f;
 }
 
 // Staging only: master state -> float32 planes (after an upload or a kinematics refresh).

@@ -82,9 +82,13 @@ struct SetStorage {
 struct sfm_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t aux_stream = nullptr;       // cell-list kernels run here, concurrently with the pair kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true, join_pending = false;
     sfm_params params{};
     bool have_params = false;
     double ox = 0.0, oy = 0.0, oz = 0.0;
+    bool origin_set = false;        // false: oz follows the first pedestrian's z so flat crowds take the planar path
     int world = 1, rank = 0;
     int64_t rows_pad = 0;
     bool partition_fixed = false;
@@ -133,7 +137,8 @@ namespace {
 struct SpanGuard {
     sfm_ctx* c;
     int idx = -1;
-    SpanGuard(sfm_ctx* ctx, int cls) : c(ctx) {
+    cudaStream_t st;
+    SpanGuard(sfm_ctx* ctx, int cls, cudaStream_t stream = nullptr) : c(ctx), st(stream ? stream : ctx->stream) {
         if (!c->profiling) return;
         TimedSpan sp;
         auto get = [&]() {
@@ -145,12 +150,12 @@ struct SpanGuard {
         sp.start = get();
         sp.stop = get();
         sp.cls = cls;
-        cudaEventRecord(sp.start, c->stream);
+        cudaEventRecord(sp.start, st);
         c->spans.push_back(sp);
         idx = (int)c->spans.size() - 1;
     }
     ~SpanGuard() {
-        if (idx >= 0) cudaEventRecord(c->spans[idx].stop, c->stream);
+        if (idx >= 0) cudaEventRecord(c->spans[idx].stop, st);
     }
 };
 
@@ -381,18 +386,19 @@ int launch_pairs(sfm_ctx* c) {
     return launch_pairs_finish(c);
 }
 
-int rebin_peds(sfm_ctx* c) {
+int rebin_peds(sfm_ctx* c, cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
     const int n = (int)c->n;
     SFM_TRY(c->perm.ensure(n));
     SFM_TRY(c->ped_cell.ensure(n));
     SFM_TRY(c->ped_start.ensure(c->ped_cells + 1));
     SFM_TRY(c->ped_cursor.ensure(c->ped_cells + 1));
-    SpanGuard g(c, ST_CELLS);
-    SFM_CUDA(cudaMemsetAsync(c->ped_start.p, 0, sizeof(int) * (c->ped_cells + 1), c->stream));
-    SFM_CUDA(cudaMemsetAsync(c->ped_cursor.p, 0, sizeof(int) * (c->ped_cells + 1), c->stream));
-    k2_ped_count<<<cdiv(n, 256), 256, 0, c->stream>>>(c->locr.p, n, c->ped_grid, c->ped_cell.p, c->ped_start.p);
-    k2_exclusive_scan<<<1, 1024, 0, c->stream>>>(c->ped_start.p, c->ped_cells + 1);
-    k2_ped_fill<<<cdiv(n, 256), 256, 0, c->stream>>>(c->ped_cell.p, n, c->ped_start.p, c->ped_cursor.p, c->perm.p);
+    SpanGuard g(c, ST_CELLS, st);
+    SFM_CUDA(cudaMemsetAsync(c->ped_start.p, 0, sizeof(int) * (c->ped_cells + 1), st));
+    SFM_CUDA(cudaMemsetAsync(c->ped_cursor.p, 0, sizeof(int) * (c->ped_cells + 1), st));
+    k2_ped_count<<<cdiv(n, 256), 256, 0, st>>>(c->locr.p, n, c->ped_grid, c->ped_cell.p, c->ped_start.p);
+    k2_exclusive_scan<<<1, 1024, 0, st>>>(c->ped_start.p, c->ped_cells + 1);
+    k2_ped_fill<<<cdiv(n, 256), 256, 0, st>>>(c->ped_cell.p, n, c->ped_start.p, c->ped_cursor.p, c->perm.p);
     c->launches += 3;
     SFM_CUDA(cudaGetLastError());
     c->perm_valid = true;
@@ -502,20 +508,21 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
     return 0;
 }
 
-int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity) {
+int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaStream_t strm = nullptr) {
+    if (!strm) strm = c->stream;
     SetStorage& st = (cls == SFM_FORCE_BORDER) ? c->borders : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->stat : c->dyn);
     DevBuf<double2>& out = (cls == SFM_FORCE_BORDER) ? c->f_border
                                                      : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->f_static : c->f_dynamic);
     const int n = (int)c->n;
     SFM_TRY(out.ensure(n));
     if (st.s.count == 0) {       // forces.py:140-141, :209-210: zeros
-        SpanGuard g(c, ST_SEGMENTS);
-        k2_zero<<<cdiv(n, 256), 256, 0, c->stream>>>(out.p, n);
+        SpanGuard g(c, ST_SEGMENTS, strm);
+        k2_zero<<<cdiv(n, 256), 256, 0, strm>>>(out.p, n);
         c->launches += 1;
         SFM_CUDA(cudaGetLastError());
         return 0;
     }
-    if (!c->perm_valid) SFM_TRY(rebin_peds(c));
+    if (!c->perm_valid) SFM_TRY(rebin_peds(c, strm));
     SegArgs a{};
     a.locr = c->locr.p; a.vels = c->vels.p; a.mode = c->mode.p; a.perm = c->perm.p; a.n = n;
     a.center = st.s.center; a.cutoff = st.s.cutoff; a.velocity = st.s.velocity; a.offset = st.s.offset;
@@ -527,9 +534,9 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity) {
     if (emit) {
         a.emit = c->emit.p; a.emit_count = c->emit_count.p; a.emit_capacity = emit_capacity;
     }
-    SpanGuard g(c, ST_SEGMENTS);
-    if (cls == SFM_FORCE_BORDER) k2_segments<0><<<cdiv(n, 32), K2_THREADS, 0, c->stream>>>(a);
-    else k2_segments<1><<<cdiv(n, 32), K2_THREADS, 0, c->stream>>>(a);
+    SpanGuard g(c, ST_SEGMENTS, strm);
+    if (cls == SFM_FORCE_BORDER) k2_segments<0><<<cdiv(n, 32), K2_THREADS, 0, strm>>>(a);
+    else k2_segments<1><<<cdiv(n, 32), K2_THREADS, 0, strm>>>(a);
     c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     return 0;
@@ -547,19 +554,31 @@ int ensure_force_buffers(sfm_ctx* c) {
 int step_begin(sfm_ctx* c) {
     const sfm_params& P = c->params;
     SFM_TRY(ensure_force_buffers(c));
+    const bool any_set = (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) ||
+                         (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) ||
+                         (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count);
+    // The cell-list kernels are FP64 / latency bound, the pair kernel FP32 issue bound: run them concurrently.  The
+    // auxiliary (high-priority) stream forks from the main stream here and is joined before K3.
+    cudaStream_t st2 = c->stream;
+    if (any_set && c->overlap && P.enable[SFM_FORCE_PEDESTRIAN]) {
+        st2 = c->aux_stream;
+        SFM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        SFM_CUDA(cudaStreamWaitEvent(st2, c->ev_fork, 0));
+    }
+    if (any_set && !c->perm_valid) SFM_TRY(rebin_peds(c, st2));
+    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0, st2));
+    if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count)
+        SFM_TRY(launch_segments(c, SFM_FORCE_STATIC_OBSTACLE, false, 0, st2));
+    if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count)
+        SFM_TRY(launch_segments(c, SFM_FORCE_DYNAMIC_OBSTACLE, false, 0, st2));
+    if (st2 != c->stream) {
+        SFM_CUDA(cudaEventRecord(c->ev_join, st2));
+        c->join_pending = true;
+    }
     if (P.enable[SFM_FORCE_PEDESTRIAN]) {
         if (c->k1_rows_mode) SFM_TRY(launch_pairs_rows(c));
         else SFM_TRY(launch_pairs_accumulate(c));
     }
-    const bool any_set = (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) ||
-                         (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) ||
-                         (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count);
-    if (any_set && !c->perm_valid) SFM_TRY(rebin_peds(c));
-    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0));
-    if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count)
-        SFM_TRY(launch_segments(c, SFM_FORCE_STATIC_OBSTACLE, false, 0));
-    if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count)
-        SFM_TRY(launch_segments(c, SFM_FORCE_DYNAMIC_OBSTACLE, false, 0));
     c->step_open = true;
     return 0;
 }
@@ -568,6 +587,10 @@ int step_begin(sfm_ctx* c) {
 int step_end(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool keep_class_forces) {
     const sfm_params& P = c->params;
     if (P.enable[SFM_FORCE_PEDESTRIAN]) SFM_TRY(launch_pairs_finish(c));
+    if (c->join_pending) {
+        SFM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        c->join_pending = false;
+    }
     StepArgs a = step_args(c);
     if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) a.f_border = c->f_border.p;
     if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) a.f_static = c->f_static.p;
@@ -632,6 +655,12 @@ int sfm_create(int device, sfm_ctx** out) {
     c->device = device;
     SFM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    int prio_lo = 0, prio_hi = 0;
+    SFM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SFM_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi));
+    SFM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    SFM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if (const char* env = std::getenv("SFM_OVERLAP")) c->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K1_TARGET_CTAS")) c->k1_target_ctas = std::max(1, std::atoi(env));
     else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
     if (const char* env = std::getenv("SFM_K1_IR")) c->k1_ir = std::atoi(env) == 1 ? 1 : 2;
@@ -654,6 +683,9 @@ int sfm_destroy(sfm_ctx* c) {
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
     c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release(); c->facc.release();
     cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->aux_stream);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
     delete c;
     return 0;
 }
@@ -690,6 +722,7 @@ int sfm_set_params(sfm_ctx* c, const sfm_params* p) {
 int sfm_set_origin(sfm_ctx* c, double ox, double oy, double oz) {
     SFM_TRY(check_ctx(c));
     c->ox = ox; c->oy = oy; c->oz = oz;
+    c->origin_set = true;
     c->staged = false;
     return 0;
 }
@@ -729,6 +762,7 @@ int sfm_upload_state(sfm_ctx* c, int64_t n, const double* loc, const double* vel
     c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     plan_ped_grid(c, n, loc);
+    if (!c->origin_set && c->world == 1) c->oz = loc[2];
     SFM_CUDA(cudaStreamSynchronize(c->stream));      // host arrays may be released by the caller on return
     return 0;
 }

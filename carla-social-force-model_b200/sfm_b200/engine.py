@@ -70,6 +70,8 @@ class Engine:
         lo, hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
         if self.world > 1:
             self.ctx.set_partition(self.world, self.rank, padded_rows(self.bounds))
+        # one origin for every rank; z of the first pedestrian, so a flat crowd stages z = 0 (planar fast path)
+        self.ctx.set_origin(0.0, 0.0, float(w.loc[0, 2]) if w.n else 0.0)
         self.ctx.upload_state(w.loc[lo:hi], w.vel[lo:hi], w.next_waypoint[lo:hi], w.radius[lo:hi],
                               w.target_speed[lo:hi], w.mode[lo:hi])
         self.lo, self.hi = lo, hi
