@@ -101,3 +101,50 @@ def test_coincident_and_degenerate_pairs(sfm_config):
     finite = np.isfinite(want).all(axis=1)
     assert finite.sum() >= 4
     assert_forces_close(got[finite], want[finite], name='degenerate')
+
+
+def test_degenerate_pairs_across_tiles(sfm_config):
+    """Coincident pedestrians that live in different 256-row tiles, a vertical-only offset and a |D| = 0 pair: the
+    unguarded symmetric fast path must hand exactly those rows to the repair path (sfm_stats.fixup_rows) and every row
+    must match numpy wherever numpy is finite."""
+    w = synth.make_config(2, n=1024)
+    loc, vel = w.loc.copy(), w.vel.copy()
+    loc[700] = loc[3]                                  # |d| = 0 across tiles 0 and 2
+    loc[900, :2] = loc[20, :2]
+    loc[900, 2] = 0.5                                  # d_xy = 0, d_z != 0  (angle_xy(e) = atan2(0, 0) = 0)
+    loc[400] = loc[130] + np.array([2.0, 0.0, 0.0])
+    vel[130], vel[400] = np.array([0.0, 0.0, 0.0]), np.array([0.5, 0.0, 0.0])      # lambda (v_i - v_j) = -e: |D| = 0
+    w.loc, w.vel = loc, vel
+    ctx = make_context(w, sfm_config)
+    ctx.reset_stats()
+    got = ctx.force(native.PEDESTRIAN)
+    repaired = ctx.stats()['fixup_rows']
+    with np.errstate(all='ignore'):
+        want, risk = O.pedestrian_force(loc, vel, w.radius, G.scene_for(w, sfm_config).ped, False, return_risk=True)
+    finite = np.isfinite(want).all(axis=1)
+    assert finite.sum() >= w.n - 2
+    assert 4 <= repaired <= 8, repaired
+    assert_forces_close(got[finite], want[finite], risk=risk[finite], name='degenerate-across-tiles')
+
+
+def test_planar_and_general_paths_agree(sfm_config):
+    """A flat crowd takes the z-free fast path; lifting one pedestrian by 0 m with a non-zero origin forces the general
+    path on the same numbers -- both must give the same forces to float32 rounding."""
+    w = synth.make_config(2, n=2048)
+    flat = make_context(w, sfm_config)
+    f_flat = flat.force(native.PEDESTRIAN)
+    general = native.Context(0)
+    general.set_params(native.params_from_config(sfm_config, w.step_length))
+    general.set_origin(0.0, 0.0, -1.0)                # staged z = 1 everywhere: non-planar flag set, same geometry
+    general.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+    f_gen = general.force(native.PEDESTRIAN)
+    np.testing.assert_allclose(f_flat, f_gen, rtol=2e-5, atol=2e-6)
+    assert np.abs(f_flat[:, 2]).max() == 0.0
+
+
+def test_pair_force_is_reproducible(sfm_config):
+    """Integer (fixed-point) accumulation: two independent contexts give bit-identical pair forces."""
+    w = synth.make_config(2, n=3000)
+    a = make_context(w, sfm_config).force(native.PEDESTRIAN)
+    b = make_context(w, sfm_config).force(native.PEDESTRIAN)
+    np.testing.assert_array_equal(a, b)
