@@ -21,8 +21,12 @@
 
 namespace sfm {
 
-constexpr int KS_THREADS = 128;
-constexpr int KS_IR = 2;
+#ifndef SFM_KS_IR
+#define SFM_KS_IR 2
+#endif
+constexpr int KS_IR = SFM_KS_IR;                         // rows per thread
+constexpr int KS_THREADS = K1_TJ / KS_IR;                // one 256-row tile per CTA
+constexpr int KS_WARPS = KS_THREADS / 32;
 constexpr int KS_QUADS = K1_TJ / 4;
 constexpr int KS_PLANES = 8;                             // PX..PVZ + the per-row non-planar flag (PSPARE)
 constexpr float KS_FIXED_SCALE = 4294967296.0f;          // 2^32 counts per m/s^2
@@ -169,7 +173,7 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
 template <bool RADIUS>
 __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
     __shared__ __align__(128) float tile[K1_STAGES][KS_PLANES][K1_TJ];
-    __shared__ __align__(16) float accj[KS_THREADS / 32][3][K1_TJ];
+    __shared__ __align__(16) float accj[KS_WARPS][3][K1_TJ];
     __shared__ __align__(8) uint64_t bar[K1_STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
         for (int s = 0; s < K1_STAGES; ++s) mbar_init(&bar[s], 1);
         mbar_fence_init();
     }
-    for (int e = tid; e < (KS_THREADS / 32) * 3 * K1_TJ; e += KS_THREADS) (&accj[0][0][0])[e] = 0.0f;
+    for (int e = tid; e < KS_WARPS * 3 * K1_TJ; e += KS_THREADS) (&accj[0][0][0])[e] = 0.0f;
     __syncthreads();
 
     auto issue = [&](int t, int stage) {
@@ -242,8 +246,10 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
         if (tid == 0 && k + 1 < n_items) issue(item_tile(k + 1), stage ^ 1);   // stage^1 was released by the barriers below
         while (!mbar_try_wait(&bar[stage], (k >> 1) & 1)) {}
         float gi[KS_IR][3];                                   // this tile's -F_i partial per row
-        const bool tile_nonplanar =
-            __syncthreads_or((tile[stage][PSPARE][tid] != 0.0f) | (tile[stage][PSPARE][tid + KS_THREADS] != 0.0f)) != 0;
+        int flag_j = 0;
+#pragma unroll
+        for (int r = 0; r < KS_IR; ++r) flag_j |= (tile[stage][PSPARE][tid + r * KS_THREADS] != 0.0f);
+        const bool tile_nonplanar = __syncthreads_or(flag_j) != 0;
         if (J == I) {
             // diagonal tile: guarded asymmetric evaluation with self pairs removed, rows of I only
             PairAcc acc[KS_IR];
@@ -270,8 +276,13 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
                 bool ok = true;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    v[c] = ((accj[0][c][e] + accj[1][c][e]) + accj[2][c][e]) + accj[3][c][e];
-                    accj[0][c][e] = accj[1][c][e] = accj[2][c][e] = accj[3][c][e] = 0.0f;
+                    v[c] = accj[0][c][e];
+                    accj[0][c][e] = 0.0f;
+#pragma unroll
+                    for (int wv = 1; wv < KS_WARPS; ++wv) {           // fixed order: deterministic
+                        v[c] += accj[wv][c][e];
+                        accj[wv][c][e] = 0.0f;
+                    }
                     ok = ok && fixed_ok(v[c]);
                 }
                 unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.facc + ((size_t)J * K1_TJ + e) * 4);
