@@ -24,6 +24,22 @@ namespace sfm {
 #ifndef SFM_KS_IR
 #define SFM_KS_IR 2
 #endif
+#ifndef SFM_KS_ASIN
+#define SFM_KS_ASIN 1           // planar tiles: interaction angle from sin/cos (no MUFU.RCP) with an asin polynomial
+#endif
+#ifndef SFM_KS_ASIN_TERMS
+#define SFM_KS_ASIN_TERMS 7
+#endif
+#ifndef SFM_KS_NEGSUB
+#define SFM_KS_NEGSUB 1         // a*b - c*d written as sub2(mul2, mul2): no 64-bit XOR negations (2 LOP3 each)
+#endif
+#ifndef SFM_KS_UNROLL
+#define SFM_KS_UNROLL 1
+#endif
+#ifndef SFM_KS_MINB
+#define SFM_KS_MINB 5           // min CTAs per SM handed to __launch_bounds__ (register cap)
+#endif
+constexpr int KS_UNROLL = SFM_KS_UNROLL;                 // unroll depth of the j-quad loop
 constexpr int KS_IR = SFM_KS_IR;                         // rows per thread
 constexpr int KS_THREADS = K1_TJ / KS_IR;                // one 256-row tile per CTA
 constexpr int KS_WARPS = KS_THREADS / 32;
@@ -41,13 +57,31 @@ struct SymArgs {
     PairParams pp;
 };
 
+// asin(x) = x P(x^2) on [0, sin(pi/4)]: minimax fits, max abs error 6.2e-7 (6 terms) / 1.0e-7 (7 terms)
+struct AsinConst {
+    f32x2 s0, s1, s2, s3, s4, s5, s6;
+};
+__device__ __forceinline__ AsinConst make_asin_const() {
+    AsinConst c;
+#if SFM_KS_ASIN_TERMS == 6
+    c.s0 = splat2(9.999993443e-01f); c.s1 = splat2(1.667610258e-01f); c.s2 = splat2(7.292483002e-02f);
+    c.s3 = splat2(6.089710817e-02f); c.s4 = splat2(-2.424139343e-02f); c.s5 = splat2(9.637616575e-02f);
+    c.s6 = 0ull;
+#else
+    c.s0 = splat2(1.000000119e+00f); c.s1 = splat2(1.666489840e-01f); c.s2 = splat2(7.553865016e-02f);
+    c.s3 = splat2(3.859527037e-02f); c.s4 = splat2(6.176946312e-02f); c.s5 = splat2(-5.651333556e-02f);
+    c.s6 = splat2(1.019138768e-01f);
+#endif
+    return c;
+}
+
 // -f_ij for two consecutive j at once: g = (a Dx - b Dy, a Dy + b Dx, a Dz); F_i -= g, F_j += g.
 template <bool RADIUS, bool PLANAR>
 __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, const f32x2 zi, const f32x2 ri,
                                             const f32x2 vxi, const f32x2 vyi, const f32x2 vzi, const f32x2 xj,
                                             const f32x2 yj, const f32x2 zj, const f32x2 rj, const f32x2 vxj,
-                                            const f32x2 vyj, const f32x2 vzj, const PackedConst& c, f32x2& gx, f32x2& gy,
-                                            f32x2& gz) {
+                                            const f32x2 vyj, const f32x2 vzj, const PackedConst& c,
+                                            const AsinConst& sc, f32x2& gx, f32x2& gy, f32x2& gz) {
     // PLANAR: every pedestrian of both tiles has the same z and no vertical velocity, so d_z = w_z = D_z = 0 exactly
     const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi);
     f32x2 dz = 0ull, wz = 0ull, Dz = 0ull;
@@ -57,7 +91,6 @@ __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, cons
         d2 = fma2(dz, dz, d2);
     }
     const f32x2 rinv = rsqrt2(d2);
-    const f32x2 dist = mul2(d2, rinv);
     const f32x2 wx = sub2(vxi, vxj), wy = sub2(vyi, vyj);
     const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy);
     f32x2 D2 = fma2(Dy, Dy, mul2(Dx, Dx));
@@ -68,38 +101,73 @@ __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, cons
     }
     const f32x2 Dinv = rsqrt2(D2);
     const f32x2 Dn = mul2(D2, Dinv);
+#if SFM_KS_NEGSUB
+    const f32x2 cross = sub2(mul2(wx, dy), mul2(wy, dx));
+#else
     const f32x2 cross = fma2(wx, dy, neg2(mul2(wy, dx)));
+#endif
     const f32x2 dot = fma2(Dx, dx, mul2(Dy, dy));
     float cl, ch, tl, th;
     unpack2(cross, cl, ch);
     unpack2(dot, tl, th);
     const float axl = fabsf(tl), ayl = fabsf(cl), axh = fabsf(th), ayh = fabsf(ch);
-    const f32x2 mn = pack2(fminf(axl, ayl), fminf(axh, ayh));
-    const f32x2 mxr = pack2(rcp_approx(fmaxf(axl, ayl)), rcp_approx(fmaxf(axh, ayh)));
-    const f32x2 q = mul2(mn, mxr);
-    const f32x2 s = mul2(q, q);
-    f32x2 p = fma2(c.a7, s, c.a6);
-    p = fma2(p, s, c.a5);
-    p = fma2(p, s, c.a4);
-    p = fma2(p, s, c.a3);
-    p = fma2(p, s, c.a2);
-    p = fma2(p, s, c.a1);
-    p = fma2(p, s, c.a0);
+    constexpr bool ASIN = PLANAR && (SFM_KS_ASIN != 0);
+    f32x2 R = 0ull, q, p;
+    if (ASIN) {
+        // planar: |D_xy| = |D| and |d_xy| = |d|, so sin/cos(theta) = cross/dot * (1/|d|)(1/|D|) -- no reciprocal
+        R = mul2(rinv, Dinv);
+        q = mul2(pack2(fminf(axl, ayl), fminf(axh, ayh)), R);
+        const f32x2 s = mul2(q, q);
+#if SFM_KS_ASIN_TERMS == 6
+        p = fma2(sc.s5, s, sc.s4);
+#else
+        p = fma2(sc.s6, s, sc.s5);
+        p = fma2(p, s, sc.s4);
+#endif
+        p = fma2(p, s, sc.s3);
+        p = fma2(p, s, sc.s2);
+        p = fma2(p, s, sc.s1);
+        p = fma2(p, s, sc.s0);
+    } else {
+        const f32x2 mxr = pack2(rcp_approx(fmaxf(axl, ayl)), rcp_approx(fmaxf(axh, ayh)));
+        q = mul2(pack2(fminf(axl, ayl), fminf(axh, ayh)), mxr);
+        const f32x2 s = mul2(q, q);
+        p = fma2(c.a7, s, c.a6);
+        p = fma2(p, s, c.a5);
+        p = fma2(p, s, c.a4);
+        p = fma2(p, s, c.a3);
+        p = fma2(p, s, c.a2);
+        p = fma2(p, s, c.a1);
+        p = fma2(p, s, c.a0);
+    }
     p = mul2(p, q);
-    float pl, ph;
-    unpack2(p, pl, ph);
-    const f32x2 theta = pack2(octant_fix(pl, axl, ayl, tl, cl), octant_fix(ph, axh, ayh, th, ch));
+    f32x2 theta;
+    {
+        float pl, ph;
+        unpack2(p, pl, ph);
+        theta = pack2(octant_fix(pl, axl, ayl, tl, cl), octant_fix(ph, axh, ayh, th, ch));
+    }
     const f32x2 thp = fma2(c.eps_gamma_neg, Dn, theta);
     const f32x2 u = mul2(Dn, thp);
     const f32x2 u2 = mul2(u, u);
-    f32x2 dl = dist;
-    if (RADIUS) dl = sub2(sub2(dist, ri), rj);
-    const f32x2 y = fma2(mul2(dl, Dinv), c.k_exp, c.log2A);
+    f32x2 y;
+    if (RADIUS) {
+        const f32x2 dl = sub2(sub2(mul2(d2, rinv), ri), rj);
+        y = fma2(mul2(dl, Dinv), c.k_exp, c.log2A);
+    } else if (ASIN) {
+        y = fma2(mul2(d2, R), c.k_exp, c.log2A);                          // |d| / |D| = d2 (1/|d|)(1/|D|)
+    } else {
+        y = fma2(mul2(mul2(d2, rinv), Dinv), c.k_exp, c.log2A);
+    }
     const f32x2 e1 = ex2_2(fma2(c.c_nprime_neg, u2, y));
     const f32x2 e2 = ex2_2(fma2(c.c_n_neg, u2, y));
     const f32x2 a = mul2(e1, Dinv);
     const f32x2 b = mul2(e2, Dinv) | (thp & 0x8000000080000000ULL);      // copysign(e2 / |D|, theta')
+#if SFM_KS_NEGSUB
+    gx = sub2(mul2(a, Dx), mul2(b, Dy));        // ptxas folds the subtraction into FFMA2 with a negated addend
+#else
     gx = fma2(a, Dx, mul2(neg2(b), Dy));
+#endif
     gy = fma2(a, Dy, mul2(b, Dx));
     gz = PLANAR ? 0ull : mul2(a, Dz);
 }
@@ -114,11 +182,12 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
                                          const int lane, const f32x2 (&xi2)[KS_IR], const f32x2 (&yi2)[KS_IR],
                                          const f32x2 (&zi2)[KS_IR], const f32x2 (&ri2)[KS_IR],
                                          const f32x2 (&vxi2)[KS_IR], const f32x2 (&vyi2)[KS_IR],
-                                         const f32x2 (&vzi2)[KS_IR], const PackedConst& pc, float (&gi)[KS_IR][3]) {
+                                         const f32x2 (&vzi2)[KS_IR], const PackedConst& pc, const AsinConst& sc,
+                                         float (&gi)[KS_IR][3]) {
     f32x2 Gx[KS_IR], Gy[KS_IR], Gz[KS_IR];
 #pragma unroll
     for (int r = 0; r < KS_IR; ++r) Gx[r] = Gy[r] = Gz[r] = 0ull;
-#pragma unroll 1
+#pragma unroll KS_UNROLL
     for (int step = 0; step < KS_QUADS; ++step) {
         const int j = ((step + lane) & (KS_QUADS - 1)) * 4;          // staggered: distinct j per lane
         const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tl[PX][j]);
@@ -136,12 +205,12 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
         for (int r = 0; r < KS_IR; ++r) {
             f32x2 gx, gy, gz;
             pair_terms2<RADIUS, PLANAR>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.x, Y.x, Z.x, R.x,
-                                        VX.x, VY.x, VZ.x, pc, gx, gy, gz);
+                                        VX.x, VY.x, VZ.x, pc, sc, gx, gy, gz);
             Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
             jx0 = r ? add2(jx0, gx) : gx; jy0 = r ? add2(jy0, gy) : gy;
             if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz0 = r ? add2(jz0, gz) : gz; }
             pair_terms2<RADIUS, PLANAR>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.y, Y.y, Z.y, R.y,
-                                        VX.y, VY.y, VZ.y, pc, gx, gy, gz);
+                                        VX.y, VY.y, VZ.y, pc, sc, gx, gy, gz);
             Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
             jx1 = r ? add2(jx1, gx) : gx; jy1 = r ? add2(jy1, gy) : gy;
             if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz1 = r ? add2(jz1, gz) : gz; }
@@ -171,7 +240,7 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
 }
 
 template <bool RADIUS>
-__global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
+__global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const SymArgs a) {
     __shared__ __align__(128) float tile[K1_STAGES][KS_PLANES][K1_TJ];
     __shared__ __align__(16) float accj[KS_WARPS][3][K1_TJ];
     __shared__ __align__(8) uint64_t bar[K1_STAGES];
@@ -234,6 +303,7 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
         bad[r] = 0;
     }
     const PackedConst pc = make_packed_const(a.pp);
+    const AsinConst sc = make_asin_const();
     // planar fast path: K3 flags every staged row whose z (relative to the origin) or vertical velocity is non-zero
     int own_flag = 0;
 #pragma unroll
@@ -266,9 +336,9 @@ __global__ void __launch_bounds__(KS_THREADS) k1_sym_pairs(const SymArgs a) {
             __syncthreads();
         } else {
             if (planar_own && !tile_nonplanar)
-                sym_tile<RADIUS, true>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, gi);
+                sym_tile<RADIUS, true>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, sc, gi);
             else
-                sym_tile<RADIUS, false>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, gi);
+                sym_tile<RADIUS, false>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, sc, gi);
             __syncthreads();                                    // every warp's J-side slice is complete
             // flush the J side: sum the warps' slices in fixed order, fixed-point atomics into the global accumulator
             for (int e = tid; e < K1_TJ; e += KS_THREADS) {
