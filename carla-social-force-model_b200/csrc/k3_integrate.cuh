@@ -11,6 +11,7 @@
 // bit-identical to numpy's.  The same pass re-emits the float32 staging planes the pair kernel reads next step.
 #pragma once
 
+#include "k4_lifecycle.cuh"
 #include "sfm_common.cuh"
 
 namespace sfm {
@@ -38,6 +39,14 @@ struct StepArgs {
     int enable_accel, enable_ped;
     int update_velocity;         // 0: forces only (Force.get_force path)
     int integrate_positions;
+    // fused arrival test + waypoint hand-over (K4b), evaluated at the position the forces were computed at -- the
+    // reference checks arrivals right after the tick, before the simulator moves anybody (run_simulation.py:114-118)
+    int advance_routes;
+    Routes routes;
+    ModeMachines mm;
+    double2* wp_rw;
+    uint8_t* mode_rw;
+    double sim_time;
 };
 
 __device__ __forceinline__ void stage_row(float* planes, int64_t rows_pad, int64_t i, double x, double y, double z,
@@ -146,6 +155,7 @@ __global__ void __launch_bounds__(256) k3_integrate(StepArgs a) {
         a.locr[i] = make_double4(x, y, z, L.w);
     }
     stage_row(a.planes_own, a.rows_pad, i, x, y, z, L.w, vx, vy, vz, a);
+    if (a.advance_routes) advance_waypoint(a.routes, a.mm, i, L.x, L.y, a.wp_rw, a.mode_rw, a.sim_time);
 }
 
 }  // namespace sfm

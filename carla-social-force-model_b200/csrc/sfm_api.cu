@@ -11,6 +11,7 @@
 #include "k1_sym.cuh"
 #include "k2_cells.cuh"
 #include "k3_integrate.cuh"
+#include "k4_lifecycle.cuh"
 
 using namespace sfm;
 
@@ -58,7 +59,7 @@ struct DevBuf {
     }
 };
 
-enum StatClass { ST_PAIRS = 0, ST_CELLS = 1, ST_SEGMENTS = 2, ST_INTEGRATE = 3, ST_COUNT = 4 };
+enum StatClass { ST_PAIRS = 0, ST_CELLS = 1, ST_SEGMENTS = 2, ST_INTEGRATE = 3, ST_LIFECYCLE = 4, ST_COUNT = 5 };
 
 struct TimedSpan {
     cudaEvent_t start, stop;
@@ -121,13 +122,34 @@ struct sfm_ctx {
     // accounting
     bool profiling = false;
     int64_t launches = 0, steps = 0, pair_launches = 0, pair_evals = 0;
-    double ms[ST_COUNT] = {0, 0, 0, 0};
+    double ms[ST_COUNT] = {0, 0, 0, 0, 0};
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> event_pool;
     int k1_target_ctas = 148 * 4 * 16;
     int k1_ir = 2, k1_minb = 5;     // tuning knobs (SFM_K1_IR, SFM_K1_MINB)
     int k1_rows_mode = 0;           // SFM_K1_MODE=rows: ordered-pair row kernel instead of the symmetric one
     DevBuf<long long> facc;         // [world * rows_pad][4] fixed-point force accumulators + poison counter
+    // ---- lifecycle: mode machines, traffic, routes, device-generated vehicle rings, recorder
+    DevBuf<double> mm_speed, mm_initial, mm_crossing, mm_margin, mm_next_time;
+    bool have_mm = false;
+    double waiting_time = 5.0, sim_time = 0.0;
+    DevBuf<double2> tr_center, tr_vel;
+    int tr_count = 0;
+    double tr_ext0[2] = {0.0, 0.0};
+    DevBuf<int> rt_end, rt_cursor;
+    DevBuf<double> rt_wp, next_wp3;
+    DevBuf<uint8_t> rt_cross, finished;
+    bool have_routes = false, routes_fused = false;
+    double route_threshold = 2.0;
+    DevBuf<unsigned long long> life_counters;      // [0] crossings started [1] idle wake-ups [2] hand-overs [3] finished
+    DevBuf<double2> veh_extent;
+    DevBuf<double> veh_yaw;
+    bool have_vehicles = false;
+    double veh_size_factor = 1.4142135623730951;
+    DevBuf<double4> rec_xyv;
+    DevBuf<uint8_t> rec_mode;
+    int64_t rec_capacity = 0, rec_rows = 0, rec_count = 0;
+    std::vector<double> rec_times;
     bool pairs_pending = false;
     bool step_open = false;         // sfm_step_begin done, sfm_step_end outstanding     // symmetric accumulation launched, finish kernel not yet run
 };
@@ -264,6 +286,28 @@ StepArgs step_args(sfm_ctx* c) {
     a.lambda_ped = c->params.ped.lambda_weight;
     a.ox = c->ox; a.oy = c->oy; a.oz = c->oz;
     return a;
+}
+
+ModeMachines mode_machines(sfm_ctx* c) {
+    ModeMachines mm;
+    mm.mode_speed = c->mm_speed.p; mm.initial_speed = c->mm_initial.p; mm.crossing_speed = c->mm_crossing.p;
+    mm.safety_margin = c->mm_margin.p; mm.next_mode_time = c->mm_next_time.p; mm.waiting_time = c->waiting_time;
+    return mm;
+}
+
+Routes routes_of(sfm_ctx* c) {
+    Routes r;
+    r.end = c->rt_end.p; r.cursor = c->rt_cursor.p; r.waypoint = c->rt_wp.p; r.crossing = c->rt_cross.p;
+    r.next_wp3 = c->next_wp3.p; r.finished = c->finished.p; r.threshold = c->route_threshold;
+    r.counters = c->life_counters.p + 2;
+    return r;
+}
+
+int ensure_life_counters(sfm_ctx* c) {
+    if (c->life_counters.p) return 0;
+    SFM_TRY(c->life_counters.ensure(4));
+    SFM_CUDA(cudaMemsetAsync(c->life_counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    return 0;
 }
 
 int launch_stage(sfm_ctx* c) {
@@ -600,6 +644,14 @@ int step_end(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool ke
     a.update_velocity = update_velocity;
     a.integrate_positions = integrate_positions;
     if (keep_class_forces) a.f_accel = c->f_accel.p;
+    if (update_velocity && c->have_routes && c->routes_fused && c->have_mm) {
+        a.advance_routes = 1;
+        a.routes = routes_of(c);
+        a.mm = mode_machines(c);
+        a.wp_rw = c->wp.p;
+        a.mode_rw = c->mode.p;
+        a.sim_time = c->sim_time;
+    }
     {
         SpanGuard g(c, ST_INTEGRATE);
         k3_integrate<<<cdiv(std::max<int64_t>(c->n, 1), 256), 256, 0, c->stream>>>(a);
@@ -682,6 +734,10 @@ int sfm_destroy(sfm_ctx* c) {
     c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
     c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release(); c->facc.release();
+    c->mm_speed.release(); c->mm_initial.release(); c->mm_crossing.release(); c->mm_margin.release();
+    c->mm_next_time.release(); c->tr_center.release(); c->tr_vel.release(); c->rt_end.release(); c->rt_cursor.release();
+    c->rt_wp.release(); c->next_wp3.release(); c->rt_cross.release(); c->finished.release(); c->life_counters.release();
+    c->veh_extent.release(); c->veh_yaw.release(); c->rec_xyv.release(); c->rec_mode.release();
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->aux_stream);
     cudaEventDestroy(c->ev_fork);
@@ -761,6 +817,10 @@ int sfm_upload_state(sfm_ctx* c, int64_t n, const double* loc, const double* vel
                                                     c->raw_mode.p, c->locr.p, c->vels.p, c->wp.p, c->mode.p);
     c->launches += 1;
     SFM_CUDA(cudaGetLastError());
+    SFM_TRY(c->next_wp3.ensure(3 * n));
+    SFM_CUDA(cudaMemcpyAsync(c->next_wp3.p, c->raw_c.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, c->stream));
+    c->have_mm = c->have_routes = false;             // per-row tables belong to the previous row set
+    c->rec_capacity = c->rec_count = 0;
     plan_ped_grid(c, n, loc);
     if (!c->origin_set && c->world == 1) c->oz = loc[2];
     SFM_CUDA(cudaStreamSynchronize(c->stream));      // host arrays may be released by the caller on return
@@ -796,6 +856,8 @@ int sfm_update_targets(sfm_ctx* c, int64_t n, const double* wp3, const double* s
                                                     c->locr.p, c->vels.p, c->wp.p, c->mode.p);
     c->launches += 1;
     SFM_CUDA(cudaGetLastError());
+    if (wp3 && c->next_wp3.p)
+        SFM_CUDA(cudaMemcpyAsync(c->next_wp3.p, c->raw_c.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, c->stream));
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -827,6 +889,7 @@ int sfm_set_obstacles(sfm_ctx* c, int which, int64_t n_obstacles, const double* 
     if (!c->have_params) return fail("sfm_set_params must be called first");
     if (which != SFM_FORCE_STATIC_OBSTACLE && which != SFM_FORCE_DYNAMIC_OBSTACLE) return fail("bad obstacle class");
     const bool dynamic = which == SFM_FORCE_DYNAMIC_OBSTACLE;
+    if (dynamic) c->have_vehicles = false;       // host-provided rings replace a device-generated vehicle set
     const double thr = dynamic ? c->params.dynamic_obs.perception_threshold : c->params.static_obs.perception_threshold;
     return upload_set(c, dynamic ? c->dyn : c->stat, n_obstacles, centers, nullptr, thr, velocities, offsets, points);
 }
@@ -977,6 +1040,318 @@ int sfm_stage(sfm_ctx* c) {
     return 0;
 }
 
+/* ================================================================================================================
+ * lifecycle: mode machines, gap acceptance, routes, device-generated vehicle rings, recorder
+ * ================================================================================================================ */
+
+int sfm_set_mode_machines(sfm_ctx* c, int64_t n, const double* initial_speed, const double* crossing_speed,
+                          const double* safety_margin, const double* mode_speed, const double* next_mode_time,
+                          double waiting_time) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n > 0 && (!initial_speed || !crossing_speed || !safety_margin || !mode_speed || !next_mode_time))
+        return fail("null mode-machine array");
+    c->waiting_time = waiting_time;
+    SFM_TRY(ensure_life_counters(c));
+    if (n == 0) { c->have_mm = true; return 0; }
+    SFM_TRY(c->mm_speed.ensure(n)); SFM_TRY(c->mm_initial.ensure(n)); SFM_TRY(c->mm_crossing.ensure(n));
+    SFM_TRY(c->mm_margin.ensure(n)); SFM_TRY(c->mm_next_time.ensure(n));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t b = sizeof(double) * n;
+    SFM_CUDA(cudaMemcpy(c->mm_initial.p, initial_speed, b, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->mm_crossing.p, crossing_speed, b, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->mm_margin.p, safety_margin, b, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->mm_speed.p, mode_speed, b, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->mm_next_time.p, next_mode_time, b, cudaMemcpyHostToDevice));
+    c->have_mm = true;
+    return 0;
+}
+
+int sfm_set_traffic(sfm_ctx* c, int64_t n_vehicles, const double* centers, const double* velocities,
+                    const double* extents) {
+    SFM_TRY(check_ctx(c));
+    if (n_vehicles < 0 || n_vehicles > (int64_t)1 << 24) return fail("bad vehicle count");
+    c->tr_count = 0;
+    if (n_vehicles == 0) return 0;
+    if (!centers || !velocities || !extents) return fail("null traffic array");
+    SFM_TRY(c->tr_center.ensure(n_vehicles)); SFM_TRY(c->tr_vel.ensure(n_vehicles));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    SFM_CUDA(cudaMemcpy(c->tr_center.p, centers, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->tr_vel.p, velocities, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
+    c->tr_ext0[0] = extents[0]; c->tr_ext0[1] = extents[1];          // vehicle_extents[:][0], check_traffic.py:35-36
+    c->tr_count = (int)n_vehicles;
+    return 0;
+}
+
+int sfm_tick_modes(sfm_ctx* c, double sim_time) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_mm) return fail("sfm_set_mode_machines must be called first");
+    c->sim_time = sim_time;
+    if (c->n == 0) return 0;
+    SFM_TRY(ensure_life_counters(c));
+    ModeTickArgs a{};
+    a.n = c->n; a.locr = c->locr.p; a.vels = c->vels.p; a.wp = c->wp.p; a.mode = c->mode.p;
+    a.mm = mode_machines(c);
+    if (c->have_vehicles) {                      // device-resident vehicle set (sfm_set_vehicles)
+        a.tr.count = (int)c->dyn.s.count; a.tr.center = c->dyn.s.center; a.tr.velocity = c->dyn.s.velocity;
+    } else {
+        a.tr.count = c->tr_count; a.tr.center = c->tr_center.p; a.tr.velocity = c->tr_vel.p;
+    }
+    a.tr.ext0_x = c->tr_ext0[0]; a.tr.ext0_y = c->tr_ext0[1];
+    a.sim_time = sim_time; a.counters = c->life_counters.p;
+    SpanGuard g(c, ST_LIFECYCLE);
+    k4_tick_modes<<<cdiv(c->n, K4_THREADS), K4_THREADS, 0, c->stream>>>(a);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sfm_download_modes(sfm_ctx* c, int64_t n, uint8_t* mode, double* mode_speed, double* next_mode_time,
+                       double* target_speed) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    if ((mode_speed || next_mode_time) && !c->have_mm) return fail("no mode machines on the device");
+    if (mode) SFM_CUDA(cudaMemcpyAsync(mode, c->mode.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (mode_speed) SFM_CUDA(cudaMemcpyAsync(mode_speed, c->mm_speed.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (next_mode_time)
+        SFM_CUDA(cudaMemcpyAsync(next_mode_time, c->mm_next_time.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (target_speed)
+        SFM_CUDA(cudaMemcpy2DAsync(target_speed, sizeof(double), &c->vels.p[0].w, sizeof(double4), sizeof(double), n,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_set_routes(sfm_ctx* c, int64_t n, const int64_t* offsets, const double* waypoints, const uint8_t* crossing,
+                   double distance_threshold, int fused) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (!c->have_mm) return fail("sfm_set_mode_machines must be called first (a hand-over requests a mode)");
+    if (n > 0 && !offsets) return fail("null route offsets");
+    c->route_threshold = distance_threshold;
+    c->routes_fused = fused != 0;
+    SFM_TRY(ensure_life_counters(c));
+    if (n == 0) { c->have_routes = true; return 0; }
+    const int64_t total = offsets[n];
+    if (total < 0 || total > (int64_t)INT32_MAX) return fail("bad route table");
+    if (total > 0 && (!waypoints || !crossing)) return fail("null waypoint array");
+    std::vector<int> cursor(n), end(n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) return fail("route offsets must be non-decreasing");
+        cursor[i] = (int)offsets[i];
+        end[i] = (int)offsets[i + 1];
+    }
+    SFM_TRY(c->rt_cursor.ensure(n)); SFM_TRY(c->rt_end.ensure(n)); SFM_TRY(c->finished.ensure(n));
+    SFM_TRY(c->rt_wp.ensure(3 * std::max<int64_t>(total, 1))); SFM_TRY(c->rt_cross.ensure(std::max<int64_t>(total, 1)));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    SFM_CUDA(cudaMemcpy(c->rt_cursor.p, cursor.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->rt_end.p, end.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemset(c->finished.p, 0, n));
+    if (total > 0) {
+        SFM_CUDA(cudaMemcpy(c->rt_wp.p, waypoints, sizeof(double) * 3 * total, cudaMemcpyHostToDevice));
+        SFM_CUDA(cudaMemcpy(c->rt_cross.p, crossing, total, cudaMemcpyHostToDevice));
+    }
+    c->have_routes = true;
+    return 0;
+}
+
+int sfm_advance_waypoints(sfm_ctx* c) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_routes || !c->have_mm) return fail("sfm_set_routes must be called first");
+    if (c->n == 0) return 0;
+    SpanGuard g(c, ST_LIFECYCLE);
+    k4_advance_waypoints<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->locr.p, c->wp.p, c->mode.p, routes_of(c),
+                                                                   mode_machines(c), c->sim_time);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sfm_download_routes(sfm_ctx* c, int64_t n, int64_t* cursor, uint8_t* finished, double* next_waypoint) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    if ((cursor || finished) && !c->have_routes) return fail("no routes on the device");
+    std::vector<int> cur;
+    if (cursor) {
+        cur.resize(n);
+        SFM_CUDA(cudaMemcpyAsync(cur.data(), c->rt_cursor.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (finished) SFM_CUDA(cudaMemcpyAsync(finished, c->finished.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (next_waypoint)
+        SFM_CUDA(cudaMemcpyAsync(next_waypoint, c->next_wp3.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    if (cursor) for (int64_t i = 0; i < n; ++i) cursor[i] = cur[i];
+    return 0;
+}
+
+int sfm_lifecycle_counters(sfm_ctx* c, int64_t* out4) {
+    SFM_TRY(check_ctx(c));
+    if (!out4) return fail("null pointer");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (!c->life_counters.p) return 0;
+    unsigned long long v[4];
+    SFM_CUDA(cudaMemcpyAsync(v, c->life_counters.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; ++k) out4[k] = (int64_t)v[k];
+    return 0;
+}
+
+namespace {
+
+VehicleArgs vehicle_args(sfm_ctx* c, double dt) {
+    VehicleArgs a{};
+    a.count = (int)c->dyn.s.count; a.center = c->dyn.s.center; a.yaw_deg = c->veh_yaw.p; a.velocity = c->dyn.s.velocity;
+    a.extent = c->veh_extent.p; a.offset = c->dyn.s.offset; a.point = c->dyn.s.point;
+    a.size_factor = c->veh_size_factor; a.dt = dt;
+    return a;
+}
+
+// (cell, index) order of the dynamic set on its FIXED grid (centres outside the grid are clamped into the border cells,
+// which never widens the index distance between a pedestrian's cell and an obstacle within the cutoff)
+int rebin_dynamic(sfm_ctx* c) {
+    SetStorage& st = c->dyn;
+    const int count = (int)st.s.count, ncell = st.s.grid.nx * st.s.grid.ny;
+    int key_bits = 1;
+    while ((1 << key_bits) < ncell) ++key_bits;
+    SpanGuard g(c, ST_CELLS);
+    k2_item_keys<<<cdiv(count, 256), 256, 0, c->stream>>>(st.center.p, count, st.s.grid, st.key.p, st.cell_item.p);
+    k2_radix_sort<<<1, SORT_THREADS, 0, c->stream>>>(st.key.p, st.cell_item.p, st.key_tmp.p, st.val_tmp.p, count, key_bits);
+    k2_cell_bounds<<<cdiv(ncell + 1, 256), 256, 0, c->stream>>>(st.key.p, count, ncell, st.cell_start.p);
+    c->launches += 3;
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_vehicle_rings(sfm_ctx* c) {
+    SpanGuard g(c, ST_LIFECYCLE);
+    const int np = (int)c->dyn.s.n_points;
+    k5_vehicle_rings<<<cdiv(np, 256), 256, 0, c->stream>>>(vehicle_args(c, 0.0), np);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, const double* yaw_deg,
+                     const double* velocities, const double* extents, double resolution, double size_factor) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    SetStorage& st = c->dyn;
+    st.s.count = 0;
+    c->have_vehicles = false;
+    if (n_vehicles <= 0) return 0;
+    if (!centers || !yaw_deg || !velocities || !extents) return fail("null vehicle array");
+    if (!(resolution > 0.0)) return fail("resolution must be positive");
+    if (n_vehicles > (int64_t)1 << 24) return fail("too many vehicles");
+    std::vector<int> off(n_vehicles + 1, 0);
+    for (int64_t v = 0; v < n_vehicles; ++v) {           // obstacles.py:273-274
+        const double circumference = 2.0 * extents[2 * v] + 2.0 * extents[2 * v + 1];
+        const long long samples = std::max<long long>(6, (long long)(circumference / resolution));
+        if (off[v] + samples > (long long)INT32_MAX) return fail("vehicle rings too large");
+        off[v + 1] = off[v] + (int)samples;
+    }
+    const int64_t np = off[n_vehicles];
+    SFM_TRY(st.center.ensure(n_vehicles)); SFM_TRY(st.cutoff.ensure(n_vehicles)); SFM_TRY(st.velocity.ensure(n_vehicles));
+    SFM_TRY(st.offset.ensure(n_vehicles + 1)); SFM_TRY(st.point.ensure(np));
+    SFM_TRY(c->veh_extent.ensure(n_vehicles)); SFM_TRY(c->veh_yaw.ensure(n_vehicles));
+    const double thr = c->params.dynamic_obs.perception_threshold;
+    std::vector<double> cut(n_vehicles, thr);
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    SFM_CUDA(cudaMemcpy(st.center.p, centers, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.velocity.p, velocities, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.cutoff.p, cut.data(), sizeof(double) * n_vehicles, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.offset.p, off.data(), sizeof(int) * (n_vehicles + 1), cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->veh_extent.p, extents, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(c->veh_yaw.p, yaw_deg, sizeof(double) * n_vehicles, cudaMemcpyHostToDevice));
+    SegmentSet& s = st.s;
+    s.center = st.center.p; s.cutoff = st.cutoff.p; s.velocity = st.velocity.p; s.offset = st.offset.p;
+    s.point = st.point.p; s.n_points = np;
+    c->veh_size_factor = size_factor;
+    c->tr_ext0[0] = extents[0]; c->tr_ext0[1] = extents[1];
+    SFM_TRY(build_set_grid(c, st, n_vehicles, centers, std::isfinite(thr) ? thr : 0.0));
+    s.count = n_vehicles;
+    c->have_vehicles = true;
+    return launch_vehicle_rings(c);
+}
+
+int sfm_advance_vehicles(sfm_ctx* c, double dt) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_vehicles) return fail("sfm_set_vehicles must be called first");
+    {
+        SpanGuard g(c, ST_LIFECYCLE);
+        k5_advance_vehicles<<<cdiv(c->dyn.s.count, 256), 256, 0, c->stream>>>(vehicle_args(c, dt));
+        c->launches += 1;
+        SFM_CUDA(cudaGetLastError());
+    }
+    SFM_TRY(launch_vehicle_rings(c));
+    return rebin_dynamic(c);
+}
+
+int sfm_download_vehicles(sfm_ctx* c, int64_t n_vehicles, double* centers, int64_t* offsets, int64_t point_capacity,
+                          double* points) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_vehicles) return fail("no device-resident vehicle set");
+    if (n_vehicles != c->dyn.s.count) return fail("vehicle count differs");
+    std::vector<int> off(n_vehicles + 1);
+    SFM_CUDA(cudaMemcpyAsync(off.data(), c->dyn.s.offset, sizeof(int) * (n_vehicles + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (centers)
+        SFM_CUDA(cudaMemcpyAsync(centers, c->dyn.s.center, sizeof(double2) * n_vehicles, cudaMemcpyDeviceToHost, c->stream));
+    if (points) {
+        if (point_capacity < c->dyn.s.n_points) return fail("point buffer too small");
+        SFM_CUDA(cudaMemcpyAsync(points, c->dyn.s.point, sizeof(double2) * c->dyn.s.n_points, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    if (offsets) for (int64_t v = 0; v <= n_vehicles; ++v) offsets[v] = off[v];
+    return 0;
+}
+
+int sfm_record_begin(sfm_ctx* c, int64_t capacity_frames) {
+    SFM_TRY(check_ctx(c));
+    if (capacity_frames < 0) return fail("negative capacity");
+    c->rec_rows = c->n;
+    c->rec_count = 0;
+    c->rec_times.clear();
+    c->rec_capacity = 0;
+    if (capacity_frames == 0 || c->n == 0) return 0;
+    SFM_TRY(c->rec_xyv.ensure((size_t)capacity_frames * c->n));
+    SFM_TRY(c->rec_mode.ensure((size_t)capacity_frames * c->n));
+    c->rec_capacity = capacity_frames;
+    return 0;
+}
+
+int sfm_record_frame(sfm_ctx* c, double sim_time) {
+    SFM_TRY(check_ctx(c));
+    if (c->rec_capacity == 0) return fail("sfm_record_begin must be called first");
+    if (c->rec_rows != c->n) return fail("row count changed since sfm_record_begin");
+    if (c->rec_count >= c->rec_capacity) return fail("frame buffer full: download and call sfm_record_begin again");
+    SpanGuard g(c, ST_LIFECYCLE);
+    const size_t at = (size_t)c->rec_count * c->n;
+    k6_record_frame<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->locr.p, c->vels.p, c->mode.p, c->rec_xyv.p + at,
+                                                              c->rec_mode.p + at);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->rec_times.push_back(sim_time);
+    c->rec_count += 1;
+    return 0;
+}
+
+int sfm_download_frames(sfm_ctx* c, int64_t first, int64_t count, double* xyv, uint8_t* mode, double* times,
+                        int64_t* frames_recorded) {
+    SFM_TRY(check_ctx(c));
+    if (frames_recorded) *frames_recorded = c->rec_count;
+    if (count == 0) return 0;
+    if (first < 0 || count < 0 || first + count > c->rec_count) return fail("frame range out of bounds");
+    const size_t at = (size_t)first * c->rec_rows, items = (size_t)count * c->rec_rows;
+    if (xyv) SFM_CUDA(cudaMemcpyAsync(xyv, c->rec_xyv.p + at, sizeof(double4) * items, cudaMemcpyDeviceToHost, c->stream));
+    if (mode) SFM_CUDA(cudaMemcpyAsync(mode, c->rec_mode.p + at, items, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    if (times) for (int64_t k = 0; k < count; ++k) times[k] = c->rec_times[first + k];
+    return 0;
+}
+
 int sfm_set_profiling(sfm_ctx* c, int enabled) {
     SFM_TRY(check_ctx(c));
     SFM_TRY(drain_spans(c));
@@ -1000,6 +1375,7 @@ int sfm_get_stats(sfm_ctx* c, sfm_stats* out) {
     out->launches = c->launches; out->steps = c->steps; out->pair_launches = c->pair_launches;
     out->ms_pairs = c->ms[ST_PAIRS]; out->ms_cells = c->ms[ST_CELLS]; out->ms_segments = c->ms[ST_SEGMENTS];
     out->ms_integrate = c->ms[ST_INTEGRATE];
+    out->ms_lifecycle = c->ms[ST_LIFECYCLE];
     out->fixup_rows = 0;
     out->pair_evaluations = c->pair_evals;
     if (c->fixup_rows.p && c->fixup_zeroed) {

@@ -1,0 +1,81 @@
+"""Device-resident run loop: what ``SimulationRunner.tick`` does every step (run_simulation.py:59-132), CARLA stubbed.
+
+Per tick, all on the device behind the C ABI:
+
+1. vehicles -- either the host hands over the 6-tuple of pedestrian_simulation.py:108-115 (rings as CARLA would produce
+   them) or the library moves the centres ballistically and regenerates the ellipse rings itself (``sfm_set_vehicles`` /
+   ``sfm_advance_vehicles``; obstacles.py:269-281,297-329);
+2. ``sfm_tick_modes`` -- apply_current_mode, the mode machines' tick and the gap acceptance (pedestrian_simulation.py:63-73);
+3. ``sfm_step`` -- the five forces, their sum, the velocity update with the speed clamp, the arrival test + waypoint
+   hand-over at the positions the forces saw (run_simulation.py:118-125), then the stub integrator x += dt v;
+4. optionally ``sfm_record_frame`` every ``record_every`` ticks (pedestrian_state.py:100-104).
+
+Nothing here computes: the class only sequences C-ABI calls.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import native
+
+IDLE = 0
+
+
+class HeadlessRunner:
+    def __init__(self, sfm_config, workload, life, device=0, device_vehicles=False, record_every=0, record_capacity=0,
+                 ctx=None):
+        w = workload
+        self.w, self.life = w, life
+        self.dt = w.step_length
+        self.ctx = ctx or native.Context(device)
+        c = self.ctx
+        c.set_params(native.params_from_config(sfm_config, w.step_length))
+        c.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+        if len(w.borders):
+            c.set_borders(w.borders, w.section_center, w.section_length)
+        if len(w.static_obstacles):
+            c.set_obstacles(native.STATIC_OBSTACLE, [p for p, _ in w.static_obstacles], [r for _, r in w.static_obstacles])
+        # PedModeManager.__init__ (ped_mode_manager.py:18-28) for every pedestrian, then set_mode(IDLE) at t = 0 for the
+        # idle ones: target speed 0, wake-up at waiting_time
+        crossing_speed = np.asarray(life.crossing_speed_factor, dtype=np.float64) * w.target_speed
+        mode_speed = np.where(life.idle, 0.0, w.target_speed)
+        next_time = np.where(life.idle, 0.0 + 5.0, -1.0)
+        mode = np.where(life.idle, IDLE, w.mode).astype(np.uint8)
+        c.update_targets(mode=mode)
+        c.set_mode_machines(w.target_speed, crossing_speed, life.crossing_safety_margin, mode_speed, next_time, 5.0)
+        c.set_routes(life.routes, life.waypoint_threshold, fused=True)
+        self.device_vehicles = device_vehicles
+        self.has_vehicles = w.veh_center is not None and len(w.veh_center) > 0
+        if self.has_vehicles and device_vehicles:
+            c.set_vehicles(w.veh_center, w.veh_yaw, w.veh_vel, w.veh_extent, w.veh_resolution)
+        self.step_index = 0
+        self.record_every = record_every
+        if record_every:
+            c.record_begin(record_capacity)
+
+    def tick(self):
+        c, k = self.ctx, self.step_index
+        if self.has_vehicles:
+            if self.device_vehicles:
+                if k > 0:
+                    c.advance_vehicles(self.dt)
+            else:
+                veh = self.w.vehicles_at(k)
+                c.set_obstacles(native.DYNAMIC_OBSTACLE, veh[1], veh[5], veh[3])
+                c.set_traffic(veh[1], veh[3], veh[4])
+        sim_time = k * self.dt
+        c.tick_modes(sim_time)
+        if self.record_every and k % self.record_every == 0:
+            c.record_frame(sim_time)                      # after the machines ticked, before the forces (:75)
+        c.step(1, integrate_positions=True)
+        self.step_index += 1
+
+    def run(self, n_steps):
+        for _ in range(n_steps):
+            self.tick()
+
+    def snapshot(self):
+        loc, vel = self.ctx.download_state()
+        modes = self.ctx.download_modes()
+        cursor, finished, wp = self.ctx.download_routes()
+        return dict(loc=loc, vel=vel, wp=wp, cursor=cursor, finished=finished, **modes)

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get('SFM_LIB', os.path.join(HERE, 'libsfm_b200.so'))     #
 FORCE_CLASSES = ('acceleration_force', 'pedestrian_force', 'border_force', 'static_obstacle_force',
                  'dynamic_obstacle_force')                      # pedestrian_simulation.py:37-48 dict order
 ACCELERATION, PEDESTRIAN, BORDER, STATIC_OBSTACLE, DYNAMIC_OBSTACLE = range(5)
+ABI_VERSION = 2
 
 # every symbol include/sfm_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create', 'sfm_destroy', 'sfm_set_stream',
@@ -25,7 +26,12 @@ SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create'
            'sfm_update_kinematics', 'sfm_update_targets', 'sfm_download_state', 'sfm_set_borders', 'sfm_set_obstacles',
            'sfm_force', 'sfm_enumerate_pairs', 'sfm_step', 'sfm_tick_host', 'sfm_download_force',
            'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_stage', 'sfm_step_begin', 'sfm_step_end',
-           'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats')
+           'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats',
+           # lifecycle
+           'sfm_set_mode_machines', 'sfm_set_traffic', 'sfm_tick_modes', 'sfm_download_modes', 'sfm_set_routes',
+           'sfm_advance_waypoints', 'sfm_download_routes', 'sfm_lifecycle_counters', 'sfm_set_vehicles',
+           'sfm_advance_vehicles', 'sfm_download_vehicles', 'sfm_record_begin', 'sfm_record_frame',
+           'sfm_download_frames')
 
 
 class SfmError(RuntimeError):
@@ -47,7 +53,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [('launches', C.c_int64), ('steps', C.c_int64), ('ms_pairs', C.c_double), ('ms_cells', C.c_double),
                 ('ms_segments', C.c_double), ('ms_integrate', C.c_double), ('pair_launches', C.c_int64),
-                ('fixup_rows', C.c_int64), ('pair_evaluations', C.c_int64)]
+                ('fixup_rows', C.c_int64), ('pair_evaluations', C.c_int64), ('ms_lifecycle', C.c_double)]
 
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
@@ -117,12 +123,26 @@ def lib():
         'sfm_set_profiling': (C.c_int, [p_ctx, C.c_int]),
         'sfm_reset_stats': (C.c_int, [p_ctx]),
         'sfm_get_stats': (C.c_int, [p_ctx, C.POINTER(Stats)]),
+        'sfm_set_mode_machines': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d, p_d, C.c_double]),
+        'sfm_set_traffic': (C.c_int, [p_ctx, i64, p_d, p_d, p_d]),
+        'sfm_tick_modes': (C.c_int, [p_ctx, C.c_double]),
+        'sfm_download_modes': (C.c_int, [p_ctx, i64, p_u8, p_d, p_d, p_d]),
+        'sfm_set_routes': (C.c_int, [p_ctx, i64, p_i64, p_d, p_u8, C.c_double, C.c_int]),
+        'sfm_advance_waypoints': (C.c_int, [p_ctx]),
+        'sfm_download_routes': (C.c_int, [p_ctx, i64, p_i64, p_u8, p_d]),
+        'sfm_lifecycle_counters': (C.c_int, [p_ctx, p_i64]),
+        'sfm_set_vehicles': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d, C.c_double, C.c_double]),
+        'sfm_advance_vehicles': (C.c_int, [p_ctx, C.c_double]),
+        'sfm_download_vehicles': (C.c_int, [p_ctx, i64, p_d, p_i64, i64, p_d]),
+        'sfm_record_begin': (C.c_int, [p_ctx, i64]),
+        'sfm_record_frame': (C.c_int, [p_ctx, C.c_double]),
+        'sfm_download_frames': (C.c_int, [p_ctx, i64, i64, p_d, p_u8, p_d, p_i64]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    if L.sfm_abi_version() != 1:
+    if L.sfm_abi_version() != ABI_VERSION:
         raise SfmError('libsfm_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L
@@ -336,6 +356,114 @@ class Context:
 
     def stage(self):
         _check(self._lib.sfm_stage(self._h))
+
+    # -- lifecycle on the device
+    def set_mode_machines(self, initial_target_speed, crossing_speed, crossing_safety_margin, mode_target_speed=None,
+                          next_mode_time=None, waiting_time=5.0):
+        n = self.n
+        ini, cro, mar = _f64(initial_target_speed, (n,)), _f64(crossing_speed, (n,)), _f64(crossing_safety_margin, (n,))
+        spd = _f64(ini if mode_target_speed is None else mode_target_speed, (n,))
+        nxt = _f64(np.full(n, -1.0) if next_mode_time is None else next_mode_time, (n,))     # ped_mode_manager.py:27
+        _check(self._lib.sfm_set_mode_machines(self._h, n, _ptr(ini), _ptr(cro), _ptr(mar), _ptr(spd), _ptr(nxt),
+                                               float(waiting_time)))
+
+    def set_traffic(self, centers, velocities, extents):
+        v = len(centers)
+        if v == 0:
+            _check(self._lib.sfm_set_traffic(self._h, 0, None, None, None))
+            return
+        c, u, e = (_f64(np.asarray(a, dtype=np.float64).reshape(-1, 2), (v, 2)) for a in (centers, velocities, extents))
+        _check(self._lib.sfm_set_traffic(self._h, v, _ptr(c), _ptr(u), _ptr(e)))
+
+    def tick_modes(self, sim_time):
+        _check(self._lib.sfm_tick_modes(self._h, float(sim_time)))
+
+    def download_modes(self):
+        """-> dict(mode uint8, mode_target_speed, next_mode_time, target_speed)"""
+        n = self.n
+        mode, spd, nxt, tgt = np.empty(n, dtype=np.uint8), np.empty(n), np.empty(n), np.empty(n)
+        _check(self._lib.sfm_download_modes(self._h, n, _ptr(mode, C.c_uint8), _ptr(spd), _ptr(nxt), _ptr(tgt)))
+        return dict(mode=mode, mode_target_speed=spd, next_mode_time=nxt, target_speed=tgt)
+
+    def download_mode_codes(self):
+        mode = np.empty(self.n, dtype=np.uint8)
+        _check(self._lib.sfm_download_modes(self._h, self.n, _ptr(mode, C.c_uint8), None, None, None))
+        return mode
+
+    def set_routes(self, routes, distance_threshold=2.0, fused=True):
+        """``routes``: per pedestrian a list of (waypoint(3), crossing_road) tuples -- SimulationRunner.waypoint_dict."""
+        sizes = np.fromiter((len(r) for r in routes), dtype=np.int64, count=len(routes))
+        offsets = np.zeros(len(routes) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=offsets[1:])
+        total = int(offsets[-1])
+        wps = np.zeros((max(total, 1), 3))
+        cross = np.zeros(max(total, 1), dtype=np.uint8)
+        k = 0
+        for r in routes:
+            for wp, crossing in r:
+                wps[k], cross[k] = wp, bool(crossing)
+                k += 1
+        self.set_routes_csr(offsets, wps, cross, distance_threshold, fused)
+
+    def set_routes_csr(self, offsets, waypoints, crossing, distance_threshold=2.0, fused=True):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        wps = _f64(waypoints)
+        cross = np.ascontiguousarray(crossing, dtype=np.uint8)
+        _check(self._lib.sfm_set_routes(self._h, self.n, _ptr(offsets, C.c_int64), _ptr(wps), _ptr(cross, C.c_uint8),
+                                        float(distance_threshold), int(bool(fused))))
+
+    def advance_waypoints(self):
+        _check(self._lib.sfm_advance_waypoints(self._h))
+
+    def download_routes(self):
+        n = self.n
+        cursor, finished, wp = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.uint8), np.empty((n, 3))
+        _check(self._lib.sfm_download_routes(self._h, n, _ptr(cursor, C.c_int64), _ptr(finished, C.c_uint8), _ptr(wp)))
+        return cursor, finished.astype(bool), wp
+
+    def lifecycle_counters(self):
+        out = np.zeros(4, dtype=np.int64)
+        _check(self._lib.sfm_lifecycle_counters(self._h, _ptr(out, C.c_int64)))
+        return dict(zip(('crossings_started', 'idle_wakeups', 'handovers', 'finished'), (int(v) for v in out)))
+
+    def set_vehicles(self, centers, yaw_deg, velocities, extents, resolution=0.1, size_factor=float(np.sqrt(2.0))):
+        v = len(centers)
+        self.n_vehicles = v
+        if v == 0:
+            _check(self._lib.sfm_set_vehicles(self._h, 0, None, None, None, None, resolution, size_factor))
+            return
+        c, u, e = (_f64(np.asarray(a, dtype=np.float64).reshape(-1, 2), (v, 2)) for a in (centers, velocities, extents))
+        yaw = _f64(yaw_deg, (v,))
+        _check(self._lib.sfm_set_vehicles(self._h, v, _ptr(c), _ptr(yaw), _ptr(u), _ptr(e), float(resolution),
+                                          float(size_factor)))
+
+    def advance_vehicles(self, dt):
+        _check(self._lib.sfm_advance_vehicles(self._h, float(dt)))
+
+    def download_vehicles(self):
+        """-> (centers [V, 2], list of rings [(P_v, 2)])"""
+        v = self.n_vehicles
+        centers, offsets = np.empty((v, 2)), np.empty(v + 1, dtype=np.int64)
+        _check(self._lib.sfm_download_vehicles(self._h, v, _ptr(centers), _ptr(offsets, C.c_int64), 0, None))
+        points = np.empty((int(offsets[-1]), 2))
+        _check(self._lib.sfm_download_vehicles(self._h, v, None, None, len(points), _ptr(points)))
+        return centers, [points[offsets[k]:offsets[k + 1]] for k in range(v)]
+
+    def record_begin(self, capacity_frames):
+        _check(self._lib.sfm_record_begin(self._h, int(capacity_frames)))
+
+    def record_frame(self, sim_time):
+        _check(self._lib.sfm_record_frame(self._h, float(sim_time)))
+
+    def download_frames(self, first=0, count=None):
+        """-> (times [F], xyv [F, n, 4] = (x, y, v_x, v_y), mode uint8 [F, n])"""
+        have = C.c_int64()
+        _check(self._lib.sfm_download_frames(self._h, 0, 0, None, None, None, C.byref(have)))
+        count = have.value - first if count is None else count
+        xyv, mode, times = np.empty((count, self.n, 4)), np.empty((count, self.n), dtype=np.uint8), np.empty(count)
+        if count:
+            _check(self._lib.sfm_download_frames(self._h, first, count, _ptr(xyv), _ptr(mode, C.c_uint8), _ptr(times), None))
+        return times, xyv, mode
 
     def set_profiling(self, enabled):
         _check(self._lib.sfm_set_profiling(self._h, int(bool(enabled))))

@@ -171,3 +171,88 @@ def make_config(k, n=None, seed=None, z_spread=0.0, scale_sets=True):
         else:
             w.veh_center, w.veh_yaw, w.veh_vel, w.veh_extent = make_vehicles(n_veh, side, rng)
     return w
+
+
+# ---- lifecycle scenario: routes, mode machines, crossing traffic ---------------------------------
+IDLE, ROAD_TO_SIDEWALK, CHECKING_TRAFFIC = 0, 3, 4
+
+
+@dataclass
+class Lifecycle:
+    """What SimulationRunner / PedSpawner keep next to the PedState table (run_simulation.py:38-39,118-132,
+    pedestrian_spawner.py:97-98,238-241): remaining waypoints per pedestrian and the PedModeManager constructor
+    arguments.  ``idle`` pedestrians get ``set_mode(IDLE)`` at sim_time 0 before the first tick."""
+    routes: list                      # per pedestrian: [(waypoint(3), crossing_road), ...]
+    crossing_speed_factor: np.ndarray
+    crossing_safety_margin: np.ndarray
+    idle: np.ndarray                  # bool
+    waypoint_threshold: float = 2.0
+    despawn_on_arrival: bool = False
+
+
+def make_lifecycle(n=48, seed=2001, n_vehicles=3, side=30.0, waypoints_per_ped=3):
+    """Small all-forces scene in which every lifecycle event happens within ~6 s: waypoint hand-overs (some requesting a
+    road crossing), gap acceptance against crossing vehicles, idle pedestrians waking up, finished routes."""
+    rng = np.random.default_rng(seed)
+    loc, vel, wp, radius, speed, _ = make_crowd(n, side, rng)
+    mode = np.full(n, WALKING_SIDEWALK, dtype=np.uint8)
+    mode[rng.random(n) < 0.15] = CROSSING_ROAD
+    mode[rng.random(n) < 0.15] = CHECKING_TRAFFIC
+    # first waypoint 1.5 .. 4 m away so that hand-overs start early
+    ang = rng.uniform(0.0, 2 * np.pi, size=n)
+    wp[:, 0] = loc[:, 0] + rng.uniform(1.5, 4.0, size=n) * np.cos(ang)
+    wp[:, 1] = loc[:, 1] + rng.uniform(1.5, 4.0, size=n) * np.sin(ang)
+    wp = _f32(wp)
+    routes = []
+    for i in range(n):
+        cur, route = wp[i].copy(), []
+        for _ in range(int(rng.integers(0, waypoints_per_ped + 1))):
+            a = rng.uniform(0.0, 2 * np.pi)
+            cur = _f32(cur + np.array([3.0 * np.cos(a), 3.0 * np.sin(a), 0.0]))
+            route.append((cur.copy(), bool(rng.random() < 0.5)))
+        routes.append(route)
+    w = Workload(f'lifecycle-n{n}', side, loc, vel, wp, radius, speed, mode)
+    w.borders, w.section_center, w.section_length = make_borders(4, 100, 0.4, 40.0, side, rng)
+    w.static_obstacles = make_static_obstacles(6, 12, 0.5, side, rng)
+    w.veh_center = _f32(rng.uniform(0.0, side, size=(n_vehicles, 2)))
+    w.veh_yaw = _f32(rng.uniform(-180.0, 180.0, size=n_vehicles))
+    sp = rng.uniform(2.0, 9.0, size=n_vehicles)
+    w.veh_vel = _f32(np.column_stack((sp * np.cos(np.radians(w.veh_yaw)), sp * np.sin(np.radians(w.veh_yaw)))))
+    w.veh_vel[0] = 0.0                                     # a parked vehicle: the zero-speed branch of check_traffic.py:48
+    w.veh_extent = np.tile(_f32(np.array([2.4, 1.0])), (n_vehicles, 1))
+    w.veh_resolution = 0.17
+    margin = _f32(rng.uniform(0.5, 2.5, size=n))
+    margin[rng.random(n) < 0.1] = -1.0                      # crosses without looking (check_traffic.py:24)
+    life = Lifecycle(routes, _f32(rng.uniform(1.2, 1.8, size=n)), margin, rng.random(n) < 0.12)
+    return w, life
+
+
+def make_output_scene(n=5, frames=4, seed=3001):
+    """A tiny recorded run in the containers ``OutputGenerator`` reads (output_generator.py:12-16): per-tick pedestrian
+    snapshots (pedestrian_state.py:100-104), per-tick vehicle snapshots (pedestrian_simulation.py:129-140), static
+    obstacles ``[(centre, ring)]`` and border polylines.  Values include sub-1e-4 and > 1e16 magnitudes so that the number
+    formatting (``str`` of a float64) is exercised on both sides of its notation switches."""
+    rng = np.random.default_rng(seed)
+    dtype = [('name', 'U8'), ('id', 'i4'), ('loc', 'f8', (3,)), ('vel', 'f8', (3,)), ('next_waypoint', 'f8', (3,)),
+             ('mode', 'O'), ('radius', 'f8'), ('target_speed', 'f8')]
+    vdtype = [('id', 'i4'), ('loc', 'f8', (2,)), ('heading', 'f8'), ('vel', 'f8', (2,)), ('extent', 'f8', (2,))]
+    ped_states, veh_states = {}, {}
+    for k in range(frames):
+        st = np.zeros(n, dtype=dtype)
+        st['name'] = [f'ped_{i + 3}' for i in range(n)]
+        st['id'] = np.arange(n) + 100
+        st['loc'] = rng.normal(0.0, 30.0, size=(n, 3))
+        st['vel'] = rng.normal(0.0, 1.0, size=(n, 3))
+        st['loc'][0, 0], st['vel'][0, 1] = 1.25e-7 * (k + 1), 3.0e17
+        st['mode'] = [int(m) for m in rng.integers(0, 5, size=n)]
+        ped_states[k * 0.05] = st
+        vs = np.zeros(2, dtype=vdtype)
+        vs['id'] = [1000, 1001]
+        vs['loc'] = rng.uniform(0.0, 40.0, size=(2, 2))
+        vs['heading'] = rng.uniform(-180.0, 180.0, size=2)
+        vs['vel'] = rng.normal(0.0, 5.0, size=(2, 2))
+        vs['extent'] = [[2.4, 1.0], [2.4, 1.0]]
+        veh_states[k * 0.05] = vs
+    static = make_static_obstacles(2, 6, 0.5, 40.0, rng)
+    borders, _, _ = make_borders(2, 5, 0.4, 40.0, 40.0, rng)
+    return dict(ped_states=ped_states, veh_states=veh_states, static_obstacles=static, borders=borders)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SFM_ABI_VERSION 1
+#define SFM_ABI_VERSION 2
 
 typedef struct sfm_ctx sfm_ctx;
 
@@ -70,6 +70,7 @@ typedef struct {
     int64_t pair_launches;                /* number of K1 launches inside ms_pairs */
     int64_t fixup_rows;                   /* rows the degenerate-pair repair path recomputed (0 for healthy crowds) */
     int64_t pair_evaluations;             /* pair terms K1 evaluated (padded slots included; one per unordered pair) */
+    double ms_lifecycle;                  /* K4/K5/K6: mode machines, waypoint hand-over, vehicle rings, recorder */
 } sfm_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -143,6 +144,54 @@ int sfm_force_accumulator(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_ran
 /* Makes this rank's block of the gather buffer reflect the current master state (after an upload or refresh), so the
  * first all-gather can run before the first step. */
 int sfm_stage(sfm_ctx* ctx);
+
+/* ---- lifecycle on the device: what PedestrianSimulation.tick and SimulationRunner.tick do in
+ *      interpreter loops around the forces.  All per-row tables are dropped by the next sfm_upload_state. ------------- */
+/* f1.  The persistent fields of every pedestrian's PedModeManager (ped_mode_manager.py:18-28): initial_target_speed,
+ * crossing_speed (= crossing_speed_factor * target_speed), crossing_safety_margin, target_speed (of the mode, :25),
+ * next_mode_time; current_mode is the `mode` column of sfm_upload_state.  waiting_time is :28 (5 s). */
+int sfm_set_mode_machines(sfm_ctx* ctx, int64_t n, const double* initial_target_speed, const double* crossing_speed,
+                          const double* crossing_safety_margin, const double* mode_target_speed,
+                          const double* next_mode_time, double waiting_time);
+/* Vehicle kinematics for the gap-acceptance test when the rings come from the host (pedestrian_simulation.py:108-113:
+ * obstacle positions, velocities, extents); sfm_set_vehicles supplies the same data itself.  extents: [V][2]. */
+int sfm_set_traffic(sfm_ctx* ctx, int64_t n_vehicles, const double* centers, const double* velocities,
+                    const double* extents);
+/* One tick of every machine: PedState.apply_current_mode (pedestrian_state.py:94-95: target_speed <- mode.target_speed),
+ * PedModeManager.tick (ped_mode_manager.py:30-35) and the gap acceptance of every CHECKING_TRAFFIC pedestrian against
+ * every vehicle (pedestrian_simulation.py:67-73, check_traffic.py:7-61) -> set_mode(CROSSING_ROAD). */
+int sfm_tick_modes(sfm_ctx* ctx, double sim_time);
+/* Any pointer may be NULL.  target_speed is the PedState column (what the speed clamp reads). */
+int sfm_download_modes(sfm_ctx* ctx, int64_t n, uint8_t* mode, double* mode_target_speed, double* next_mode_time,
+                       double* target_speed);
+/* f3.  Remaining waypoints per pedestrian (SimulationRunner.waypoint_dict, run_simulation.py:118-125) as CSR:
+ * offsets int64 [n+1] into waypoints [W][3] and crossing uint8 [W] (the (waypoint, crossing_road) tuples of
+ * pedestrian_state.py:83-92).  With `fused` != 0 every sfm_step / sfm_step_end performs the arrival test
+ * (pedestrian_simulation.py:88-97, at the positions the forces were evaluated at) and the hand-over inside K3. */
+int sfm_set_routes(sfm_ctx* ctx, int64_t n, const int64_t* offsets, const double* waypoints, const uint8_t* crossing,
+                   double distance_threshold, int fused);
+/* The same arrival test + hand-over as a call of its own, at the current device positions. */
+int sfm_advance_waypoints(sfm_ctx* ctx);
+/* cursor: next unread entry of each pedestrian's route; finished: arrived with nothing left (run_simulation.py:127). */
+int sfm_download_routes(sfm_ctx* ctx, int64_t n, int64_t* cursor, uint8_t* finished, double* next_waypoint);
+/* out4: crossings started, idle wake-ups, waypoint hand-overs, pedestrians finished -- since the context was created. */
+int sfm_lifecycle_counters(sfm_ctx* ctx, int64_t* out4);
+/* f2.  Dynamic-obstacle set generated on the device: obstacles.py:297-329 (get_dynamic_obstacles) with the ellipse of
+ * :269-281 -- max(6, int((2 ex + 2 ey) / resolution)) points per vehicle on semi-axes extent * size_factor, rotated by
+ * yaw (degrees) about the centre.  Replaces sfm_set_obstacles(SFM_FORCE_DYNAMIC_OBSTACLE, ...) + sfm_set_traffic. */
+int sfm_set_vehicles(sfm_ctx* ctx, int64_t n_vehicles, const double* centers, const double* yaw_deg,
+                     const double* velocities, const double* extents, double resolution, double size_factor);
+/* Headless stand-in for the simulator's vehicle actors: centres += velocity * dt, rings regenerated, cells rebuilt. */
+int sfm_advance_vehicles(sfm_ctx* ctx, double dt);
+/* centers [V][2], offsets int64 [V+1], points [point_capacity][2]; any pointer may be NULL. */
+int sfm_download_vehicles(sfm_ctx* ctx, int64_t n_vehicles, double* centers, int64_t* offsets, int64_t point_capacity,
+                          double* points);
+/* f4.  Device-resident recorder: PedState.record_current_state (pedestrian_state.py:100-104) keeps the columns
+ * pedestrian.csv is written from (output_generator.py:35-52): per frame [n][4] float64 (x, y, v_x, v_y) + uint8 mode. */
+int sfm_record_begin(sfm_ctx* ctx, int64_t capacity_frames);
+int sfm_record_frame(sfm_ctx* ctx, double sim_time);
+int sfm_download_frames(sfm_ctx* ctx, int64_t first, int64_t count, double* xyv, uint8_t* mode, double* times,
+                        int64_t* frames_recorded);
 
 /* ---- accounting -------------------------------------------------------------------------------------------------- */
 int sfm_set_profiling(sfm_ctx* ctx, int enabled);

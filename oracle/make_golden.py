@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the imported, unmodified reference (build container only).
 
-TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden [--only cfg1|cfg2]
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden [--only cfg1|cfg2|lifecycle|csv]
 The inputs are regenerated from ``sfm_b200.synth`` by seed; each file stores a SHA-256 of the input bytes so that a
 drift of the generator is detected instead of silently comparing against stale outputs.
 """
@@ -66,6 +66,49 @@ def golden_cfg2(ref, cfg):
                                 **{f'F_{k}': v for k, v in forces.items()})
 
 
+def lifecycle_digest(w, life):
+    h = hashlib.sha256(workload_digest(w).encode())
+    for route in life.routes:
+        for wp, crossing in route:
+            h.update(np.ascontiguousarray(wp).tobytes())
+            h.update(bytes([int(crossing)]))
+    for a in (life.crossing_speed_factor, life.crossing_safety_margin, life.idle, w.veh_center, w.veh_vel, w.veh_yaw):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+LIFECYCLE_STEPS = 140
+
+
+def golden_lifecycle(ref, cfg):
+    """Mode machines + gap acceptance + waypoint hand-over, run by the reference's own classes (ref_loader.run_lifecycle)."""
+    w, life = synth.make_lifecycle()
+    out = ref_loader.run_lifecycle(ref, w, life, cfg, LIFECYCLE_STEPS)
+    np.savez_compressed(os.path.join(GOLDEN, 'lifecycle.npz'), digest=lifecycle_digest(w, life), **out)
+
+
+def golden_output_csv(ref_dir):
+    """The four CSV files the reference's own OutputGenerator writes for a tiny recorded scene (output_generator.py)."""
+    import importlib.util
+    import tempfile
+    import types
+    spec = importlib.util.spec_from_file_location('_ref_output_generator', os.path.join(ref_dir, 'output_generator.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    scene = synth.make_output_scene()
+    ped_sim = types.SimpleNamespace(peds=types.SimpleNamespace(all_states=scene['ped_states']),
+                                    all_dyn_obs_states=scene['veh_states'], static_obstacles=scene['static_obstacles'],
+                                    borders=scene['borders'])
+    files = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        gen = mod.OutputGenerator(ped_sim, tmp, 'golden')
+        gen.generate_ped_csv(); gen.generate_veh_csv(); gen.generate_borders_csv(); gen.generate_obstacles_csv()
+        for name in ('pedestrian.csv', 'vehicle.csv', 'borders.csv', 'obstacles.csv'):
+            with open(os.path.join(gen.output_dir, name), 'rb') as f:
+                files[name.replace('.', '_')] = np.frombuffer(f.read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLDEN, 'output_csv.npz'), **files)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default=None)
@@ -76,6 +119,10 @@ def main():
         golden_cfg1(ref, cfg)
     if args.only in (None, 'cfg2'):
         golden_cfg2(ref, cfg)
+    if args.only in (None, 'lifecycle'):
+        golden_lifecycle(ref, cfg)
+    if args.only in (None, 'csv'):
+        golden_output_csv(ref_loader.REFERENCE_DIR)
 
 
 if __name__ == '__main__':

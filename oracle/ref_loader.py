@@ -3,8 +3,10 @@
 TEST INFRASTRUCTURE.  Works only in the build container: the GPU box has no ``/root/reference``, so nothing that runs
 there imports this module (``available()`` is the guard).  Two shims, both documented in SURVEY.md section 8c:
 
-* ``shapely`` (check_traffic.py:2) is not installed -> a stub module is registered before the import.  ``check_traffic``
-  is only *called* for pedestrians in CHECKING_TRAFFIC (pedestrian_simulation.py:67-70), which the synthetic crowds avoid.
+* ``shapely`` (check_traffic.py:2) is not installed -> a stand-in module is registered before the import with the two
+  classes ``check_traffic`` uses (``LineString([a, b]).intersection(other)`` -> something with ``is_empty`` and
+  ``distance(Point)``), restricted to two-point segments.  The reference's own gap-acceptance code then runs unmodified;
+  only the intersection primitive is ours (parity unpinned for shapely itself).
 * ``BorderForce.__init__`` does ``np.array(section_info)`` on a ragged list (forces.py:130), which numpy >= 1.24
   rejects -> ``section_info`` is passed as a pre-built ``dtype=object`` array, the form the reference's own ``.npz`` cache
   yields (obstacles.py:43-45).
@@ -19,6 +21,33 @@ import numpy as np
 
 REFERENCE_DIR = os.environ.get('SFM_REFERENCE_DIR', '/root/reference')
 _OWN_MODULES = ('forces', 'stateutils', 'pedestrian_state', 'pedestrian_simulation', 'ped_mode_manager', 'check_traffic')
+
+
+class _Point:
+    """Stand-in for shapely.geometry.Point (2-D)."""
+    is_empty = False
+
+    def __init__(self, xy):
+        self.xy = np.asarray(xy, dtype=np.float64)[:2]
+
+    def distance(self, other):
+        return float(np.linalg.norm(self.xy - other.xy))
+
+
+class _Empty:
+    is_empty = True
+
+
+class _LineString:
+    """Stand-in for shapely.geometry.LineString restricted to one segment."""
+
+    def __init__(self, coords):
+        self.a, self.b = (np.asarray(c, dtype=np.float64)[:2] for c in coords)
+
+    def intersection(self, other):
+        from oracle.lifecycle_oracle import segment_intersection
+        hit = segment_intersection(self.a, self.b, other.a, other.b)
+        return _Empty() if hit is None else _Point(hit)
 
 
 def available():
@@ -39,7 +68,7 @@ def load():
     sys.dont_write_bytecode = True                       # the reference tree is read-only
     if 'shapely' not in sys.modules:
         sh, geo = types.ModuleType('shapely'), types.ModuleType('shapely.geometry')
-        geo.LineString = geo.Point = object
+        geo.LineString, geo.Point = _LineString, _Point
         sh.geometry = geo
         sys.modules['shapely'], sys.modules['shapely.geometry'] = sh, geo
     sys.path.insert(0, REFERENCE_DIR)
@@ -104,3 +133,51 @@ def run_ticks(ref, workload, sfm_config, n_steps, record_forces=True):
         locs.append(sim.peds.state['loc'].copy())
         vels.append(sim.peds.state['vel'].copy())
     return dict(loc=np.array(locs), vel=np.array(vels), forces={k: np.array(v) for k, v in forces.items()})
+
+
+def run_lifecycle(ref, workload, life, sfm_config, n_steps):
+    """The reference's tick loop with its own mode machines, gap acceptance and waypoint hand-over, CARLA stubbed.
+
+    Follows SimulationRunner.tick (run_simulation.py:94-132) for everything that does not need the simulator: vehicles
+    refreshed -> ``PedestrianSimulation.tick`` -> arrival test + ``update_next_waypoint`` -> positions advanced by the
+    stub.  Pedestrians are spawned through ``spawn_pedestrian`` with real ``PedModeManager`` objects
+    (pedestrian_spawner.py:238-241)."""
+    sim = ref.pedestrian_simulation.PedestrianSimulation(list(workload.borders), workload.section_info(),
+                                                         list(workload.static_obstacles), sfm_config,
+                                                         workload.step_length)
+    PedMode, Manager = ref.ped_mode_manager.PedMode, ref.ped_mode_manager.PedModeManager
+    n = workload.n
+    names = [f'p_{i}' for i in range(n)]
+    for i in range(n):
+        m = Manager(names[i], float(workload.target_speed[i]), PedMode(int(workload.mode[i])),
+                    float(life.crossing_speed_factor[i]), float(life.crossing_safety_margin[i]))
+        if life.idle[i]:
+            m.set_mode(PedMode.IDLE)
+        sim.spawn_pedestrian((names[i], i, workload.loc[i], workload.vel[i], workload.next_waypoint[i], m,
+                              float(workload.radius[i]), float(workload.target_speed[i])))
+    waypoint_dict = {names[i]: list(life.routes[i]) for i in range(n)}
+    dt = workload.step_length
+    codes = lambda: np.array([int(m.current_mode) for m in sim.peds.state['mode']], dtype=np.uint8)   # noqa: E731
+    speeds = lambda: np.array([float(m.target_speed) for m in sim.peds.state['mode']])                # noqa: E731
+    hist = dict(loc=[sim.peds.state['loc'].copy()], vel=[sim.peds.state['vel'].copy()], mode=[codes()],
+                wp=[sim.peds.state['next_waypoint'].copy()], target_speed=[], mode_speed=[speeds()],
+                remaining=[np.array([len(waypoint_dict[k]) for k in names])])
+    for step in range(n_steps):
+        veh = workload.vehicles_at(step)
+        if veh is not None:
+            sim.update_dynamic_obstacles(veh)
+        sim.tick(step * dt)
+        nv = sim.get_new_velocities()
+        hist['target_speed'].append(sim.peds.state['target_speed'].copy())
+        for ped_name in sim.get_arrived_peds(life.waypoint_threshold):        # run_simulation.py:118-125
+            remaining = waypoint_dict[ped_name]
+            if remaining:
+                sim.peds.update_next_waypoint(ped_name, remaining.pop(0))
+        sim.peds.state['loc'] += nv['vel'] * dt
+        sim.peds.all_states.clear()
+        sim.all_dyn_obs_states.clear()
+        hist['loc'].append(sim.peds.state['loc'].copy()); hist['vel'].append(sim.peds.state['vel'].copy())
+        hist['mode'].append(codes()); hist['wp'].append(sim.peds.state['next_waypoint'].copy())
+        hist['mode_speed'].append(speeds())
+        hist['remaining'].append(np.array([len(waypoint_dict[k]) for k in names]))
+    return {k: np.array(v) for k, v in hist.items()}

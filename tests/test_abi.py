@@ -29,14 +29,14 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(built)
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.sfm_abi_version() == 1
+    assert lib.sfm_abi_version() == native.ABI_VERSION
 
 
 def test_struct_layout_matches_header():
-    # sfm_params: 5 doubles + 3 x 7 doubles + 6 int32 ; sfm_stats: 9 x 8 bytes
+    # sfm_params: 5 doubles + 3 x 7 doubles + 6 int32 ; sfm_stats: 10 x 8 bytes
     assert ctypes.sizeof(native.MoussaidParams) == 56
     assert ctypes.sizeof(native.Params) == 5 * 8 + 3 * 56 + 6 * 4
-    assert ctypes.sizeof(native.Stats) == 72
+    assert ctypes.sizeof(native.Stats) == 80
 
 
 def test_fails_loudly_without_device(built):

@@ -1,0 +1,164 @@
+"""-m gpu: the device lifecycle through the C ABI against the oracle and the reference goldens:
+mode machines + gap acceptance (K4a), arrival test + waypoint hand-over fused into K3 (K4b), vehicle rings generated on
+the device (K5), the frame recorder (K6)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lifecycle_oracle as LO
+from oracle import sfm_oracle as O
+from oracle.make_golden import LIFECYCLE_STEPS
+from sfm_b200 import native, synth
+from sfm_b200.headless import HeadlessRunner
+from tests.golden_util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def scenario():
+    return synth.make_lifecycle()
+
+
+@pytest.fixture(scope='module')
+def golden():
+    return np.load(os.path.join(GOLDEN, 'lifecycle.npz'))
+
+
+def test_free_running_device_loop_matches_reference_golden(scenario, golden, sfm_config):
+    """All five forces + lifecycle on the device for 140 ticks; only the pair force is float32, so positions drift by
+    <= 1e-3 m while every discrete decision (mode, hand-over tick, target speed) equals the reference's."""
+    w, life = scenario
+    run = HeadlessRunner(sfm_config, w, life)
+    for k in range(LIFECYCLE_STEPS):
+        run.tick()
+        s = run.snapshot()
+        assert np.array_equal(s['mode'], golden['mode'][k + 1]), f'modes differ after tick {k}'
+        assert np.array_equal(s['wp'], golden['wp'][k + 1]), f'waypoints differ after tick {k}'
+        assert np.array_equal(s['target_speed'], golden['target_speed'][k]), f'applied target speeds differ at tick {k}'
+        assert np.array_equal(s['mode_target_speed'], golden['mode_speed'][k + 1])
+    assert np.abs(s['loc'] - golden['loc'][-1]).max() < 1e-2 and np.median(np.abs(s['loc'] - golden['loc'][-1])) < 1e-4
+    remaining = np.array([len(r) for r in life.routes]) - s['cursor']
+    assert np.array_equal(remaining, golden['remaining'][-1])
+    counters = run.ctx.lifecycle_counters()
+    m = golden['mode'].astype(int)
+    assert counters['handovers'] == int((np.diff(golden['remaining'], axis=0) != 0).sum())
+    assert counters['idle_wakeups'] == int(((m[:-1] == 0) & (m[1:] != 0)).sum())
+    assert counters['finished'] == int(s['finished'].sum()) > 0
+
+
+def test_teacher_forced_decisions_equal_reference(scenario, golden, sfm_config):
+    """Same loop, but the kinematics of every tick are the reference's own (sfm_update_kinematics): inputs identical =>
+    every decision identical, including the borderline ones."""
+    w, life = scenario
+    run = HeadlessRunner(sfm_config, w, life)
+    for k in range(LIFECYCLE_STEPS):
+        run.ctx.update_kinematics(golden['loc'][k], golden['vel'][k])
+        run.tick()
+        s = run.snapshot()
+        assert np.array_equal(s['mode'], golden['mode'][k + 1]) and np.array_equal(s['wp'], golden['wp'][k + 1])
+        assert np.abs(s['vel'] - golden['vel'][k + 1]).max() < 2e-5        # one float32 pair-force step
+
+
+def test_gap_acceptance_many_vehicles(sfm_config):
+    """Every pedestrian CHECKING_TRAFFIC against 300 vehicles (more than one shared-memory tile): device decisions ==
+    oracle decisions, pedestrian by pedestrian."""
+    rng = np.random.default_rng(17)
+    w = synth.make_config(2, n=1024)
+    v = 300
+    centres, vels = rng.uniform(0, w.side, (v, 2)), rng.normal(0, 6, (v, 2))
+    vels[rng.random(v) < 0.1] = 0.0
+    extents = np.tile([2.4, 1.0], (v, 1))
+    margin = rng.uniform(-0.3, 2.0, w.n)
+    wp = w.loc.copy()
+    wp[:, :2] += rng.normal(0, 4.0, (w.n, 2))
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+    mode = np.full(w.n, 4, dtype=np.uint8)
+    ctx.upload_state(w.loc, w.vel, wp, w.radius, w.target_speed, mode)
+    ctx.set_mode_machines(w.target_speed, 1.5 * w.target_speed, margin)
+    ctx.set_traffic(centres, vels, extents)
+    ctx.tick_modes(0.0)
+    got = ctx.download_modes()
+    want = np.array([LO.check_traffic(w.loc[i], wp[i], 1.5 * w.target_speed[i], margin[i], centres, vels, extents)
+                     for i in range(w.n)])
+    assert np.array_equal(got['mode'] == 2, want)
+    assert 0.05 < want.mean() < 0.95
+    assert np.array_equal(got['mode_target_speed'], np.where(want, 1.5 * w.target_speed, w.target_speed))
+    assert np.array_equal(got['target_speed'], w.target_speed)            # applied before the machines changed
+    # no vehicles: everybody crosses (pedestrian_simulation.py:68-73)
+    ctx.update_targets(mode=mode)
+    ctx.set_traffic([], [], [])
+    ctx.tick_modes(0.05)
+    assert (ctx.download_mode_codes() == 2).all()
+
+
+def test_device_vehicle_rings_and_forces(sfm_config):
+    """sfm_set_vehicles / sfm_advance_vehicles: ring points equal the restated obstacles.py:269-281 to 1e-12, the
+    neighbour enumeration on them is bit-exact, and the force equals the host-ring path on the very same points."""
+    w = synth.make_config(4, n=8192)
+    v = len(w.veh_center)
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+    ctx.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+    ctx.set_vehicles(w.veh_center, w.veh_yaw, w.veh_vel, w.veh_extent, w.veh_resolution)
+    centre = w.veh_center.copy()
+    for k in range(3):
+        if k:
+            ctx.advance_vehicles(w.step_length)
+            centre = centre + w.veh_vel * w.step_length
+        got_c, rings = ctx.download_vehicles()
+        assert np.array_equal(got_c, centre)
+        for j in range(v):
+            want = LO.ellipse_ring(centre[j], w.veh_yaw[j], w.veh_extent[j, 0], w.veh_extent[j, 1], w.veh_resolution)
+            assert rings[j].shape == want.shape and np.abs(rings[j] - want).max() < 1e-12
+        f_dev = ctx.force(native.DYNAMIC_OBSTACLE)
+        pairs_dev = ctx.enumerate_pairs(native.DYNAMIC_OBSTACLE)
+        p = O.moussaid_params(sfm_config['dynamic_obstacle_force'], O.OBSTACLE_DEFAULTS)
+        f_ref, pairs_ref = O.obstacle_force(w.loc, w.vel, w.radius, got_c, rings, w.veh_vel, p, False, return_pairs=True)
+        assert np.array_equal(pairs_dev, pairs_ref)
+        assert np.abs(f_dev - f_ref).max() < 1e-10
+        host = native.Context(0)
+        host.set_params(native.params_from_config(sfm_config, w.step_length))
+        host.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+        host.set_obstacles(native.DYNAMIC_OBSTACLE, got_c, rings, w.veh_vel)
+        assert np.array_equal(host.force(native.DYNAMIC_OBSTACLE), f_dev)
+        host.close()
+    assert len(pairs_ref) > 1000
+
+
+def test_standalone_waypoint_advance_and_recorder(scenario, sfm_config, tmp_path):
+    """sfm_advance_waypoints as its own call == the oracle's hand-over; the recorder's frames == the device state at the
+    recorded ticks, and the CSV written from them has the reference's schema."""
+    w, life = scenario
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+    ctx.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+    ctx.set_mode_machines(w.target_speed, life.crossing_speed_factor * w.target_speed, life.crossing_safety_margin)
+    ctx.set_routes(life.routes, 2.5, fused=False)
+    machines = LO.Machines.create(w.target_speed, w.mode, life.crossing_speed_factor, life.crossing_safety_margin)
+    wp, cursor, finished = w.next_waypoint.copy(), np.zeros(w.n, dtype=np.int64), np.zeros(w.n, dtype=bool)
+    ctx.record_begin(4)
+    for k in range(4):
+        ctx.record_frame(0.05 * k)
+        ctx.advance_waypoints()
+        LO.advance_waypoints(machines, w.loc, wp, life.routes, cursor, finished, 2.5)
+        got_cursor, got_finished, got_wp = ctx.download_routes()
+        assert np.array_equal(got_cursor, cursor) and np.array_equal(got_finished, finished)
+        assert np.array_equal(got_wp, wp) and np.array_equal(ctx.download_mode_codes(), machines.mode)
+    assert cursor.sum() > 10 and finished.any()
+    times, xyv, mode = ctx.download_frames()
+    assert np.array_equal(times, 0.05 * np.arange(4)) and xyv.shape == (4, w.n, 4)
+    assert np.array_equal(xyv[0], np.column_stack((w.loc[:, :2], w.vel[:, :2]))) and np.array_equal(mode[0], w.mode)
+    with pytest.raises(native.SfmError):
+        ctx.record_frame(1.0)                                             # buffer full: fails loudly
+    import types
+    from output_generator import OutputGenerator
+    sim = types.SimpleNamespace(peds=types.SimpleNamespace(all_states={}), all_dyn_obs_states={}, static_obstacles=[],
+                                borders=[])
+    gen = OutputGenerator(sim, str(tmp_path), 'dev')
+    gen.generate_ped_csv(device_frames=(times, xyv, mode), ped_ids=np.arange(w.n))
+    lines = open(os.path.join(gen.output_dir, 'pedestrian.csv')).read().splitlines()
+    assert lines[0] == 'ped_id,frame,time,x,y,v_x,v_y,mode' and len(lines) == 1 + 4 * w.n
+    assert lines[1].split(',')[:3] == ['0', '0', '0.0']
