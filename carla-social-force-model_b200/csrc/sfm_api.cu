@@ -150,6 +150,7 @@ struct sfm_ctx {
     DevBuf<uint8_t> rec_mode;
     int64_t rec_capacity = 0, rec_rows = 0, rec_count = 0;
     std::vector<double> rec_times;
+    std::vector<int> rt_begin;                     // host copy of the routes' first entries (cursor downloads are relative)
     bool pairs_pending = false;
     bool step_open = false;         // sfm_step_begin done, sfm_step_end outstanding     // symmetric accumulation launched, finish kernel not yet run
 };
@@ -1146,6 +1147,7 @@ int sfm_set_routes(sfm_ctx* c, int64_t n, const int64_t* offsets, const double* 
     SFM_TRY(c->rt_wp.ensure(3 * std::max<int64_t>(total, 1))); SFM_TRY(c->rt_cross.ensure(std::max<int64_t>(total, 1)));
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     SFM_CUDA(cudaMemcpy(c->rt_cursor.p, cursor.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    c->rt_begin = cursor;
     SFM_CUDA(cudaMemcpy(c->rt_end.p, end.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemset(c->finished.p, 0, n));
     if (total > 0) {
@@ -1182,7 +1184,7 @@ int sfm_download_routes(sfm_ctx* c, int64_t n, int64_t* cursor, uint8_t* finishe
     if (next_waypoint)
         SFM_CUDA(cudaMemcpyAsync(next_waypoint, c->next_wp3.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     SFM_CUDA(cudaStreamSynchronize(c->stream));
-    if (cursor) for (int64_t i = 0; i < n; ++i) cursor[i] = cur[i];
+    if (cursor) for (int64_t i = 0; i < n; ++i) cursor[i] = cur[i] - c->rt_begin[i];
     return 0;
 }
 

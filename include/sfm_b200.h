@@ -172,7 +172,7 @@ int sfm_set_routes(sfm_ctx* ctx, int64_t n, const int64_t* offsets, const double
                    double distance_threshold, int fused);
 /* The same arrival test + hand-over as a call of its own, at the current device positions. */
 int sfm_advance_waypoints(sfm_ctx* ctx);
-/* cursor: next unread entry of each pedestrian's route; finished: arrived with nothing left (run_simulation.py:127). */
+/* cursor: entries of each pedestrian's route already handed out; finished: arrived with nothing left (run_simulation.py:127). */
 int sfm_download_routes(sfm_ctx* ctx, int64_t n, int64_t* cursor, uint8_t* finished, double* next_waypoint);
 /* out4: crossings started, idle wake-ups, waypoint hand-overs, pedestrians finished -- since the context was created. */
 int sfm_lifecycle_counters(sfm_ctx* ctx, int64_t* out4);
