@@ -13,10 +13,20 @@
 //       the box, stage an item's points in shared memory and let every lane that passes the reference's exact filter
 //       scan them.
 //
-// Bit-exact enumeration: the filter sqrt(dx*dx + dy*dy) < cutoff and the nearest-point argmin are evaluated in float64
-// with numpy's operation order (np.linalg.norm = sqrt(add.reduce(x*x)), unfused), np.argmin's first-index tie rule
-// included -- so the (pedestrian, item, nearest point) triplets equal the reference's exactly, and the forces (also
-// float64, reference operation order) agree to a few ulp.
+// Bit-exact enumeration: the filter sqrt(dx*dx + dy*dy) < cutoff is evaluated in float64 with numpy's operation order
+// (np.linalg.norm = sqrt(add.reduce(x*x)), unfused).  The nearest-point argmin is found in two stages: a float32
+// scan over centre-relative coordinates brackets every point that could be the float64 minimum -- squared distances within
+// the item's rigorous rounding bound `tol` of the float32 minimum, a contiguous index window that is almost always 1-3
+// points wide -- and that window is then scanned with numpy's exact float64 arithmetic, np.argmin's first-index tie rule
+// included.  So the (pedestrian, item, nearest point) triplets equal the reference's exactly, and the forces (float64,
+// reference operation order) agree to a few ulp.
+//
+// Why the bracket is a superset: coordinates are taken relative to the item's centre c in float64 and rounded once to
+// float32, |x~ - (x - c)| <= 2^-24 |x - c|; with M >= every |component| involved (M = max(cutoff, ring extent), per item,
+// computed at upload) a difference carries <= 3.1 * 2^-24 M and the squared distance <= 42 * 2^-24 M^2 =: Delta of
+// absolute error, all float32 roundings included.  If q* is the float64 argmin and q~ the float32 one,
+// d~(q*) <= D(q*) + Delta <= D(q~) + Delta <= d~(q~) + 2 Delta.  tol = 128 * 2^-24 M^2 >= 2 Delta with slack for the
+// float32 evaluation of the threshold itself.
 #pragma once
 
 #include "sfm_common.cuh"
@@ -25,7 +35,7 @@ namespace sfm {
 
 constexpr int K2_WARPS = 4;             // warps sharing one group of 32 pedestrians
 constexpr int K2_THREADS = 32 * K2_WARPS;
-constexpr int K2_CHUNK = 128;           // points one warp stages per pass
+constexpr int K2_CHUNK = 256;           // points (float2, centre-relative) one warp stages per pass
 constexpr int SORT_THREADS = 512;
 constexpr int SORT_RADIX_BITS = 4;
 
@@ -218,6 +228,7 @@ struct SegArgs {
     const double2* velocity;
     const int* offset;
     const double2* point;
+    const float* tol;               // [count] float32 bracket width of the two-stage nearest-point search
     CellGrid grid;
     const int* cell_start;
     const int* cell_item;
@@ -276,7 +287,7 @@ __device__ __forceinline__ double2 segment_force(const SegArgs& a, double px, do
 }
 
 // np.argmin(np.linalg.norm(loc - points, axis=-1)) with numpy's arithmetic (rare tie path of the scan below).
-__device__ __noinline__ int exact_argmin(const double2* __restrict__ point, int o0, int o1, double px, double py) {
+__device__ __forceinline__ int exact_argmin(const double2* __restrict__ point, int o0, int o1, double px, double py) {
     double best = __longlong_as_double(0x7ff0000000000000LL);
     int best_q = o0;
     for (int q = o0; q < o1; ++q) {
@@ -296,8 +307,8 @@ __device__ __noinline__ int exact_argmin(const double2* __restrict__ point, int 
 // shared-memory slice (warp-level barriers only), scans them, and keeps a partial force per pedestrian; the partials
 // are combined in warp order at the end, so the summation order is fixed.
 template <int KIND>
-__global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
-    __shared__ double2 sp[K2_WARPS][K2_CHUNK];
+__global__ void __launch_bounds__(K2_THREADS, 4) k2_segments(const SegArgs a) {
+    __shared__ __align__(16) float2 sp[K2_WARPS][K2_CHUNK];
     __shared__ double2 part[K2_WARPS][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int slot = blockIdx.x * 32 + lane;
@@ -335,11 +346,13 @@ __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
             int s_l = -1, o0_l = 0, o1_l = 0;
             double2 cen_l = make_double2(0.0, 0.0);
             double cut_l = 0.0;
+            float tol_l = 0.0f;
             bool accept_l = false;
             if (kk < k_end) {
                 s_l = a.cell_item[kk];
                 cen_l = a.center[s_l];
                 cut_l = a.cutoff[s_l];
+                tol_l = a.tol[s_l];
                 o0_l = a.offset[s_l];
                 o1_l = a.offset[s_l + 1];
                 // conservative reject: the cutoff disc misses the warp's bounding box (slack covers rounding)
@@ -361,30 +374,67 @@ __global__ void __launch_bounds__(K2_THREADS) k2_segments(const SegArgs a) {
                 // the reference's filter, bit for bit: norm(loc - centre) < cutoff  (forces.py:149-150, :222-223)
                 const bool pass = active && (norm2_np(__dsub_rn(px, cxs), __dsub_rn(py, cys)) < cut);
                 if (!__any_sync(0xffffffffu, pass)) continue;
-                // Nearest point = np.argmin over the *rounded square roots* (forces.py:154, :228), first index on
-                // ties.  The scan tracks the smallest squared distance m1 (first index, strict <) and the runner-up
-                // m2; sqrt is monotone, so that index is numpy's answer unless another point's d2 lies within
-                // rounding distance of m1 -- then (rare) the item is rescanned with numpy's exact arithmetic.
-                double m1 = INF, m2 = INF;
-                int best_q = o0;
-                for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
-                    const int m = min(K2_CHUNK, o1 - c0);
-                    __syncwarp();
-                    for (int q = lane; q < m; q += 32) sp[wid][q] = a.point[c0 + q];
-                    __syncwarp();
-#pragma unroll 4
-                    for (int q = 0; q < m; ++q) {
-                        const double2 P = sp[wid][q];
-                        const double dx = px - P.x, dy = py - P.y;
-                        const double d2 = fma(dx, dx, dy * dy);          // argmin only; ties go to exact_argmin
-                        const bool lt1 = d2 < m1, lt2 = d2 < m2;
-                        m2 = lt1 ? m1 : (lt2 ? d2 : m2);
-                        m1 = lt1 ? d2 : m1;
-                        best_q = lt1 ? (c0 + q) : best_q;
+                // Nearest point, stage 1 (float32, all lanes in lock step over the staged points): the smallest squared
+                // distance m1, then the index window [lo, hi] of every point within tol of it.
+                const float tol = __shfl_sync(0xffffffffu, tol_l, src);
+                const float pxf = (float)(px - cxs), pyf = (float)(py - cys);
+                const float FAR = 1.0e18f;                                   // pad value: d2 = 2e36, finite, never a candidate
+                float m1 = 3.0e38f;
+                int lo = 0x7fffffff, hi = -1;
+                const bool one_chunk = (o1 - o0) <= K2_CHUNK;
+                for (int phase = 0; phase < 2; ++phase) {
+                    const float thr = m1 + tol;
+                    for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
+                        const int m = min(K2_CHUNK, o1 - c0);
+                        const int m4 = (m + 3) & ~3;
+                        if (phase == 0 || !one_chunk) {
+                            __syncwarp();
+                            for (int q = lane; q < m4; q += 32) {
+                                float2 v = make_float2(FAR, FAR);
+                                if (q < m) {
+                                    const double2 P = a.point[c0 + q];
+                                    v = make_float2((float)(P.x - cxs), (float)(P.y - cys));
+                                }
+                                sp[wid][q] = v;
+                            }
+                            __syncwarp();
+                        }
+                        if (phase == 0) {
+#pragma unroll 2
+                            for (int q = 0; q < m4; q += 4) {
+                                const float4 A = *reinterpret_cast<const float4*>(&sp[wid][q]);
+                                const float4 B = *reinterpret_cast<const float4*>(&sp[wid][q + 2]);
+                                const float ax = pxf - A.x, ay = pyf - A.y, bx = pxf - A.z, by = pyf - A.w;
+                                const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
+                                const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
+                                const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
+                                m1 = fminf(fminf(m1, d0), fminf(d1, fminf(d2, d3)));
+                            }
+                        } else {
+#pragma unroll 2
+                            for (int q = 0; q < m4; q += 4) {
+                                const float4 A = *reinterpret_cast<const float4*>(&sp[wid][q]);
+                                const float4 B = *reinterpret_cast<const float4*>(&sp[wid][q + 2]);
+                                const float ax = pxf - A.x, ay = pyf - A.y, bx = pxf - A.z, by = pyf - A.w;
+                                const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
+                                const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
+                                const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
+                                if (fminf(fminf(d0, d1), fminf(d2, d3)) <= thr) {
+                                    const int base = c0 + q;
+                                    if (d0 <= thr) { lo = min(lo, base); hi = max(hi, base); }
+                                    if (d1 <= thr) { lo = min(lo, base + 1); hi = max(hi, base + 1); }
+                                    if (d2 <= thr) { lo = min(lo, base + 2); hi = max(hi, base + 2); }
+                                    if (d3 <= thr) { lo = min(lo, base + 3); hi = max(hi, base + 3); }
+                                }
+                            }
+                        }
                     }
                 }
+                int best_q = o0;
                 if (pass) {
-                    if (m2 <= m1 * 1.00000000000001) best_q = exact_argmin(a.point, o0, o1, px, py);
+                    // stage 2: numpy's exact arithmetic over the bracket (first index on exact ties, forces.py:154, :228)
+                    best_q = (hi < lo) ? exact_argmin(a.point, o0, o1, px, py)        // non-finite coordinates: full scan
+                                       : exact_argmin(a.point, lo, min(hi + 1, o1), px, py);
                     const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
                                                           KIND ? a.velocity[s] : make_double2(0.0, 0.0));
                     fx = __dadd_rn(fx, f.x);

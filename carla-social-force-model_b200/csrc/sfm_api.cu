@@ -72,7 +72,9 @@ struct SetStorage {
     DevBuf<double> cutoff;
     DevBuf<int> offset, cell_start, cell_item, val_tmp;
     DevBuf<unsigned> key, key_tmp;
+    DevBuf<float> tol;
     void release() {
+        tol.release();
         center.release(); velocity.release(); point.release(); cutoff.release(); offset.release();
         cell_start.release(); cell_item.release(); val_tmp.release(); key.release(); key_tmp.release();
     }
@@ -515,6 +517,14 @@ int build_set_grid(sfm_ctx* c, SetStorage& st, int64_t count, const double* cent
     return 0;
 }
 
+// Bracket width of the float32 nearest-point stage for an item whose centre-relative coordinates (pedestrians inside
+// the cutoff and the item's own points) are bounded by M in every component: 128 * 2^-24 * M^2 (see k2_cells.cuh).
+float bracket_tolerance(double M) {
+    if (!std::isfinite(M)) return INFINITY;
+    const double t = 128.0 * std::ldexp(1.0, -24) * M * M * 1.0001;
+    return t < 3.0e38 ? (float)t : INFINITY;
+}
+
 int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers, const double* cutoffs,
                double uniform_cut, const double* velocities, const int64_t* offsets, const double* points) {
     SegmentSet& s = st.s;
@@ -538,6 +548,16 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
         if (std::isfinite(cut[i])) max_cut = std::max(max_cut, cut[i]);
     }
     for (int64_t i = 0; i <= count; ++i) off[i] = (int)offsets[i];
+    std::vector<float> tol(count);
+    for (int64_t i = 0; i < count; ++i) {
+        double M = std::isfinite(cut[i]) ? std::fabs(cut[i]) : INFINITY;
+        for (int64_t q = offsets[i]; q < offsets[i + 1]; ++q) {
+            M = std::max(M, std::fabs(points[2 * q] - centers[2 * i]));
+            M = std::max(M, std::fabs(points[2 * q + 1] - centers[2 * i + 1]));
+        }
+        tol[i] = bracket_tolerance(M);
+    }
+    SFM_TRY(st.tol.ensure(count));
     // synchronous copies from pageable host memory: the inputs may be temporaries of the caller
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     SFM_CUDA(cudaMemcpy(st.center.p, centers, sizeof(double2) * count, cudaMemcpyHostToDevice));
@@ -546,6 +566,8 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
     else SFM_CUDA(cudaMemset(st.velocity.p, 0, sizeof(double2) * count));
     SFM_CUDA(cudaMemcpy(st.offset.p, off.data(), sizeof(int) * (count + 1), cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemcpy(st.point.p, points, sizeof(double2) * np, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.tol.p, tol.data(), sizeof(float) * count, cudaMemcpyHostToDevice));
+    s.tol = st.tol.p;
     s.center = st.center.p; s.cutoff = st.cutoff.p; s.velocity = st.velocity.p; s.offset = st.offset.p;
     s.point = st.point.p; s.n_points = np;
     SFM_TRY(build_set_grid(c, st, count, centers, max_cut));
@@ -571,7 +593,7 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
     SegArgs a{};
     a.locr = c->locr.p; a.vels = c->vels.p; a.mode = c->mode.p; a.perm = c->perm.p; a.n = n;
     a.center = st.s.center; a.cutoff = st.s.cutoff; a.velocity = st.s.velocity; a.offset = st.s.offset;
-    a.point = st.s.point; a.grid = st.s.grid; a.cell_start = st.s.cell_start; a.cell_item = st.s.cell_item;
+    a.point = st.s.point; a.tol = st.s.tol; a.grid = st.s.grid; a.cell_start = st.s.cell_start; a.cell_item = st.s.cell_item;
     a.mp = make_moussaid_d(cls == SFM_FORCE_DYNAMIC_OBSTACLE ? c->params.dynamic_obs : c->params.static_obs);
     a.border_a = c->params.border_a; a.border_b = c->params.border_b;
     a.use_radius = c->params.use_ped_radius;
@@ -1261,6 +1283,11 @@ int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, cons
     SFM_TRY(c->veh_extent.ensure(n_vehicles)); SFM_TRY(c->veh_yaw.ensure(n_vehicles));
     const double thr = c->params.dynamic_obs.perception_threshold;
     std::vector<double> cut(n_vehicles, thr);
+    std::vector<float> tol(n_vehicles);
+    for (int64_t v = 0; v < n_vehicles; ++v)          // ring points lie within size_factor * max(extent) of the centre
+        tol[v] = bracket_tolerance(std::max(std::fabs(thr), 1.001 * std::fabs(size_factor) *
+                                                                std::max(std::fabs(extents[2 * v]), std::fabs(extents[2 * v + 1]))));
+    SFM_TRY(st.tol.ensure(n_vehicles));
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     SFM_CUDA(cudaMemcpy(st.center.p, centers, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemcpy(st.velocity.p, velocities, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
@@ -1268,7 +1295,9 @@ int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, cons
     SFM_CUDA(cudaMemcpy(st.offset.p, off.data(), sizeof(int) * (n_vehicles + 1), cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemcpy(c->veh_extent.p, extents, sizeof(double2) * n_vehicles, cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemcpy(c->veh_yaw.p, yaw_deg, sizeof(double) * n_vehicles, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.tol.p, tol.data(), sizeof(float) * n_vehicles, cudaMemcpyHostToDevice));
     SegmentSet& s = st.s;
+    s.tol = st.tol.p;
     s.center = st.center.p; s.cutoff = st.cutoff.p; s.velocity = st.velocity.p; s.offset = st.offset.p;
     s.point = st.point.p; s.n_points = np;
     c->veh_size_factor = size_factor;

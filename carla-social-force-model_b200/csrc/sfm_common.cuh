@@ -46,6 +46,7 @@ struct SegmentSet {
     double2* velocity = nullptr;// [count]  obstacle velocity (zeros for borders / static)
     int* offset = nullptr;      // [count + 1]
     double2* point = nullptr;   // [n_points]
+    float* tol = nullptr;       // [count]  float32 bracket width of the two-stage nearest-point search (k2_cells.cuh)
     CellGrid grid{};
     int* cell_start = nullptr;  // [nx * ny + 1]
     int* cell_item = nullptr;   // [count]  set items ordered by (cell, index)
