@@ -394,7 +394,9 @@ __global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const Sy
 struct FinishArgs {
     const float* planes;
     int rows_pad, world, own_block, n_local;
-    const long long* facc_own;      // [rows_pad][4] this rank's block (after the reduce-scatter)
+    const long long* facc_own;      // [rows_pad][4] this rank's block (after the reduce-scatter) ...
+    const long long* facc_peer[7];  // ... or, with peer memory (K7), the same block inside every other rank's accumulator:
+    int n_peer;                     //     the reduce-scatter is the sum below
     double* f_ped;                  // [n_local][3]
     unsigned long long* fixup_rows;
     PairParams pp;
@@ -408,12 +410,17 @@ __global__ void __launch_bounds__(256) k1_sym_finish(const FinishArgs a) {
     double sx = 0.0, sy = 0.0, sz = 0.0;
     bool bad = false;
     if (live) {
-        const long long* f = a.facc_own + (size_t)row * 4;
+        const longlong4 own = *reinterpret_cast<const longlong4*>(a.facc_own + (size_t)row * 4);
+        long long fx = own.x, fy = own.y, fz = own.z, poison = own.w;
+        for (int r = 0; r < a.n_peer; ++r) {            // integer sums: associative, so any order gives the same bits
+            const longlong4 o = *reinterpret_cast<const longlong4*>(a.facc_peer[r] + (size_t)row * 4);
+            fx += o.x; fy += o.y; fz += o.z; poison += o.w;
+        }
         const double inv = 1.0 / 4294967296.0;
-        sx = (double)f[0] * inv;
-        sy = (double)f[1] * inv;
-        sz = (double)f[2] * inv;
-        bad = f[3] != 0;
+        sx = (double)fx * inv;
+        sy = (double)fy * inv;
+        sz = (double)fz * inv;
+        bad = poison != 0;
     }
     unsigned mask = __ballot_sync(0xffffffffu, bad);
     while (mask) {

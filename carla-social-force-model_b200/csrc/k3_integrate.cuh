@@ -33,6 +33,8 @@ struct StepArgs {
     double* f_total;             // [n][3]
     double* f_accel;             // [n][3] or nullptr (kept only when class forces are requested)
     float* planes_own;           // this rank's block of the gather buffer: [NPLANES][rows_pad]
+    float* planes_peer[7];       // the same block inside the other ranks' gather buffers (peer memory, K7) ...
+    int n_peer;                  // ... when the all-gather is fused into this kernel; 0 otherwise
     // parameters
     double dt, tau, max_speed_factor, lambda_ped;
     double ox, oy, oz;
@@ -49,28 +51,35 @@ struct StepArgs {
     double sim_time;
 };
 
-__device__ __forceinline__ void stage_row(float* planes, int64_t rows_pad, int64_t i, double x, double y, double z,
-                                          double r, double vx, double vy, double vz, const StepArgs& a) {
-    planes[PX * rows_pad + i] = (float)(x - a.ox);
-    planes[PY * rows_pad + i] = (float)(y - a.oy);
-    planes[PZ * rows_pad + i] = (float)(z - a.oz);
-    planes[PR * rows_pad + i] = (float)r;
-    planes[PVX * rows_pad + i] = (float)(a.lambda_ped * vx);
-    planes[PVY * rows_pad + i] = (float)(a.lambda_ped * vy);
-    planes[PVZ * rows_pad + i] = (float)(a.lambda_ped * vz);
-    // non-planar flag read by the symmetric pair kernel (its z-free fast path needs z == origin and v_z == 0)
-    planes[PSPARE * rows_pad + i] = ((float)(z - a.oz) != 0.0f || (float)(a.lambda_ped * vz) != 0.0f) ? 1.0f : 0.0f;
+__device__ __forceinline__ void store_row(float* planes, int64_t rows_pad, int64_t i, const float (&v)[NPLANES]) {
+#pragma unroll
+    for (int p = 0; p < NPLANES; ++p) planes[p * rows_pad + i] = v[p];
 }
 
-__device__ __forceinline__ void stage_pad(float* planes, int64_t rows_pad, int64_t i) {
-    planes[PX * rows_pad + i] = PAD_POS;
-    planes[PY * rows_pad + i] = PAD_POS;
-    planes[PZ * rows_pad + i] = 0.0f;
-    planes[PR * rows_pad + i] = 0.0f;
-    planes[PVX * rows_pad + i] = 0.0f;
-    planes[PVY * rows_pad + i] = 0.0f;
-    planes[PVZ * rows_pad + i] = 0.0f;
-    planes[PSPARE * rows_pad + i] = 0.0f;
+// one staged row into this rank's block of the gather buffer and -- fused all-gather -- into every peer's copy of it
+__device__ __forceinline__ void store_row_everywhere(const StepArgs& a, int64_t i, const float (&v)[NPLANES]) {
+    store_row(a.planes_own, a.rows_pad, i, v);
+    for (int r = 0; r < a.n_peer; ++r) store_row(a.planes_peer[r], a.rows_pad, i, v);
+}
+
+__device__ __forceinline__ void stage_row(const StepArgs& a, int64_t i, double x, double y, double z, double r, double vx,
+                                          double vy, double vz) {
+    float v[NPLANES];
+    v[PX] = (float)(x - a.ox);
+    v[PY] = (float)(y - a.oy);
+    v[PZ] = (float)(z - a.oz);
+    v[PR] = (float)r;
+    v[PVX] = (float)(a.lambda_ped * vx);
+    v[PVY] = (float)(a.lambda_ped * vy);
+    v[PVZ] = (float)(a.lambda_ped * vz);
+    // non-planar flag read by the symmetric pair kernel (its z-free fast path needs z == origin and v_z == 0)
+    v[PSPARE] = (v[PZ] != 0.0f || v[PVZ] != 0.0f) ? 1.0f : 0.0f;
+    store_row_everywhere(a, i, v);
+}
+
+__device__ __forceinline__ void stage_pad(const StepArgs& a, int64_t i) {
+    const float v[NPLANES] = {PAD_POS, PAD_POS, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    store_row_everywhere(a, i, v);
 }
 
 // Staging only: master state -> float32 planes (after an upload or a kinematics refresh).
@@ -78,11 +87,11 @@ __global__ void __launch_bounds__(256) k3_stage(StepArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.rows_pad) return;
     if (i >= a.n) {
-        stage_pad(a.planes_own, a.rows_pad, i);
+        stage_pad(a, i);
         return;
     }
     const double4 L = a.locr[i], V = a.vels[i];
-    stage_row(a.planes_own, a.rows_pad, i, L.x, L.y, L.z, L.w, V.x, V.y, V.z, a);
+    stage_row(a, i, L.x, L.y, L.z, L.w, V.x, V.y, V.z);
 }
 
 __global__ void __launch_bounds__(256) k3_integrate(StepArgs a) {
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(256) k3_integrate(StepArgs a) {
         z = __dadd_rn(z, __dmul_rn(vz, a.dt));
         a.locr[i] = make_double4(x, y, z, L.w);
     }
-    stage_row(a.planes_own, a.rows_pad, i, x, y, z, L.w, vx, vy, vz, a);
+    stage_row(a, i, x, y, z, L.w, vx, vy, vz);
     if (a.advance_routes) advance_waypoint(a.routes, a.mm, i, L.x, L.y, a.wp_rw, a.mode_rw, a.sim_time);
 }
 

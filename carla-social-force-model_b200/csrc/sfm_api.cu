@@ -12,6 +12,7 @@
 #include "k2_cells.cuh"
 #include "k3_integrate.cuh"
 #include "k4_lifecycle.cuh"
+#include "k7_peer.cuh"
 
 using namespace sfm;
 
@@ -153,6 +154,15 @@ struct sfm_ctx {
     int64_t rec_capacity = 0, rec_rows = 0, rec_count = 0;
     std::vector<double> rec_times;
     std::vector<int> rt_begin;                     // host copy of the routes' first entries (cursor downloads are relative)
+    // ---- peer-memory exchange (K7): mapped buffers of the other ranks, flag barrier, double-buffered gather buffer
+    bool p2p = false;
+    int parity = 0;                                  // which half of `planes` the pair kernel reads this tick
+    void* peer_planes[MAX_PEERS] = {};               // [rank] base of that rank's `planes` (own entry = own pointer)
+    void* peer_facc[MAX_PEERS] = {};
+    void* peer_flags[MAX_PEERS] = {};
+    DevBuf<unsigned> flags;                          // [MAX_PEERS] epochs signalled by the peers + [MAX_PEERS] error word
+    unsigned epoch = 0;
+    int64_t barriers = 0;
     bool pairs_pending = false;
     bool step_open = false;         // sfm_step_begin done, sfm_step_end outstanding     // symmetric accumulation launched, finish kernel not yet run
 };
@@ -274,17 +284,32 @@ int ensure_layout(sfm_ctx* c, int64_t n) {
         return fail("row count exceeds the rows_pad given to sfm_set_partition");
     }
     if (c->rows_pad * (int64_t)c->world > (int64_t)1 << 30) return fail("too many staged rows");
-    SFM_TRY(c->planes.ensure((size_t)c->world * NPLANES * c->rows_pad));
+    if (c->p2p && (size_t)2 * c->world * NPLANES * c->rows_pad > c->planes.cap)
+        return fail("the row layout changed after the peer-memory exchange was set up");
+    SFM_TRY(c->planes.ensure((size_t)(c->world > 1 ? 2 : 1) * c->world * NPLANES * c->rows_pad));
     return 0;
 }
 
-StepArgs step_args(sfm_ctx* c) {
+// The gather buffer the pair kernel reads this tick, and the one K3 stages the next tick's rows into (the same buffer
+// unless the peer-memory exchange alternates between the two halves).
+float* planes_cur(sfm_ctx* c) { return c->planes.p + (size_t)c->parity * c->world * NPLANES * c->rows_pad; }
+int next_parity(sfm_ctx* c) { return c->p2p ? c->parity ^ 1 : c->parity; }
+
+// `target_parity`: the half of the gather buffer the staged rows go to (K3: the next tick's; k3_stage: either)
+StepArgs step_args(sfm_ctx* c, int target_parity = -1) {
+    if (target_parity < 0) target_parity = next_parity(c);
     StepArgs a{};
     a.locr = c->locr.p; a.vels = c->vels.p; a.wp = c->wp.p; a.mode = c->mode.p;
     a.n = c->n; a.rows_pad = c->rows_pad;
     a.ped_force = c->f_ped.p;
     a.f_total = c->f_total.p;
-    a.planes_own = c->planes.p + (size_t)c->rank * NPLANES * c->rows_pad;
+    const size_t own_off = (size_t)c->rank * NPLANES * c->rows_pad;
+    const size_t half = (size_t)target_parity * c->world * NPLANES * c->rows_pad;
+    a.planes_own = c->planes.p + half + own_off;
+    if (c->p2p) {                                   // fused all-gather: the same block inside every peer's buffer
+        for (int r = 0; r < c->world; ++r)
+            if (r != c->rank) a.planes_peer[a.n_peer++] = reinterpret_cast<float*>(c->peer_planes[r]) + half + own_off;
+    }
     a.dt = c->params.step_length; a.tau = c->params.tau; a.max_speed_factor = c->params.max_speed_factor;
     a.lambda_ped = c->params.ped.lambda_weight;
     a.ox = c->ox; a.oy = c->oy; a.oz = c->oz;
@@ -313,13 +338,31 @@ int ensure_life_counters(sfm_ctx* c) {
     return 0;
 }
 
-int launch_stage(sfm_ctx* c) {
-    SpanGuard g(c, ST_INTEGRATE);
-    StepArgs a = step_args(c);
-    k3_stage<<<cdiv(c->rows_pad, 256), 256, 0, c->stream>>>(a);
+int launch_barrier(sfm_ctx* c) {
+    PeerPtrs fl{};
+    for (int r = 0; r < c->world; ++r) fl.p[r] = c->peer_flags[r];
+    c->epoch += 1;
+    k7_barrier<<<1, 32, 0, c->stream>>>(fl, c->flags.p, c->world, c->rank, c->epoch, c->flags.p + MAX_PEERS);
     c->launches += 1;
+    c->barriers += 1;
     SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// master state -> staged rows of the current tick.  With the peer-memory exchange the rows (pad rows included) go to
+// both halves of every rank's gather buffer, and a barrier makes sure everybody's rows have arrived: a collective call.
+int launch_stage(sfm_ctx* c) {
+    {
+        SpanGuard g(c, ST_INTEGRATE);
+        for (int half = 0; half < (c->p2p ? 2 : 1); ++half) {
+            StepArgs a = step_args(c, c->p2p ? half : c->parity);
+            k3_stage<<<cdiv(c->rows_pad, 256), 256, 0, c->stream>>>(a);
+            c->launches += 1;
+        }
+        SFM_CUDA(cudaGetLastError());
+    }
     c->staged = true;
+    if (c->p2p) SFM_TRY(launch_barrier(c));
     return 0;
 }
 
@@ -341,10 +384,10 @@ int launch_pairs_rows(sfm_ctx* c) {
     do {                                                                                                               \
         if (rad)                                                                                                       \
             k1_ped_pairs<IRV, true, MINBV><<<grid, K1_THREADS, 0, c->stream>>>(                                         \
-                c->planes.p, (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
+                planes_cur(c), (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
         else                                                                                                           \
             k1_ped_pairs<IRV, false, MINBV><<<grid, K1_THREADS, 0, c->stream>>>(                                        \
-                c->planes.p, (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
+                planes_cur(c), (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
     } while (0)
     if (IR == 2 && c->k1_minb <= 5) SFM_K1_LAUNCH(2, 5);
     else if (IR == 2 && c->k1_minb == 6) SFM_K1_LAUNCH(2, 6);
@@ -364,7 +407,7 @@ int launch_pairs_rows(sfm_ctx* c) {
         c->fixup_zeroed = true;
     }
     ReduceArgs ra{};
-    ra.planes = c->planes.p; ra.rows_pad = (int)c->rows_pad; ra.world = c->world; ra.own_block = c->rank;
+    ra.planes = planes_cur(c); ra.rows_pad = (int)c->rows_pad; ra.world = c->world; ra.own_block = c->rank;
     ra.n_local = (int)c->n; ra.partial = c->partial.p; ra.nsplit = nsplit; ra.f_ped = c->f_ped.p;
     ra.fixup_rows = c->fixup_rows.p; ra.pp = pp;
     if (c->params.use_ped_radius) k1_reduce_fixup<true><<<cdiv(c->n, 256), 256, 0, c->stream>>>(ra);
@@ -376,6 +419,7 @@ int launch_pairs_rows(sfm_ctx* c) {
 
 // Symmetric pair kernel, phase 1: zero the fixed-point accumulators and add every tile pair this rank owns.
 int launch_pairs_accumulate(sfm_ctx* c) {
+    if (!c->staged && c->p2p) return fail("peer-memory contexts restage collectively: call sfm_stage on every rank first");
     if (!c->staged) SFM_TRY(launch_stage(c));
     const int own_tiles = (int)(c->rows_pad / K1_TJ);
     const int total_tiles = own_tiles * c->world;
@@ -386,7 +430,7 @@ int launch_pairs_accumulate(sfm_ctx* c) {
     nsplit = std::min(nsplit, half);
     c->nsplit = nsplit;
     SymArgs a{};
-    a.planes = c->planes.p; a.rows_pad = (int)c->rows_pad; a.total_tiles = total_tiles;
+    a.planes = planes_cur(c); a.rows_pad = (int)c->rows_pad; a.total_tiles = total_tiles;
     a.own_first_tile = c->rank * own_tiles; a.facc = c->facc.p; a.pp = make_pair_params(c->params.ped);
     SpanGuard g(c, ST_PAIRS);
     SFM_CUDA(cudaMemsetAsync(c->facc.p, 0, slots * 4 * sizeof(long long), c->stream));
@@ -415,9 +459,13 @@ int launch_pairs_finish(sfm_ctx* c) {
         c->fixup_zeroed = true;
     }
     FinishArgs f{};
-    f.planes = c->planes.p; f.rows_pad = (int)c->rows_pad; f.world = c->world; f.own_block = c->rank;
+    f.planes = planes_cur(c); f.rows_pad = (int)c->rows_pad; f.world = c->world; f.own_block = c->rank;
     f.n_local = (int)c->n; f.facc_own = c->facc.p + (size_t)c->rank * c->rows_pad * 4; f.f_ped = c->f_ped.p;
     f.fixup_rows = c->fixup_rows.p; f.pp = make_pair_params(c->params.ped);
+    if (c->p2p)                                     // fused reduce-scatter: this rank's rows inside every peer's accumulator
+        for (int r = 0; r < c->world; ++r)
+            if (r != c->rank)
+                f.facc_peer[f.n_peer++] = reinterpret_cast<const long long*>(c->peer_facc[r]) + (size_t)c->rank * c->rows_pad * 4;
     SpanGuard g(c, ST_PAIRS);
     if (c->params.use_ped_radius) k1_sym_finish<true><<<cdiv(c->n, 256), 256, 0, c->stream>>>(f);
     else k1_sym_finish<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(f);
@@ -757,6 +805,13 @@ int sfm_destroy(sfm_ctx* c) {
     c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
     c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release(); c->facc.release();
+    if (c->p2p)
+        for (int r = 0; r < c->world; ++r)
+            if (r != c->rank) {
+                cudaIpcCloseMemHandle(c->peer_planes[r]); cudaIpcCloseMemHandle(c->peer_facc[r]);
+                cudaIpcCloseMemHandle(c->peer_flags[r]);
+            }
+    c->flags.release();
     c->mm_speed.release(); c->mm_initial.release(); c->mm_crossing.release(); c->mm_margin.release();
     c->mm_next_time.release(); c->tr_center.release(); c->tr_vel.release(); c->rt_end.release(); c->rt_cursor.release();
     c->rt_wp.release(); c->next_wp3.release(); c->rt_cross.release(); c->finished.release(); c->life_counters.release();
@@ -1380,6 +1435,80 @@ int sfm_download_frames(sfm_ctx* c, int64_t first, int64_t count, double* xyv, u
     if (mode) SFM_CUDA(cudaMemcpyAsync(mode, c->rec_mode.p + at, items, cudaMemcpyDeviceToHost, c->stream));
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     if (times) for (int64_t k = 0; k < count; ++k) times[k] = c->rec_times[first + k];
+    return 0;
+}
+
+/* ---- peer-memory exchange (K7) ------------------------------------------------------------------------------------- */
+int sfm_peer_export(sfm_ctx* c, void* handles) {
+    SFM_TRY(check_ctx(c));
+    if (!handles) return fail("null pointer");
+    if (!c->partition_fixed || c->world < 2) return fail("sfm_set_partition (world >= 2) must be called first");
+    if (c->world > MAX_PEERS) return fail("the peer-memory exchange supports up to 8 ranks (one box)");
+    if (!c->planes.p) return fail("no state uploaded yet");
+    SFM_TRY(c->facc.ensure((size_t)c->world * c->rows_pad * 4));
+    SFM_TRY(c->flags.ensure(2 * MAX_PEERS));
+    SFM_CUDA(cudaMemsetAsync(c->flags.p, 0, 2 * MAX_PEERS * sizeof(unsigned), c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(handles);
+    SFM_CUDA(cudaIpcGetMemHandle(&h[0], c->planes.p));
+    SFM_CUDA(cudaIpcGetMemHandle(&h[1], c->facc.p));
+    SFM_CUDA(cudaIpcGetMemHandle(&h[2], c->flags.p));
+    return 0;
+}
+
+int sfm_peer_import(sfm_ctx* c, const void* all_handles) {
+    SFM_TRY(check_ctx(c));
+    if (!all_handles) return fail("null pointer");
+    if (!c->flags.p) return fail("sfm_peer_export must be called first");
+    const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) {
+            c->peer_planes[r] = c->planes.p; c->peer_facc[r] = c->facc.p; c->peer_flags[r] = c->flags.p;
+            continue;
+        }
+        SFM_CUDA(cudaIpcOpenMemHandle(&c->peer_planes[r], h[3 * r + 0], cudaIpcMemLazyEnablePeerAccess));
+        SFM_CUDA(cudaIpcOpenMemHandle(&c->peer_facc[r], h[3 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+        SFM_CUDA(cudaIpcOpenMemHandle(&c->peer_flags[r], h[3 * r + 2], cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->p2p = true;
+    c->parity = 0;
+    c->staged = false;
+    return 0;
+}
+
+int sfm_peer_barrier(sfm_ctx* c) {
+    SFM_TRY(check_ctx(c));
+    if (!c->p2p) return fail("the peer-memory exchange is not set up");
+    return launch_barrier(c);
+}
+
+int sfm_step_peer(sfm_ctx* c, int n_steps, int integrate_positions) {
+    SFM_TRY(check_ctx(c));
+    if (!c->p2p) return fail("the peer-memory exchange is not set up (sfm_peer_export / sfm_peer_import)");
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (c->k1_rows_mode) return fail("the peer-memory exchange needs the symmetric pair kernel");
+    for (int s = 0; s < n_steps; ++s) {
+        SFM_TRY(step_begin(c));                          // pair accumulation into this rank's accumulator + cell-list forces
+        SFM_TRY(launch_barrier(c));                      // every rank's accumulator is complete
+        SFM_TRY(step_end(c, true, integrate_positions != 0, false));   // pull-reduce + finish, K3 with the fused push
+        SFM_TRY(launch_barrier(c));                      // everybody has read my accumulator and received my rows
+        c->parity ^= 1;
+    }
+    return 0;
+}
+
+int sfm_peer_status(sfm_ctx* c, int64_t* barriers, int* timed_out) {
+    SFM_TRY(check_ctx(c));
+    if (barriers) *barriers = c->barriers;
+    if (timed_out) {
+        *timed_out = 0;
+        if (c->flags.p) {
+            unsigned e = 0;
+            SFM_CUDA(cudaMemcpyAsync(&e, c->flags.p + MAX_PEERS, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+            SFM_CUDA(cudaStreamSynchronize(c->stream));
+            *timed_out = (int)e;
+        }
+    }
     return 0;
 }
 

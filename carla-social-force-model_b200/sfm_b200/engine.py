@@ -2,9 +2,16 @@
 
 Rows shard: each rank owns the state, the cell-list forces and the integration of a contiguous row block.  The pair
 force is evaluated once per unordered pair by exactly one rank (half-shell over 256-row tiles), so a step has two
-exchanges through ``torch.distributed`` (NCCL over NVLink; gloo in the CPU tests): an integer reduce-scatter of the
-fixed-point force accumulators (32 B per pedestrian) and an all-gather of each rank's staged block (32 B per pedestrian).  torch is plumbing only -- streams, the process group and a tensor view of the library's gather buffer; all
-arithmetic runs in ``libsfm_b200.so``.
+exchanges: an integer reduce-scatter of the fixed-point force accumulators (32 B per pedestrian) and an all-gather of
+each rank's staged block (32 B per pedestrian).  Two transports:
+
+* ``exchange='peer'`` (default on one box): the library maps every rank's buffers through CUDA IPC once, and the two
+  collectives are folded into its own kernels -- ``k1_sym_finish`` pulls the partial accumulators over NVLink, K3 pushes
+  the staged rows into every peer's gather buffer, flag barriers in between (``csrc/k7_peer.cuh``).  ``torch.distributed``
+  only carries the 192-byte handle table at set-up.
+* ``exchange='nccl'``: ``reduce_scatter_tensor`` / ``all_gather_into_tensor`` on tensor views of the library's buffers.
+
+torch is plumbing only -- streams, the process group, tensor views; all arithmetic runs in ``libsfm_b200.so``.
 """
 from __future__ import annotations
 
@@ -39,8 +46,12 @@ class _DeviceView:
 
 
 class Engine:
-    def __init__(self, sfm_config, step_length, device=None, group=None, use_torch_stream=True):
+    def __init__(self, sfm_config, step_length, device=None, group=None, use_torch_stream=True, exchange=None):
+        import os
         import torch                                   # plumbing only
+        self.exchange_mode = exchange or os.environ.get('SFM_EXCHANGE', 'peer')
+        if self.exchange_mode not in ('peer', 'nccl'):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
         self.torch = torch
         if not torch.cuda.is_available():
             raise native.SfmError('no CUDA device: the Social Force Model step has no CPU fallback')
@@ -81,14 +92,29 @@ class Engine:
             self.ctx.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles],
                                    [r for _, r in w.static_obstacles])
         self.set_vehicles(w.vehicles_at(0))
-        self.ctx.stage()
-        self._bind_gather()
-        self.exchange()
+        if self.world > 1 and self.exchange_mode == 'peer':
+            self._bind_peers()
+            self.ctx.stage()                               # collective: rows pushed to every rank + barrier
+        else:
+            self.ctx.stage()
+            self._bind_gather()
+            self.exchange()
 
     def set_vehicles(self, dyn_tuple):
         """The 6-tuple of pedestrian_simulation.py:108-115 (ids, centres, headings, velocities, extents, rings)."""
         if dyn_tuple is not None:
             self.ctx.set_obstacles(native.DYNAMIC_OBSTACLE, dyn_tuple[1], dyn_tuple[5], dyn_tuple[3])
+
+    @property
+    def peer(self):
+        return self.world > 1 and self.exchange_mode == 'peer'
+
+    def _bind_peers(self):
+        """Exchange the CUDA IPC handles of (gather buffer, force accumulator, barrier flags) once."""
+        mine = self.ctx.peer_export()
+        table = [None] * self.world
+        self.dist.all_gather_object(table, mine, group=self.group)
+        self.ctx.peer_import(table)
 
     def _bind_gather(self):
         if self.world == 1:
@@ -122,6 +148,9 @@ class Engine:
         if self.world == 1:
             self.ctx.step(n_steps, integrate_positions)
             return
+        if self.peer:
+            self.ctx.step_peer(n_steps, integrate_positions)
+            return
         for _ in range(n_steps):
             self.ctx.step_begin()
             self.reduce_forces()
@@ -135,6 +164,10 @@ class Engine:
             return
         self.ctx.update_kinematics(loc, vel)        # refresh -> restage -> exchange -> step, so every rank sees the
         self.ctx.stage()                            # other ranks' refreshed rows
+        if self.peer:
+            self.ctx.step_peer(1, new_loc is not None)
+            self.ctx.download_state(new_loc if new_loc is not None else np.empty_like(new_vel), new_vel)
+            return
         self.exchange()
         self.ctx.step_begin()
         self.reduce_forces()

@@ -31,7 +31,9 @@ SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create'
            'sfm_set_mode_machines', 'sfm_set_traffic', 'sfm_tick_modes', 'sfm_download_modes', 'sfm_set_routes',
            'sfm_advance_waypoints', 'sfm_download_routes', 'sfm_lifecycle_counters', 'sfm_set_vehicles',
            'sfm_advance_vehicles', 'sfm_download_vehicles', 'sfm_record_begin', 'sfm_record_frame',
-           'sfm_download_frames')
+           'sfm_download_frames',
+           # peer-memory exchange (K7)
+           'sfm_peer_export', 'sfm_peer_import', 'sfm_step_peer', 'sfm_peer_barrier', 'sfm_peer_status')
 
 
 class SfmError(RuntimeError):
@@ -137,6 +139,11 @@ def lib():
         'sfm_record_begin': (C.c_int, [p_ctx, i64]),
         'sfm_record_frame': (C.c_int, [p_ctx, C.c_double]),
         'sfm_download_frames': (C.c_int, [p_ctx, i64, i64, p_d, p_u8, p_d, p_i64]),
+        'sfm_peer_export': (C.c_int, [p_ctx, C.c_void_p]),
+        'sfm_peer_import': (C.c_int, [p_ctx, C.c_void_p]),
+        'sfm_step_peer': (C.c_int, [p_ctx, C.c_int, C.c_int]),
+        'sfm_peer_barrier': (C.c_int, [p_ctx]),
+        'sfm_peer_status': (C.c_int, [p_ctx, p_i64, C.POINTER(C.c_int)]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -356,6 +363,29 @@ class Context:
 
     def stage(self):
         _check(self._lib.sfm_stage(self._h))
+
+    # -- peer-memory exchange (K7)
+    PEER_HANDLE_BYTES = 3 * 64
+
+    def peer_export(self):
+        buf = C.create_string_buffer(self.PEER_HANDLE_BYTES)
+        _check(self._lib.sfm_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_import(self, handles_by_rank):
+        blob = b''.join(handles_by_rank)
+        _check(self._lib.sfm_peer_import(self._h, C.create_string_buffer(blob, len(blob))))
+
+    def step_peer(self, n_steps=1, integrate_positions=True):
+        _check(self._lib.sfm_step_peer(self._h, int(n_steps), int(bool(integrate_positions))))
+
+    def peer_barrier(self):
+        _check(self._lib.sfm_peer_barrier(self._h))
+
+    def peer_status(self):
+        n, bad = C.c_int64(), C.c_int()
+        _check(self._lib.sfm_peer_status(self._h, C.byref(n), C.byref(bad)))
+        return dict(barriers=n.value, timed_out=bool(bad.value))
 
     # -- lifecycle on the device
     def set_mode_machines(self, initial_target_speed, crossing_speed, crossing_safety_margin, mode_target_speed=None,

@@ -145,6 +145,21 @@ int sfm_force_accumulator(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_ran
  * first all-gather can run before the first step. */
 int sfm_stage(sfm_ctx* ctx);
 
+/* ---- peer-memory exchange over NVLink (K7): the two collectives of the multi-GPU tick folded into the kernels next to
+ *      them.  Set-up (once, after sfm_set_partition + sfm_upload_state on every rank): each rank exports three
+ *      cudaIpcMemHandle_t (gather buffer, force accumulator, barrier flags: 3 x 64 bytes), the host side all-gathers
+ *      them, each rank imports the table [world][3].  From then on sfm_stage and sfm_step_peer are COLLECTIVE calls:
+ *      every rank of the box must make them in the same order. ------------------------------------------------------- */
+int sfm_peer_export(sfm_ctx* ctx, void* handles);
+int sfm_peer_import(sfm_ctx* ctx, const void* all_handles);
+/* One tick = pair accumulation + cell-list forces; flag barrier; k1_sym_finish pulling every rank's partial accumulator
+ * of its rows over NVLink (the reduce-scatter); K3 pushing the newly staged rows into every rank's gather buffer (the
+ * all-gather); flag barrier.  No NCCL call on the path. */
+int sfm_step_peer(sfm_ctx* ctx, int n_steps, int integrate_positions);
+int sfm_peer_barrier(sfm_ctx* ctx);
+/* barriers executed so far; timed_out != 0 when a barrier gave up waiting for a peer (~2 s). */
+int sfm_peer_status(sfm_ctx* ctx, int64_t* barriers, int* timed_out);
+
 /* ---- lifecycle on the device: what PedestrianSimulation.tick and SimulationRunner.tick do in
  *      interpreter loops around the forces.  All per-row tables are dropped by the next sfm_upload_state. ------------- */
 /* f1.  The persistent fields of every pedestrian's PedModeManager (ped_mode_manager.py:18-28): initial_target_speed,

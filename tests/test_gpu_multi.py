@@ -1,4 +1,5 @@
-"""Real multi-GPU path (NCCL all-gather + integer reduce-scatter) -- runs only where >= 2 GPUs are visible."""
+"""Real multi-GPU path, both transports (peer memory: pull-reduce + push fused into the kernels, flag barriers; NCCL:
+all-gather + integer reduce-scatter) -- runs only where >= 2 GPUs are visible."""
 import os
 import socket
 
@@ -10,7 +11,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _rank_main(rank, world, port, n, steps, out_dir):
+def _rank_main(rank, world, port, n, steps, out_dir, exchange):
     import sys
     import tomllib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,17 +24,20 @@ def _rank_main(rank, world, port, n, steps, out_dir):
     with open(os.path.join(pkg, 'config', 'sfm_config.toml'), 'rb') as f:
         cfg = tomllib.load(f)
     w = synth.make_config(2, n=n)
-    e = engine.Engine(cfg, w.step_length, device=rank)
+    e = engine.Engine(cfg, w.step_length, device=rank, exchange=exchange)
     e.load(w)
     e.step(steps, True)
     loc, vel = e.local_state()
+    status = e.ctx.peer_status()
+    assert not status['timed_out'] and (status['barriers'] == 1 + 2 * steps if exchange == 'peer' else status['barriers'] == 0)
     np.savez(os.path.join(out_dir, f'r{rank}.npz'), loc=loc, vel=vel, lo=e.lo, hi=e.hi)
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
 
+@pytest.mark.parametrize('exchange', ['peer', 'nccl'])
 @pytest.mark.parametrize('n', [3000, 4096])
-def test_two_gpu_engine_matches_single_gpu(tmp_path, sfm_config, n):
+def test_two_gpu_engine_matches_single_gpu(tmp_path, sfm_config, n, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs')
     from sfm_b200 import synth
@@ -42,7 +46,7 @@ def test_two_gpu_engine_matches_single_gpu(tmp_path, sfm_config, n):
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
     steps = 3
-    mp.spawn(_rank_main, args=(2, port, n, steps, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_rank_main, args=(2, port, n, steps, str(tmp_path), exchange), nprocs=2, join=True)
     w = synth.make_config(2, n=n)
     whole = make_context(w, sfm_config)
     whole.step(steps, True)
