@@ -130,6 +130,9 @@ struct sfm_ctx {
     std::vector<cudaEvent_t> event_pool;
     int k1_target_ctas = 148 * 4 * 16;
     int k1_ir = 2, k1_minb = 5;     // tuning knobs (SFM_K1_IR, SFM_K1_MINB)
+    bool k1_first = false;
+    int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
+                                    // cell-list kernels stay co-resident on every SM (see step_begin)
     int k1_rows_mode = 0;           // SFM_K1_MODE=rows: ordered-pair row kernel instead of the symmetric one
     DevBuf<long long> facc;         // [world * rows_pad][4] fixed-point force accumulators + poison counter
     // ---- lifecycle: mode machines, traffic, routes, device-generated vehicle rings, recorder
@@ -435,8 +438,10 @@ int launch_pairs_accumulate(sfm_ctx* c) {
     SpanGuard g(c, ST_PAIRS);
     SFM_CUDA(cudaMemsetAsync(c->facc.p, 0, slots * 4 * sizeof(long long), c->stream));
     dim3 grid(own_tiles, nsplit);
-    if (c->params.use_ped_radius) k1_sym_pairs<true><<<grid, KS_THREADS, 0, c->stream>>>(a);
-    else k1_sym_pairs<false><<<grid, KS_THREADS, 0, c->stream>>>(a);
+    // experiment knob: extra dynamic shared memory caps the pair kernel's CTAs per SM while cell-list kernels are in flight
+    const int pad = c->join_pending ? c->k1_smem_pad : 0;
+    if (c->params.use_ped_radius) k1_sym_pairs<true><<<grid, KS_THREADS, pad, c->stream>>>(a);
+    else k1_sym_pairs<false><<<grid, KS_THREADS, pad, c->stream>>>(a);
     c->launches += 1;
     c->pair_launches += 1;
     for (int t = 0; t < own_tiles; ++t) {        // pair terms this launch evaluates: half shell + the diagonal tile
@@ -672,28 +677,29 @@ int step_begin(sfm_ctx* c) {
     const bool any_set = (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) ||
                          (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) ||
                          (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count);
-    // The cell-list kernels are FP64 / latency bound, the pair kernel FP32 issue bound: run them concurrently.  The
-    // auxiliary (high-priority) stream forks from the main stream here and is joined before K3.
-    cudaStream_t st2 = c->stream;
-    if (any_set && c->overlap && P.enable[SFM_FORCE_PEDESTRIAN]) {
-        st2 = c->aux_stream;
+    // The cell-list kernels run on the auxiliary (high-priority) stream, forked from the main stream here and joined
+    // before K3; the pair kernel fills the machine behind them.  SFM_K1_FIRST / SFM_AUX_PRIORITY / SFM_K1_SMEM_PAD are
+    // the knobs of the co-residency experiments (profiles/overlap_sweep.sh).
+    const bool forked = any_set && c->overlap && P.enable[SFM_FORCE_PEDESTRIAN];
+    cudaStream_t st2 = forked ? c->aux_stream : c->stream;
+    if (forked) {
         SFM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         SFM_CUDA(cudaStreamWaitEvent(st2, c->ev_fork, 0));
+        c->join_pending = true;
     }
+    auto pairs = [&]() -> int {
+        if (!P.enable[SFM_FORCE_PEDESTRIAN]) return 0;
+        return c->k1_rows_mode ? launch_pairs_rows(c) : launch_pairs_accumulate(c);
+    };
+    if (forked && c->k1_first) SFM_TRY(pairs());
     if (any_set && !c->perm_valid) SFM_TRY(rebin_peds(c, st2));
     if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0, st2));
     if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count)
         SFM_TRY(launch_segments(c, SFM_FORCE_STATIC_OBSTACLE, false, 0, st2));
     if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count)
         SFM_TRY(launch_segments(c, SFM_FORCE_DYNAMIC_OBSTACLE, false, 0, st2));
-    if (st2 != c->stream) {
-        SFM_CUDA(cudaEventRecord(c->ev_join, st2));
-        c->join_pending = true;
-    }
-    if (P.enable[SFM_FORCE_PEDESTRIAN]) {
-        if (c->k1_rows_mode) SFM_TRY(launch_pairs_rows(c));
-        else SFM_TRY(launch_pairs_accumulate(c));
-    }
+    if (forked) SFM_CUDA(cudaEventRecord(c->ev_join, st2));
+    if (!(forked && c->k1_first)) SFM_TRY(pairs());
     c->step_open = true;
     return 0;
 }
@@ -776,11 +782,24 @@ int sfm_create(int device, sfm_ctx** out) {
     SFM_CUDA(cudaSetDevice(device));
     sfm_ctx* c = new sfm_ctx();
     c->device = device;
-    SFM_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->stream = c->own_stream;
     int prio_lo = 0, prio_hi = 0;
     SFM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    SFM_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi));
+    // Measured on cfg3 (profiles/overlap_sweep_r1*.log): both kernels are issue-slot bound, so co-residency buys nothing
+    // -- the best schedule lets the cell-list kernels claim the machine first (high priority, enqueued first, 4.93 ms
+    // per tick) and the pair kernel fill in behind them; pair-kernel-first / equal priorities / capped CTAs: 5.24-5.73.
+    int own_prio = prio_lo, aux_prio = prio_hi;
+    if (const char* env = std::getenv("SFM_AUX_PRIORITY")) {
+        if (std::strcmp(env, "low") == 0) { own_prio = prio_hi; aux_prio = prio_lo; }
+        if (std::strcmp(env, "equal") == 0) { own_prio = prio_lo; aux_prio = prio_lo; }
+    }
+    SFM_CUDA(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, own_prio));
+    c->stream = c->own_stream;
+    SFM_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, aux_prio));
+    c->k1_smem_pad = 0;
+    if (const char* env = std::getenv("SFM_K1_SMEM_PAD")) c->k1_smem_pad = std::max(0, std::atoi(env));
+    if (const char* env = std::getenv("SFM_K1_FIRST")) c->k1_first = std::atoi(env) != 0;
+    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char* env = std::getenv("SFM_OVERLAP")) c->overlap = std::atoi(env) != 0;

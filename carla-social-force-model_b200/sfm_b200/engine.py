@@ -66,7 +66,8 @@ class Engine:
         self.ctx.set_params(native.params_from_config(sfm_config, step_length))
         # A dedicated (non-default) torch stream carries both the library's kernels and the NCCL all-gather, so the
         # two are ordered without host synchronisation; CUDA events recorded on it time the whole step.
-        self.stream = torch.cuda.Stream(self.device) if use_torch_stream else None
+        prio = -1 if os.environ.get('SFM_AUX_PRIORITY', 'high') == 'low' else 0      # experiment knob, see sfm_api.cu
+        self.stream = torch.cuda.Stream(self.device, priority=prio) if use_torch_stream else None
         if self.stream is not None:
             self.ctx.set_stream(self.stream.cuda_stream)
         self.n_global = 0
