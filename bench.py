@@ -170,7 +170,7 @@ def run_ours(args, world, rank, local_rank):
     w, name = build_workload(args, world)
     n = w.n
     e = eng.Engine(cfg, w.step_length, device=local_rank)
-    e.load(w)
+    e.load(w, device_vehicles=(args.workload == 'cfg4'))     # cfg4: vehicle rings regenerated on the device every tick
     ctx = e.ctx
     stream = e.stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')       # > 126 MB L2
@@ -267,7 +267,7 @@ def run_ours(args, world, rank, local_rank):
         k1_ordered_rate = (e.hi - e.lo) * (n - 1) / (k1_ms * 1e-3)
         achieved = k1_rate * instr / 1e12
         traffic = None
-        prof = os.path.join(ROOT, 'profiles', 'k1_ncu_summary.json')
+        prof = os.path.join(ROOT, 'profiles', 'k1_ncu_summary.json')          # ncu --set full capture of k1_sym_pairs
         if os.path.exists(prof):
             with open(prof) as f:
                 traffic = json.load(f).get('dram_bytes_per_launch')
@@ -280,7 +280,13 @@ def run_ours(args, world, rank, local_rank):
             'dtype': 'f32 pair forces / f64 state, cell-list forces and integration', 'data': 'synthetic',
             'config': {'workload': name, 'n_pedestrians': n, 'rows_per_gpu': rows, 'step_length': w.step_length,
                        'forces': 'all five on', 'l2': 'flushed between timed steps (256 MiB fill, outside the timed spans)',
-                       'partition': f'row blocks over {world} rank(s), all-gather of 32 B/pedestrian per step'},
+                       'partition': (f'row blocks over {world} rank(s); per tick an integer reduce-scatter of the pair-force '
+                                     f'accumulators and an all-gather of the staged rows (32 B/pedestrian each), transport: '
+                                     + ('none (1 rank)' if world == 1 else
+                                        ('peer memory over NVLink, fused into k1_sym_finish / k3_integrate (K7)'
+                                         if e.peer else 'NCCL reduce_scatter + all_gather'))),
+                       'vehicles': ('device-resident: centres advanced and ellipse rings regenerated on the device every tick'
+                                    if e.device_vehicles else 'none' if w.veh_center is None else 'host rings')},
             'e2e': {'value': e2e_value, 'unit': 'pair-interactions/s', 'ms_per_step': e2e_ms_per_step,
                     'h2d_bytes_per_step': int(rows * 48), 'd2h_bytes_per_step': int(rows * 48), 'steps': e2e_steps,
                     'api': 'sfm_tick_host (pinned host loc/vel in, new loc/vel out)'},

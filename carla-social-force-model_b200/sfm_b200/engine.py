@@ -73,9 +73,10 @@ class Engine:
         self.n_global = 0
         self.bounds = None
         self._gather = None
+        self.device_vehicles = False
 
     # ---- set-up ---------------------------------------------------------------------------------------------------
-    def load(self, w):
+    def load(self, w, device_vehicles=False):
         """Take a ``synth.Workload`` (or anything with the same attributes): this rank keeps its row block."""
         self.n_global = w.n
         self.bounds = partition_rows(w.n, self.world)
@@ -92,7 +93,13 @@ class Engine:
         if len(w.static_obstacles):
             self.ctx.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles],
                                    [r for _, r in w.static_obstacles])
-        self.set_vehicles(w.vehicles_at(0))
+        self.device_vehicles = bool(device_vehicles) and w.veh_center is not None and len(w.veh_center) > 0
+        if self.device_vehicles:
+            # the vehicle set lives on the device (replicated on every rank): centres advance ballistically and the
+            # ellipse rings are regenerated there every tick (obstacles.py:269-281,297-329) -- no per-tick upload
+            self.ctx.set_vehicles(w.veh_center, w.veh_yaw, w.veh_vel, w.veh_extent, w.veh_resolution)
+        else:
+            self.set_vehicles(w.vehicles_at(0))
         if self.world > 1 and self.exchange_mode == 'peer':
             self._bind_peers()
             self.ctx.stage()                               # collective: rows pushed to every rank + barrier
@@ -146,6 +153,11 @@ class Engine:
 
     # ---- stepping -------------------------------------------------------------------------------------------------
     def step(self, n_steps=1, integrate_positions=True):
+        if self.device_vehicles:
+            for _ in range(n_steps):
+                self.ctx.advance_vehicles(self.step_length)
+                self._step_once(integrate_positions)
+            return
         if self.world == 1:
             self.ctx.step(n_steps, integrate_positions)
             return
@@ -153,6 +165,14 @@ class Engine:
             self.ctx.step_peer(n_steps, integrate_positions)
             return
         for _ in range(n_steps):
+            self._step_once(integrate_positions)
+
+    def _step_once(self, integrate_positions):
+        if self.world == 1:
+            self.ctx.step(1, integrate_positions)
+        elif self.peer:
+            self.ctx.step_peer(1, integrate_positions)
+        else:
             self.ctx.step_begin()
             self.reduce_forces()
             self.ctx.step_end(integrate_positions)
@@ -160,6 +180,8 @@ class Engine:
 
     def tick_host(self, loc, vel, new_vel, new_loc=None):
         """One tick with host buffers for this rank's rows (H2D, kernels, D2H inside the call)."""
+        if self.device_vehicles:
+            self.ctx.advance_vehicles(self.step_length)
         if self.world == 1:
             self.ctx.tick_host(loc, vel, new_vel, new_loc)
             return
