@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the per-tick Social Force Model step (BASELINE.json metric) -- prints ONE JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4|cfg5] [--n N]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4|cfg5] [--peds N]
 
 A step = one tick of the hot path over the whole synthetic crowd: all enabled force classes (all-pairs pedestrian force,
 border / static-obstacle / dynamic-obstacle cell-list forces, acceleration force) + force sum + speed clamp + Euler
@@ -336,7 +336,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg4', 'cfg5'])
-    ap.add_argument('--n', type=int, default=None, help='override the pedestrian count')
+    ap.add_argument('--peds', dest='n', type=int, default=None, help='override the pedestrian count')
     ap.add_argument('--cpu-rows-per-core', type=int, default=48)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

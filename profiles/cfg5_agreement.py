@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--phase', required=True, choices=['multi', 'single', 'compare'])
     ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--n', type=int, default=1048576)
+    ap.add_argument('--peds', dest='n', type=int, default=1048576)
     ap.add_argument('--oracle-rows', type=int, default=48)
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
