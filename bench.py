@@ -184,12 +184,12 @@ def run_ours(args, world, rank, local_rank):
     # ---- device-resident timing ---------------------------------------------------------------------------------
     for _ in range(args.warmup + (3 if world > 1 else 0)):     # NCCL builds its channels lazily: a few extra untimed steps
         e.step(1, True)
-    barrier()
-    ctx.reset_stats()
-    ctx.set_profiling(True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 else None            # NVML start-up costs ~0.1 s on rank 0 only:
+    ctx.reset_stats()                                                     # keep it in front of the barrier, or the other
+    ctx.set_profiling(True)                                               # ranks' first timed tick waits for rank 0
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
     t_wall = time.perf_counter()
     for k in range(args.steps):
         with torch.cuda.stream(stream):
