@@ -200,7 +200,8 @@ def run_ours(args, world, rank, local_rank):
     barrier()
     wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if sampler else None
-    ms_total = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+    per_step = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    ms_total = sum(per_step)
     stats = ctx.stats()
     ctx.set_profiling(False)
     t = torch.tensor([ms_total, stats['ms_pairs'], stats['ms_integrate'], stats['ms_segments'] + stats['ms_cells']],
@@ -311,6 +312,7 @@ def run_ours(args, world, rank, local_rank):
                              'frac': (k3_gbs / float(peaks.get('hbm_gbs', 6650.0))) if k3_gbs else None,
                              'ms_per_launch': k3_ms, 'peak_kind': peak_kind},
             'clocks': clocks, 'wall_s_timed_loop': wall,
+            'ms_per_step_rank0': {'median': float(np.median(per_step)), 'min': float(min(per_step)), 'max': float(max(per_step))},
         }
         if clocks and clocks.get('sm_mhz'):
             line['roofline']['frac_at_sampled_clock'] = achieved / (SMS * LANES * clocks['sm_mhz'] * 1e6 / 1e12)
