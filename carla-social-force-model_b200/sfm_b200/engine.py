@@ -38,6 +38,18 @@ def padded_rows(bounds):
     return max(ROW_ALIGN, (largest + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN)
 
 
+def crowd_origin(loc):
+    """Origin of the float32 staging copies: the centre of the crowd's bounding box rounded to whole metres (so that
+    coordinates which are exact in float32 mostly stay exact), z of the first pedestrian (a flat crowd stages z = 0 and
+    takes the planar fast path).  Halves the largest staged magnitude -- and with it the float32 rounding of positions --
+    compared with an origin at (0, 0)."""
+    if len(loc) == 0:
+        return 0.0, 0.0, 0.0
+    lo, hi = loc[:, :2].min(axis=0), loc[:, :2].max(axis=0)
+    cx, cy = np.round((lo + hi) * 0.5)
+    return float(cx), float(cy), float(loc[0, 2])
+
+
 class _DeviceView:
     """Minimal ``__cuda_array_interface__`` holder so torch can alias memory owned by the library."""
 
@@ -83,8 +95,7 @@ class Engine:
         lo, hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
         if self.world > 1:
             self.ctx.set_partition(self.world, self.rank, padded_rows(self.bounds))
-        # one origin for every rank; z of the first pedestrian, so a flat crowd stages z = 0 (planar fast path)
-        self.ctx.set_origin(0.0, 0.0, float(w.loc[0, 2]) if w.n else 0.0)
+        self.ctx.set_origin(*crowd_origin(w.loc))          # one origin for every rank
         self.ctx.upload_state(w.loc[lo:hi], w.vel[lo:hi], w.next_waypoint[lo:hi], w.radius[lo:hi],
                               w.target_speed[lo:hi], w.mode[lo:hi])
         self.lo, self.hi = lo, hi

@@ -166,3 +166,32 @@ def test_standalone_waypoint_advance_and_recorder(scenario, sfm_config, tmp_path
     lines = open(os.path.join(gen.output_dir, 'pedestrian.csv')).read().splitlines()
     assert lines[0] == 'ped_id,frame,time,x,y,v_x,v_y,mode' and len(lines) == 1 + 4 * w.n
     assert lines[1].split(',')[:3] == ['0', '0', '0.0']
+
+
+def test_headless_loop_with_device_vehicles(scenario, sfm_config):
+    """The fully device-resident loop: vehicles advanced and their rings regenerated on the device every tick, gap
+    acceptance against that set.  Oracle: the same loop with centres accumulated the same way and rings restated from
+    obstacles.py:269-281 (float64, unrounded)."""
+    w, life = scenario
+    run = HeadlessRunner(sfm_config, w, life, device_vehicles=True)
+    centres = [w.veh_center.copy()]
+
+    def vehicles_at(step):
+        while len(centres) <= step:
+            centres.append(centres[-1] + w.veh_vel * w.step_length)
+        c = centres[step]
+        rings = [LO.ellipse_ring(c[v], w.veh_yaw[v], w.veh_extent[v, 0], w.veh_extent[v, 1], w.veh_resolution)
+                 for v in range(len(c))]
+        return (None, list(c), list(w.veh_yaw), list(w.veh_vel), list(w.veh_extent), rings)
+
+    steps = 60
+    scene = O.Scene(sfm_config, w.step_length, w.borders, w.section_center, w.section_length, w.static_obstacles)
+    want = LO.run_headless(scene, w, life, steps, vehicles_at=vehicles_at)
+    for k in range(steps):
+        run.tick()
+        s = run.snapshot()
+        assert np.array_equal(s['mode'], want['mode'][k + 1]), f'modes differ after tick {k}'
+        assert np.array_equal(s['wp'], want['wp'][k + 1])
+    assert np.abs(s['loc'] - want['loc'][-1]).max() < 1e-2
+    got_c, _ = run.ctx.download_vehicles()
+    assert np.array_equal(got_c, centres[steps - 1])

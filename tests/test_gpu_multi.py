@@ -49,6 +49,8 @@ def test_two_gpu_engine_matches_single_gpu(tmp_path, sfm_config, n, exchange):
     mp.spawn(_rank_main, args=(2, port, n, steps, str(tmp_path), exchange), nprocs=2, join=True)
     w = synth.make_config(2, n=n)
     whole = make_context(w, sfm_config)
+    from sfm_b200.engine import crowd_origin
+    whole.set_origin(*crowd_origin(w.loc))                    # the engine's staging origin
     whole.step(steps, True)
     loc_w, vel_w = whole.download_state()
     parts = [np.load(tmp_path / f'r{r}.npz') for r in range(2)]
