@@ -229,6 +229,8 @@ struct SegArgs {
     const int* offset;
     const double2* point;
     const float* tol;               // [count] float32 bracket width of the two-stage nearest-point search
+    const int* chunk_first;         // [count] first entry of the item's pruning chunks in `chunk`, or -1 (may be null)
+    const float4* chunk;            // two float4 per chunk: (a_x, a_y, u_x, u_y), (1/|u|^2, deviation, -, -), centre-relative
     CellGrid grid;
     const int* cell_start;
     const int* cell_item;
@@ -301,6 +303,64 @@ __device__ __forceinline__ int exact_argmin(const double2* __restrict__ point, i
     return best_q;
 }
 
+
+// ---- stage 1 helpers: float32 scans over staged, centre-relative points ---------------------------------------------
+constexpr int K2_PRUNE_CHUNK = 16;      // points per pruning chunk (chord + deviation, built at upload)
+constexpr int K2_PRUNE_MAX = K2_CHUNK / K2_PRUNE_CHUNK;      // chunk tables cover items that fit one staging pass
+constexpr float K2_FAR = 1.0e18f;       // pad value: d2 = 2e36, finite, never a candidate
+
+// smallest squared distance over sp[q0 .. q1) (q0, q1 multiples of 4)
+__device__ __forceinline__ float scan_min(const float2* __restrict__ sp, int q0, int q1, float pxf, float pyf, float m1) {
+#pragma unroll 2
+    for (int q = q0; q < q1; q += 4) {
+        const float4 A = *reinterpret_cast<const float4*>(&sp[q]);
+        const float4 B = *reinterpret_cast<const float4*>(&sp[q + 2]);
+        const float ax = pxf - A.x, ay = pyf - A.y, bx = pxf - A.z, by = pyf - A.w;
+        const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
+        const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
+        const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
+        m1 = fminf(fminf(m1, d0), fminf(d1, fminf(d2, d3)));
+    }
+    return m1;
+}
+
+// index window [lo, hi] (global point indices, base = index of sp[0]) of the points with d2 <= thr in sp[q0 .. q1)
+__device__ __forceinline__ void scan_window(const float2* __restrict__ sp, int q0, int q1, float pxf, float pyf, float thr,
+                                            int base0, int& lo, int& hi) {
+#pragma unroll 2
+    for (int q = q0; q < q1; q += 4) {
+        const float4 A = *reinterpret_cast<const float4*>(&sp[q]);
+        const float4 B = *reinterpret_cast<const float4*>(&sp[q + 2]);
+        const float ax = pxf - A.x, ay = pyf - A.y, bx = pxf - A.z, by = pyf - A.w;
+        const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
+        const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
+        const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) <= thr) {
+            const int base = base0 + q;
+            if (d0 <= thr) { lo = min(lo, base); hi = max(hi, base); }
+            if (d1 <= thr) { lo = min(lo, base + 1); hi = max(hi, base + 1); }
+            if (d2 <= thr) { lo = min(lo, base + 2); hi = max(hi, base + 2); }
+            if (d3 <= thr) { lo = min(lo, base + 3); hi = max(hi, base + 3); }
+        }
+    }
+}
+
+// centre-relative float32 copy of points [c0, c0 + m) into sp[0 .. round_up(m, pad)), padded with K2_FAR
+__device__ __forceinline__ void stage_points(float2* __restrict__ sp, const double2* __restrict__ point, int c0, int m, int pad,
+                                             double cxs, double cys, int lane) {
+    const int mp = (m + pad - 1) & ~(pad - 1);
+    __syncwarp();
+    for (int q = lane; q < mp; q += 32) {
+        float2 v = make_float2(K2_FAR, K2_FAR);
+        if (q < m) {
+            const double2 P = point[c0 + q];
+            v = make_float2((float)(P.x - cxs), (float)(P.y - cys));
+        }
+        sp[q] = v;
+    }
+    __syncwarp();
+}
+
 // One CTA = 32 spatially adjacent pedestrians (lane = pedestrian) x K2_WARPS warps.  All warps walk the same candidate
 // list -- metadata of 32 items is fetched lane-parallel and broadcast by shuffles -- and share it by item index: warp k
 // takes the items with index % K2_WARPS == k that survive the bounding-box test.  Each warp stages its item's points in its own
@@ -309,6 +369,7 @@ __device__ __forceinline__ int exact_argmin(const double2* __restrict__ point, i
 template <int KIND>
 __global__ void __launch_bounds__(K2_THREADS, 4) k2_segments(const SegArgs a) {
     __shared__ __align__(16) float2 sp[K2_WARPS][K2_CHUNK];
+    __shared__ __align__(16) float4 sc[K2_WARPS][2 * K2_PRUNE_MAX];
     __shared__ double2 part[K2_WARPS][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int slot = blockIdx.x * 32 + lane;
@@ -347,12 +408,14 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_segments(const SegArgs a) {
             double2 cen_l = make_double2(0.0, 0.0);
             double cut_l = 0.0;
             float tol_l = 0.0f;
+            int cf_l = -1;
             bool accept_l = false;
             if (kk < k_end) {
                 s_l = a.cell_item[kk];
                 cen_l = a.center[s_l];
                 cut_l = a.cutoff[s_l];
                 tol_l = a.tol[s_l];
+                if (a.chunk_first) cf_l = a.chunk_first[s_l];
                 o0_l = a.offset[s_l];
                 o1_l = a.offset[s_l + 1];
                 // conservative reject: the cutoff disc misses the warp's bounding box (slack covers rounding)
@@ -378,55 +441,65 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_segments(const SegArgs a) {
                 // distance m1, then the index window [lo, hi] of every point within tol of it.
                 const float tol = __shfl_sync(0xffffffffu, tol_l, src);
                 const float pxf = (float)(px - cxs), pyf = (float)(py - cys);
-                const float FAR = 1.0e18f;                                   // pad value: d2 = 2e36, finite, never a candidate
                 float m1 = 3.0e38f;
                 int lo = 0x7fffffff, hi = -1;
-                const bool one_chunk = (o1 - o0) <= K2_CHUNK;
-                for (int phase = 0; phase < 2; ++phase) {
-                    const float thr = m1 + tol;
-                    for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
-                        const int m = min(K2_CHUNK, o1 - c0);
-                        const int m4 = (m + 3) & ~3;
-                        if (phase == 0 || !one_chunk) {
-                            __syncwarp();
-                            for (int q = lane; q < m4; q += 32) {
-                                float2 v = make_float2(FAR, FAR);
-                                if (q < m) {
-                                    const double2 P = a.point[c0 + q];
-                                    v = make_float2((float)(P.x - cxs), (float)(P.y - cys));
-                                }
-                                sp[wid][q] = v;
-                            }
-                            __syncwarp();
+                const int np = o1 - o0;
+                const int cf = __shfl_sync(0xffffffffu, cf_l, src);
+                if (cf >= 0) {
+                    // Pruned search (items with a chunk table: 48 .. 256 points).  Every run of 16 points is covered by
+                    // its chord a + t u (t in [0, 1]) and the largest distance `dev` of its points from that chord, so no
+                    // point of the chunk is closer than dist(p, chord) - dev.  A chunk is scanned only if that bound does
+                    // not exceed the distance to the nearest chunk START (an actual point, hence an upper bound on the
+                    // minimum) -- for at least one pedestrian of the warp that passed the filter.
+                    const int nch = (np + K2_PRUNE_CHUNK - 1) / K2_PRUNE_CHUNK;
+                    stage_points(sp[wid], a.point, o0, np, K2_PRUNE_CHUNK, cxs, cys, lane);
+                    if (lane < 2 * nch) sc[wid][lane] = a.chunk[2 * cf + lane];
+                    __syncwarp();
+                    float ds[K2_PRUNE_MAX];
+                    float ub = 3.0e38f;
+#pragma unroll
+                    for (int c = 0; c < K2_PRUNE_MAX; ++c) {
+                        ds[c] = 3.0e38f;
+                        if (c < nch) {
+                            const float4 g = sc[wid][2 * c], h = sc[wid][2 * c + 1];
+                            const float wx = pxf - g.x, wy = pyf - g.y;
+                            ub = fminf(ub, fmaf(wx, wx, wy * wy));
+                            const float t = __saturatef(fmaf(wx, g.z, wy * g.w) * h.x);
+                            const float rx = fmaf(-t, g.z, wx), ry = fmaf(-t, g.w, wy);
+                            ds[c] = fmaf(rx, rx, ry * ry);
                         }
-                        if (phase == 0) {
-#pragma unroll 2
-                            for (int q = 0; q < m4; q += 4) {
-                                const float4 A = *reinterpret_cast<const float4*>(&sp[wid][q]);
-                                const float4 B = *reinterpret_cast<const float4*>(&sp[wid][q + 2]);
-                                const float ax = pxf - A.x, ay = pyf - A.y, bx = pxf - A.z, by = pyf - A.w;
-                                const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
-                                const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
-                                const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
-                                m1 = fminf(fminf(m1, d0), fminf(d1, fminf(d2, d3)));
-                            }
-                        } else {
-#pragma unroll 2
-                            for (int q = 0; q < m4; q += 4) {
-                                const float4 A = *reinterpret_cast<const float4*>(&sp[wid][q]);
-                                const float4 B = *reinterpret_cast<const float4*>(&sp[wid][q + 2]);
-                                const float ax = pxf - A.x, ay = pyf - A.y, bx = pxf - A.z, by = pyf - A.w;
-                                const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
-                                const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
-                                const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
-                                if (fminf(fminf(d0, d1), fminf(d2, d3)) <= thr) {
-                                    const int base = c0 + q;
-                                    if (d0 <= thr) { lo = min(lo, base); hi = max(hi, base); }
-                                    if (d1 <= thr) { lo = min(lo, base + 1); hi = max(hi, base + 1); }
-                                    if (d2 <= thr) { lo = min(lo, base + 2); hi = max(hi, base + 2); }
-                                    if (d3 <= thr) { lo = min(lo, base + 3); hi = max(hi, base + 3); }
-                                }
-                            }
+                    }
+                    const float b = ub + tol;
+                    const float rb2 = 2.000002f * sqrtf(b);
+                    const float slack = b + 4.0f * tol;          // float32 error of the chord distance: <= 2 tol, doubled
+                    unsigned need = 0;
+#pragma unroll
+                    for (int c = 0; c < K2_PRUNE_MAX; ++c) {
+                        if (c < nch) {
+                            const float dev = sc[wid][2 * c + 1].y;
+                            const bool wanted = pass && !(ds[c] > fmaf(dev, rb2 + dev, slack));      // NaN-safe
+                            if (__any_sync(0xffffffffu, wanted)) need |= 1u << c;
+                        }
+                    }
+                    for (unsigned mm = need; mm; mm &= mm - 1) {
+                        const int q0 = (__ffs(mm) - 1) * K2_PRUNE_CHUNK;
+                        m1 = scan_min(sp[wid], q0, q0 + K2_PRUNE_CHUNK, pxf, pyf, m1);
+                    }
+                    const float thr = m1 + tol;
+                    for (unsigned mm = need; mm; mm &= mm - 1) {
+                        const int q0 = (__ffs(mm) - 1) * K2_PRUNE_CHUNK;
+                        scan_window(sp[wid], q0, q0 + K2_PRUNE_CHUNK, pxf, pyf, thr, o0, lo, hi);
+                    }
+                } else {
+                    const bool one_chunk = np <= K2_CHUNK;
+                    for (int phase = 0; phase < 2; ++phase) {
+                        const float thr = m1 + tol;
+                        for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
+                            const int m = min(K2_CHUNK, o1 - c0);
+                            const int m4 = (m + 3) & ~3;
+                            if (phase == 0 || !one_chunk) stage_points(sp[wid], a.point, c0, m, 4, cxs, cys, lane);
+                            if (phase == 0) m1 = scan_min(sp[wid], 0, m4, pxf, pyf, m1);
+                            else scan_window(sp[wid], 0, m4, pxf, pyf, thr, c0, lo, hi);
                         }
                     }
                 }

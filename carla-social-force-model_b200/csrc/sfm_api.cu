@@ -74,8 +74,10 @@ struct SetStorage {
     DevBuf<int> offset, cell_start, cell_item, val_tmp;
     DevBuf<unsigned> key, key_tmp;
     DevBuf<float> tol;
+    DevBuf<int> chunk_first;
+    DevBuf<float4> chunk;
     void release() {
-        tol.release();
+        tol.release(); chunk_first.release(); chunk.release();
         center.release(); velocity.release(); point.release(); cutoff.release(); offset.release();
         cell_start.release(); cell_item.release(); val_tmp.release(); key.release(); key_tmp.release();
     }
@@ -131,6 +133,7 @@ struct sfm_ctx {
     int k1_target_ctas = 148 * 4 * 16;
     int k1_ir = 2, k1_minb = 5;     // tuning knobs (SFM_K1_IR, SFM_K1_MINB)
     bool k1_first = false;
+    bool k2_prune = true;           // SFM_K2_PRUNE=0: cell-list kernels scan every point of an item (no chunk bounds)
     int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
                                     // cell-list kernels stay co-resident on every SM (see step_begin)
     int k1_rows_mode = 0;           // SFM_K1_MODE=rows: ordered-pair row kernel instead of the symmetric one
@@ -611,6 +614,38 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
         tol[i] = bracket_tolerance(M);
     }
     SFM_TRY(st.tol.ensure(count));
+    // Pruning chunks (k2_cells.cuh): every run of 16 points of a 48..256-point item as chord a + t u and the largest
+    // distance of its points from that chord, centre-relative float32, the deviation rounded up.
+    std::vector<int> chunk_first(count, -1);
+    std::vector<float4> chunk;
+    for (int64_t i = 0; i < count; ++i) {
+        const int64_t b = offsets[i], e = offsets[i + 1];
+        if (e - b < 48 || e - b > K2_CHUNK || !std::isfinite((double)tol[i])) continue;
+        chunk_first[i] = (int)(chunk.size() / 2);
+        const double cx = centers[2 * i], cy = centers[2 * i + 1];
+        double M = 0.0;
+        for (int64_t q = b; q < e; ++q) M = std::max(M, std::max(std::fabs(points[2 * q] - cx), std::fabs(points[2 * q + 1] - cy)));
+        for (int64_t first = b; first < e; first += K2_PRUNE_CHUNK) {
+            const int64_t last = std::min<int64_t>(first + K2_PRUNE_CHUNK, e) - 1;
+            const float ax = (float)(points[2 * first] - cx), ay = (float)(points[2 * first + 1] - cy);
+            const float ux = (float)(points[2 * last] - points[2 * first]), uy = (float)(points[2 * last + 1] - points[2 * first + 1]);
+            const double uu = (double)ux * ux + (double)uy * uy;
+            const float inv = uu > 0.0 ? (float)(1.0 / uu) : 0.0f;
+            double dev = 0.0;
+            for (int64_t q = first; q <= last; ++q) {           // distance of each point from the (float32-rounded) chord
+                const double wx = points[2 * q] - cx - ax, wy = points[2 * q + 1] - cy - ay;
+                double t = (wx * ux + wy * uy) * inv;
+                t = std::min(1.0, std::max(0.0, t));
+                const double rx = wx - t * ux, ry = wy - t * uy;
+                dev = std::max(dev, std::sqrt(rx * rx + ry * ry));
+            }
+            const float devf = std::nextafter((float)(dev * 1.0001 + 8.0 * std::ldexp(1.0, -24) * M), INFINITY);
+            chunk.push_back(make_float4(ax, ay, ux, uy));
+            chunk.push_back(make_float4(inv, devf, 0.0f, 0.0f));
+        }
+    }
+    SFM_TRY(st.chunk_first.ensure(count));
+    SFM_TRY(st.chunk.ensure(std::max<size_t>(chunk.size(), 1)));
     // synchronous copies from pageable host memory: the inputs may be temporaries of the caller
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     SFM_CUDA(cudaMemcpy(st.center.p, centers, sizeof(double2) * count, cudaMemcpyHostToDevice));
@@ -620,7 +655,12 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
     SFM_CUDA(cudaMemcpy(st.offset.p, off.data(), sizeof(int) * (count + 1), cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemcpy(st.point.p, points, sizeof(double2) * np, cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemcpy(st.tol.p, tol.data(), sizeof(float) * count, cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.chunk_first.p, chunk_first.data(), sizeof(int) * count, cudaMemcpyHostToDevice));
+    if (!chunk.empty())
+        SFM_CUDA(cudaMemcpy(st.chunk.p, chunk.data(), sizeof(float4) * chunk.size(), cudaMemcpyHostToDevice));
     s.tol = st.tol.p;
+    s.chunk_first = st.chunk_first.p;
+    s.chunk = st.chunk.p;
     s.center = st.center.p; s.cutoff = st.cutoff.p; s.velocity = st.velocity.p; s.offset = st.offset.p;
     s.point = st.point.p; s.n_points = np;
     SFM_TRY(build_set_grid(c, st, count, centers, max_cut));
@@ -646,7 +686,8 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
     SegArgs a{};
     a.locr = c->locr.p; a.vels = c->vels.p; a.mode = c->mode.p; a.perm = c->perm.p; a.n = n;
     a.center = st.s.center; a.cutoff = st.s.cutoff; a.velocity = st.s.velocity; a.offset = st.s.offset;
-    a.point = st.s.point; a.tol = st.s.tol; a.grid = st.s.grid; a.cell_start = st.s.cell_start; a.cell_item = st.s.cell_item;
+    a.point = st.s.point; a.tol = st.s.tol; a.chunk_first = c->k2_prune ? st.s.chunk_first : nullptr; a.chunk = st.s.chunk;
+    a.grid = st.s.grid; a.cell_start = st.s.cell_start; a.cell_item = st.s.cell_item;
     a.mp = make_moussaid_d(cls == SFM_FORCE_DYNAMIC_OBSTACLE ? c->params.dynamic_obs : c->params.static_obs);
     a.border_a = c->params.border_a; a.border_b = c->params.border_b;
     a.use_radius = c->params.use_ped_radius;
@@ -798,6 +839,7 @@ int sfm_create(int device, sfm_ctx** out) {
     c->k1_smem_pad = 0;
     if (const char* env = std::getenv("SFM_K1_SMEM_PAD")) c->k1_smem_pad = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("SFM_K1_FIRST")) c->k1_first = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SFM_K2_PRUNE")) c->k2_prune = std::atoi(env) != 0;
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -1372,6 +1414,7 @@ int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, cons
     SFM_CUDA(cudaMemcpy(st.tol.p, tol.data(), sizeof(float) * n_vehicles, cudaMemcpyHostToDevice));
     SegmentSet& s = st.s;
     s.tol = st.tol.p;
+    s.chunk_first = nullptr;                       // rings are regenerated every tick: no chunk tables
     s.center = st.center.p; s.cutoff = st.cutoff.p; s.velocity = st.velocity.p; s.offset = st.offset.p;
     s.point = st.point.p; s.n_points = np;
     c->veh_size_factor = size_factor;
