@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_segments(const SegArgs a) {
                     // not exceed the distance to the nearest chunk START (an actual point, hence an upper bound on the
                     // minimum) -- for at least one pedestrian of the warp that passed the filter.
                     const int nch = (np + K2_PRUNE_CHUNK - 1) / K2_PRUNE_CHUNK;
-                    stage_points(sp[wid], a.point, o0, np, K2_PRUNE_CHUNK, cxs, cys, lane);
+                    __syncwarp();
                     if (lane < 2 * nch) sc[wid][lane] = a.chunk[2 * cf + lane];
                     __syncwarp();
                     float ds[K2_PRUNE_MAX];
@@ -481,6 +481,21 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_segments(const SegArgs a) {
                             if (__any_sync(0xffffffffu, wanted)) need |= 1u << c;
                         }
                     }
+                    // only the chunks somebody needs are fetched: two per pass (16 lanes each), at their own positions
+                    for (unsigned mm = need; mm;) {
+                        const int ca = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int cb = mm ? __ffs(mm) - 1 : ca;
+                        mm &= mm - 1;
+                        const int q = ((lane < 16) ? ca : cb) * K2_PRUNE_CHUNK + (lane & 15);
+                        float2 v = make_float2(K2_FAR, K2_FAR);
+                        if (q < np) {
+                            const double2 P = a.point[o0 + q];
+                            v = make_float2((float)(P.x - cxs), (float)(P.y - cys));
+                        }
+                        sp[wid][q] = v;
+                    }
+                    __syncwarp();
                     for (unsigned mm = need; mm; mm &= mm - 1) {
                         const int q0 = (__ffs(mm) - 1) * K2_PRUNE_CHUNK;
                         m1 = scan_min(sp[wid], q0, q0 + K2_PRUNE_CHUNK, pxf, pyf, m1);
