@@ -224,6 +224,22 @@ __global__ void __launch_bounds__(256) k4_advance_waypoints(int64_t n, const dou
     advance_waypoint(r, mm, i, L.x, L.y, wp, mode, sim_time);
 }
 
+// ---- despawn (run_simulation.py:127-132: pedestrians that arrived with no waypoint left are destroyed) ---------------
+// keep[i] = !finished[i]; an exclusive scan of keep gives every surviving row its new index (order preserved, like the
+// boolean-mask copy of PedState.remove_pedestrian, pedestrian_state.py:42-43); one gather per column.
+__global__ void k4_keep_flags(int64_t n, const uint8_t* finished, int* keep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = finished[i] ? 0 : 1;
+}
+
+template <typename T>
+__global__ void k4_compact(int64_t n, const uint8_t* finished, const int* new_index, const T* src, T* dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !finished[i]) dst[new_index[i]] = src[i];
+}
+
+struct double3s { double x, y, z; };      // one next_waypoint row
+
 // ---- vehicle rings ---------------------------------------------------------------------------------------------
 struct VehicleArgs {
     int count;

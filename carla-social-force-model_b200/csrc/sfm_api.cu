@@ -159,6 +159,8 @@ struct sfm_ctx {
     DevBuf<uint8_t> rec_mode;
     int64_t rec_capacity = 0, rec_rows = 0, rec_count = 0;
     std::vector<double> rec_times;
+    DevBuf<double4> cmp4; DevBuf<double2> cmp2; DevBuf<double3s> cmp3; DevBuf<double> cmp1; DevBuf<int> cmpi;
+    DevBuf<uint8_t> cmpb;                          // scratch columns of sfm_despawn_finished
     std::vector<int> rt_begin;                     // host copy of the routes' first entries (cursor downloads are relative)
     // ---- peer-memory exchange (K7): mapped buffers of the other ranks, flag barrier, double-buffered gather buffer
     bool p2p = false;
@@ -797,6 +799,22 @@ int download3(sfm_ctx* c, const double* dev, int64_t n, double* out) {
 
 }  // namespace
 
+namespace {
+
+template <typename T>
+int compact_column(sfm_ctx* c, DevBuf<T>& col, DevBuf<T>& scratch, int64_t n, const uint8_t* finished, const int* new_index) {
+    if (!col.p) return 0;
+    SFM_TRY(scratch.ensure(n));
+    k4_compact<T><<<cdiv(n, 256), 256, 0, c->stream>>>(n, finished, new_index, col.p, scratch.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    std::swap(col.p, scratch.p);
+    std::swap(col.cap, scratch.cap);
+    return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
 int sfm_abi_version(void) { return SFM_ABI_VERSION; }
@@ -873,6 +891,7 @@ int sfm_destroy(sfm_ctx* c) {
                 cudaIpcCloseMemHandle(c->peer_flags[r]);
             }
     c->flags.release();
+    c->cmp4.release(); c->cmp2.release(); c->cmp3.release(); c->cmp1.release(); c->cmpi.release(); c->cmpb.release();
     c->mm_speed.release(); c->mm_initial.release(); c->mm_crossing.release(); c->mm_margin.release();
     c->mm_next_time.release(); c->tr_center.release(); c->tr_vel.release(); c->rt_end.release(); c->rt_cursor.release();
     c->rt_wp.release(); c->next_wp3.release(); c->rt_cross.release(); c->finished.release(); c->life_counters.release();
@@ -1323,6 +1342,73 @@ int sfm_download_routes(sfm_ctx* c, int64_t n, int64_t* cursor, uint8_t* finishe
         SFM_CUDA(cudaMemcpyAsync(next_waypoint, c->next_wp3.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     if (cursor) for (int64_t i = 0; i < n; ++i) cursor[i] = cur[i] - c->rt_begin[i];
+    return 0;
+}
+
+
+int sfm_despawn_finished(sfm_ctx* c, int64_t* n_after, int64_t* n_removed) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_routes || !c->have_mm) return fail("sfm_set_routes must be called first");
+    if (c->world > 1) return fail("despawning changes the row partition: single-rank contexts only");
+    if (c->step_open) return fail("despawn between sfm_step_begin and sfm_step_end");
+    const int64_t n = c->n;
+    if (n_after) *n_after = n;
+    if (n_removed) *n_removed = 0;
+    if (n == 0) return 0;
+    DevBuf<int>& idx = c->ped_cursor;                      // scratch of the pedestrian binning, rebuilt every tick anyway
+    SFM_TRY(idx.ensure(n + 1));
+    {
+        SpanGuard g(c, ST_LIFECYCLE);
+        k4_keep_flags<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->finished.p, idx.p);
+        k2_exclusive_scan<<<1, 1024, 0, c->stream>>>(idx.p, (int)n + 1);     // idx[n] = survivors
+        c->launches += 2;
+        SFM_CUDA(cudaGetLastError());
+    }
+    int survivors = 0;
+    SFM_CUDA(cudaMemcpyAsync(&survivors, idx.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    if (survivors == n) return 0;
+    {
+        SpanGuard g(c, ST_LIFECYCLE);
+        DevBuf<double4>& s4 = c->cmp4;
+        DevBuf<double2>& s2 = c->cmp2;
+        DevBuf<double3s>& s3 = c->cmp3;
+        DevBuf<double>& s1 = c->cmp1;
+        DevBuf<int>& si = c->cmpi;
+        DevBuf<uint8_t>& sb = c->cmpb;
+        const uint8_t* fin = c->finished.p;
+        SFM_TRY(compact_column(c, c->locr, s4, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->vels, s4, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->wp, s2, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->mode, sb, n, fin, idx.p));
+        {   // next_wp3 is a double[n][3] buffer
+            DevBuf<double3s> view; view.p = reinterpret_cast<double3s*>(c->next_wp3.p); view.cap = c->next_wp3.cap / 3;
+            SFM_TRY(compact_column(c, view, s3, n, fin, idx.p));
+            c->next_wp3.p = reinterpret_cast<double*>(view.p); c->next_wp3.cap = view.cap * 3;
+        }
+        SFM_TRY(compact_column(c, c->mm_speed, s1, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->mm_initial, s1, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->mm_crossing, s1, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->mm_margin, s1, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->mm_next_time, s1, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->rt_cursor, si, n, fin, idx.p));
+        SFM_TRY(compact_column(c, c->rt_end, si, n, fin, idx.p));
+        // the route table's host copy of the first entries (relative cursors) follows the same mask
+        std::vector<uint8_t> fin_host(n);
+        SFM_CUDA(cudaMemcpyAsync(fin_host.data(), fin, n, cudaMemcpyDeviceToHost, c->stream));
+        SFM_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<int> begin;
+        begin.reserve(survivors);
+        for (int64_t i = 0; i < n; ++i) if (!fin_host[i]) begin.push_back(c->rt_begin[i]);
+        c->rt_begin.swap(begin);
+        SFM_CUDA(cudaMemsetAsync(c->finished.p, 0, n, c->stream));
+    }
+    c->n = survivors;
+    c->staged = false;                   // every staged slot moved
+    c->perm_valid = false;
+    c->rec_capacity = 0;                 // recorded frames have a fixed row count: the recorder must be re-armed
+    if (n_after) *n_after = survivors;
+    if (n_removed) *n_removed = n - survivors;
     return 0;
 }
 

@@ -49,6 +49,8 @@ class HeadlessRunner:
         if self.has_vehicles and device_vehicles:
             c.set_vehicles(w.veh_center, w.veh_yaw, w.veh_vel, w.veh_extent, w.veh_resolution)
         self.step_index = 0
+        self.ids = np.arange(w.n)                          # original row of every pedestrian still in the crowd
+        self._finished_seen = 0
         self.record_every = record_every
         if record_every:
             c.record_begin(record_capacity)
@@ -68,6 +70,12 @@ class HeadlessRunner:
         if self.record_every and k % self.record_every == 0:
             c.record_frame(sim_time)                      # after the machines ticked, before the forces (:75)
         c.step(1, integrate_positions=True)
+        if self.life.despawn_on_arrival and c.lifecycle_counters()['finished'] > self._finished_seen:
+            # run_simulation.py:127-132.  The counter read-back (32 bytes) is the only per-tick synchronisation; the mask
+            # is fetched only on ticks on which somebody actually finished.
+            _, finished, _ = c.download_routes()
+            self.ids = self.ids[~finished]
+            self._finished_seen += c.despawn_finished()
         self.step_index += 1
 
     def run(self, n_steps):

@@ -29,7 +29,7 @@ SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create'
            'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats',
            # lifecycle
            'sfm_set_mode_machines', 'sfm_set_traffic', 'sfm_tick_modes', 'sfm_download_modes', 'sfm_set_routes',
-           'sfm_advance_waypoints', 'sfm_download_routes', 'sfm_lifecycle_counters', 'sfm_set_vehicles',
+           'sfm_advance_waypoints', 'sfm_download_routes', 'sfm_despawn_finished', 'sfm_lifecycle_counters', 'sfm_set_vehicles',
            'sfm_advance_vehicles', 'sfm_download_vehicles', 'sfm_record_begin', 'sfm_record_frame',
            'sfm_download_frames',
            # peer-memory exchange (K7)
@@ -132,6 +132,7 @@ def lib():
         'sfm_set_routes': (C.c_int, [p_ctx, i64, p_i64, p_d, p_u8, C.c_double, C.c_int]),
         'sfm_advance_waypoints': (C.c_int, [p_ctx]),
         'sfm_download_routes': (C.c_int, [p_ctx, i64, p_i64, p_u8, p_d]),
+        'sfm_despawn_finished': (C.c_int, [p_ctx, p_i64, p_i64]),
         'sfm_lifecycle_counters': (C.c_int, [p_ctx, p_i64]),
         'sfm_set_vehicles': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d, C.c_double, C.c_double]),
         'sfm_advance_vehicles': (C.c_int, [p_ctx, C.c_double]),
@@ -450,6 +451,13 @@ class Context:
         cursor, finished, wp = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.uint8), np.empty((n, 3))
         _check(self._lib.sfm_download_routes(self._h, n, _ptr(cursor, C.c_int64), _ptr(finished, C.c_uint8), _ptr(wp)))
         return cursor, finished.astype(bool), wp
+
+    def despawn_finished(self):
+        """Remove the pedestrians that arrived with no waypoint left; returns how many were removed."""
+        after, removed = C.c_int64(), C.c_int64()
+        _check(self._lib.sfm_despawn_finished(self._h, C.byref(after), C.byref(removed)))
+        self.n = after.value
+        return removed.value
 
     def lifecycle_counters(self):
         out = np.zeros(4, dtype=np.int64)

@@ -189,6 +189,10 @@ int sfm_set_routes(sfm_ctx* ctx, int64_t n, const int64_t* offsets, const double
 int sfm_advance_waypoints(sfm_ctx* ctx);
 /* cursor: entries of each pedestrian's route already handed out; finished: arrived with nothing left (run_simulation.py:127). */
 int sfm_download_routes(sfm_ctx* ctx, int64_t n, int64_t* cursor, uint8_t* finished, double* next_waypoint);
+/* Removes every pedestrian whose `finished` flag is set (run_simulation.py:127-132 with despawn_on_arrival; row order
+ * preserved like PedState.remove_pedestrian, pedestrian_state.py:42-43) from all per-row tables and restages.  Returns
+ * the new row count; later uploads / downloads use it.  Synchronises the stream.  Single-rank contexts only. */
+int sfm_despawn_finished(sfm_ctx* ctx, int64_t* n_after, int64_t* n_removed);
 /* out4: crossings started, idle wake-ups, waypoint hand-overs, pedestrians finished -- since the context was created. */
 int sfm_lifecycle_counters(sfm_ctx* ctx, int64_t* out4);
 /* f2.  Dynamic-obstacle set generated on the device: obstacles.py:297-329 (get_dynamic_obstacles) with the ellipse of

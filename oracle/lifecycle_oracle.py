@@ -184,9 +184,13 @@ def ellipse_ring(centre, yaw_deg, extent_x, extent_y, resolution=0.1, size_facto
     return out
 
 
-def run_headless(scene, w, life, n_steps, vehicles_at=None, fused_order=True):
+def run_headless(scene, w, life, n_steps, vehicles_at=None, despawn=False):
     """The whole per-tick loop with CARLA stubbed: vehicles -> mode machines + gap acceptance -> forces, velocity
     update -> arrival test at the positions the forces saw -> x += dt v.
+
+    With ``despawn`` pedestrians that arrive with no waypoint left are removed right after the hand-over loop
+    (run_simulation.py:127-132); histories then carry ``ids`` (original row of every surviving pedestrian) per tick and
+    ragged state lists.
 
     Returns per-tick histories (T+1 entries for state, T for decisions)."""
     n = w.n
@@ -195,7 +199,8 @@ def run_headless(scene, w, life, n_steps, vehicles_at=None, fused_order=True):
     loc, vel, wp = w.loc.copy(), w.vel.copy(), w.next_waypoint.copy()
     target_speed = w.target_speed.copy()
     cursor, finished = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=bool)
-    hist = dict(loc=[loc.copy()], vel=[vel.copy()], mode=[machines.mode.copy()], wp=[wp.copy()],
+    ids, radius, routes = np.arange(n), w.radius.copy(), list(life.routes)
+    hist = dict(ids=[ids.copy()], loc=[loc.copy()], vel=[vel.copy()], mode=[machines.mode.copy()], wp=[wp.copy()],
                 target_speed=[], mode_speed=[machines.target_speed.copy()], cursor=[cursor.copy()],
                 finished=[finished.copy()])
     vehicles_at = vehicles_at or w.vehicles_at
@@ -205,12 +210,24 @@ def run_headless(scene, w, life, n_steps, vehicles_at=None, fused_order=True):
         traffic = (veh[1], veh[3], veh[4]) if veh is not None else None
         tick_modes(machines, target_speed, loc, wp, t, traffic)
         dyn = list(zip(veh[1], veh[5])) if veh is not None else None
-        new_loc, new_vel, _ = O.step(scene, loc, vel, wp, w.radius, target_speed, machines.mode, dyn,
+        new_loc, new_vel, _ = O.step(scene, loc, vel, wp, radius, target_speed, machines.mode, dyn,
                                      veh[3] if veh is not None else None)
-        advance_waypoints(machines, loc, wp, life.routes, cursor, finished, life.waypoint_threshold)
+        advance_waypoints(machines, loc, wp, routes, cursor, finished, life.waypoint_threshold)
         loc, vel = new_loc, new_vel
+        if despawn and finished.any():
+            keep = ~finished
+            loc, vel, wp, radius, target_speed = loc[keep], vel[keep], wp[keep], radius[keep], target_speed[keep]
+            cursor, ids = cursor[keep], ids[keep]
+            routes = [r for r, k in zip(routes, keep) if k]
+            machines = Machines(machines.mode[keep], machines.target_speed[keep], machines.initial_target_speed[keep],
+                                machines.crossing_speed[keep], machines.crossing_safety_margin[keep],
+                                machines.next_mode_time[keep], machines.waiting_time, machines.sim_time)
+            finished = np.zeros(len(ids), dtype=bool)
+        hist['ids'].append(ids.copy())
         hist['loc'].append(loc.copy()); hist['vel'].append(vel.copy()); hist['mode'].append(machines.mode.copy())
         hist['wp'].append(wp.copy()); hist['target_speed'].append(target_speed.copy())
         hist['mode_speed'].append(machines.target_speed.copy()); hist['cursor'].append(cursor.copy())
         hist['finished'].append(finished.copy())
+    if despawn:
+        return hist
     return {k: np.array(v) for k, v in hist.items()}

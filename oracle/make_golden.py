@@ -87,6 +87,26 @@ def golden_lifecycle(ref, cfg):
     np.savez_compressed(os.path.join(GOLDEN, 'lifecycle.npz'), digest=lifecycle_digest(w, life), **out)
 
 
+def pack_ragged(hist, n):
+    """Ragged per-tick histories of a run with despawns -> dense arrays: alive mask, modes (255 = gone), final state."""
+    ticks = len(hist['ids'])
+    alive = np.zeros((ticks, n), dtype=bool)
+    mode = np.full((ticks, n), 255, dtype=np.uint8)
+    for k in range(ticks):
+        alive[k, hist['ids'][k]] = True
+        mode[k, hist['ids'][k]] = hist['mode'][k]
+    return dict(alive=alive, mode=mode, ids_final=np.asarray(hist['ids'][-1]), loc_final=np.asarray(hist['loc'][-1]),
+                vel_final=np.asarray(hist['vel'][-1]), wp_final=np.asarray(hist['wp'][-1]))
+
+
+def golden_lifecycle_despawn(ref, cfg):
+    """The same scenario with despawn_on_arrival (run_simulation.py:38,127-132): the crowd shrinks from 48 to 10."""
+    w, life = synth.make_lifecycle()
+    out = ref_loader.run_lifecycle(ref, w, life, cfg, LIFECYCLE_STEPS, despawn=True)
+    np.savez_compressed(os.path.join(GOLDEN, 'lifecycle_despawn.npz'), digest=lifecycle_digest(w, life),
+                        **pack_ragged(out, w.n))
+
+
 def golden_output_csv(ref_dir):
     """The four CSV files the reference's own OutputGenerator writes for a tiny recorded scene (output_generator.py)."""
     import importlib.util
@@ -121,6 +141,7 @@ def main():
         golden_cfg2(ref, cfg)
     if args.only in (None, 'lifecycle'):
         golden_lifecycle(ref, cfg)
+        golden_lifecycle_despawn(ref, cfg)
     if args.only in (None, 'csv'):
         golden_output_csv(ref_loader.REFERENCE_DIR)
 

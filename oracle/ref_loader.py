@@ -135,7 +135,7 @@ def run_ticks(ref, workload, sfm_config, n_steps, record_forces=True):
     return dict(loc=np.array(locs), vel=np.array(vels), forces={k: np.array(v) for k, v in forces.items()})
 
 
-def run_lifecycle(ref, workload, life, sfm_config, n_steps):
+def run_lifecycle(ref, workload, life, sfm_config, n_steps, despawn=False):
     """The reference's tick loop with its own mode machines, gap acceptance and waypoint hand-over, CARLA stubbed.
 
     Follows SimulationRunner.tick (run_simulation.py:94-132) for everything that does not need the simulator: vehicles
@@ -173,11 +173,21 @@ def run_lifecycle(ref, workload, life, sfm_config, n_steps):
             remaining = waypoint_dict[ped_name]
             if remaining:
                 sim.peds.update_next_waypoint(ped_name, remaining.pop(0))
+            elif despawn:                                                      # run_simulation.py:127-132
+                sim.destroy_pedestrian(ped_name)
+                waypoint_dict.pop(ped_name)
+        if despawn:
+            if sim.peds.size() == 0:
+                break
+            nv = sim.peds.state[['id', 'vel']]
+            hist.setdefault('ids', [np.arange(n)]).append(sim.peds.state['id'].copy())
         sim.peds.state['loc'] += nv['vel'] * dt
         sim.peds.all_states.clear()
         sim.all_dyn_obs_states.clear()
         hist['loc'].append(sim.peds.state['loc'].copy()); hist['vel'].append(sim.peds.state['vel'].copy())
         hist['mode'].append(codes()); hist['wp'].append(sim.peds.state['next_waypoint'].copy())
         hist['mode_speed'].append(speeds())
-        hist['remaining'].append(np.array([len(waypoint_dict[k]) for k in names]))
+        hist['remaining'].append(np.array([len(waypoint_dict[k]) for k in names if k in waypoint_dict]))
+    if despawn:
+        return hist
     return {k: np.array(v) for k, v in hist.items()}

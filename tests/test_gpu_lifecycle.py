@@ -195,3 +195,21 @@ def test_headless_loop_with_device_vehicles(scenario, sfm_config):
     assert np.abs(s['loc'] - want['loc'][-1]).max() < 1e-2
     got_c, _ = run.ctx.download_vehicles()
     assert np.array_equal(got_c, centres[steps - 1])
+
+
+def test_despawn_on_arrival_matches_reference_golden(scenario, sfm_config):
+    """sfm_despawn_finished: the device removes the pedestrians the reference destroys, at the same ticks, keeps the row
+    order, and the shrinking crowd keeps producing the reference's modes."""
+    import dataclasses
+    w, life = scenario
+    g = np.load(os.path.join(GOLDEN, 'lifecycle_despawn.npz'))
+    run = HeadlessRunner(sfm_config, w, dataclasses.replace(life, despawn_on_arrival=True))
+    for k in range(LIFECYCLE_STEPS):
+        run.tick()
+        alive = np.nonzero(g['alive'][k + 1])[0]
+        assert np.array_equal(run.ids, alive), f'crowd differs after tick {k}'
+        assert run.ctx.n == len(alive)
+        assert np.array_equal(run.ctx.download_mode_codes(), g['mode'][k + 1][alive]), f'modes differ after tick {k}'
+    s = run.snapshot()
+    assert np.array_equal(run.ids, g['ids_final']) and np.array_equal(s['wp'], g['wp_final'])
+    assert np.abs(s['loc'] - g['loc_final']).max() < 0.1 and np.median(np.abs(s['loc'] - g['loc_final'])) < 1e-4

@@ -144,3 +144,17 @@ def test_output_generator_bytes_equal_reference(tmp_path):
     gen2.generate_ped_csv(device_frames=(times, xyv, mode), ped_ids=ids)
     with open(os.path.join(gen2.output_dir, 'pedestrian.csv'), 'rb') as f:
         assert f.read() == g['pedestrian_csv'].tobytes()
+
+
+def test_oracle_despawn_reproduces_reference_golden(scenario, sfm_config):
+    """despawn_on_arrival: the oracle removes the same pedestrians at the same ticks as the reference's
+    destroy_pedestrian calls and the survivors end in the same state."""
+    from oracle.make_golden import pack_ragged
+    w, life = scenario
+    scene = O.Scene(sfm_config, w.step_length, w.borders, w.section_center, w.section_length, w.static_obstacles)
+    got = pack_ragged(LO.run_headless(scene, w, life, LIFECYCLE_STEPS, despawn=True), w.n)
+    g = np.load(os.path.join(GOLDEN, 'lifecycle_despawn.npz'))
+    assert str(g['digest']) == lifecycle_digest(w, life)
+    assert np.array_equal(g['alive'], got['alive']) and np.array_equal(g['mode'], got['mode'])
+    assert np.array_equal(g['ids_final'], got['ids_final']) and 0 < len(got['ids_final']) < w.n // 2
+    assert np.abs(g['loc_final'] - got['loc_final']).max() <= 1e-9 and np.array_equal(g['wp_final'], got['wp_final'])
