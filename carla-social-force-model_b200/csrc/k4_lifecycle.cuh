@@ -1,9 +1,10 @@
 // K4 / K5 / K6 -- the per-tick bookkeeping around the force kernels, moved onto the device.
 //
-//  K4a  k4_tick_modes        PedState.apply_current_mode (reference pedestrian_state.py:94-95), PedModeManager.tick
-//                            (ped_mode_manager.py:30-35) and the gap-acceptance loop of PedestrianSimulation.tick
+//  K4a  k4_tick_modes +      PedState.apply_current_mode (reference pedestrian_state.py:94-95), PedModeManager.tick
+//       k4_gap_acceptance    (ped_mode_manager.py:30-35) and the gap-acceptance loop of PedestrianSimulation.tick
 //                            (pedestrian_simulation.py:67-73) with check_traffic (check_traffic.py:7-61) as a
-//                            closed-form segment test -- one thread per pedestrian, vehicles staged in shared memory.
+//                            closed-form segment test -- waiting pedestrians compacted first, one thread each, vehicles
+//                            staged in shared memory.
 //  K4b  advance_waypoint()   arrival test (pedestrian_simulation.py:88-97) + waypoint hand-over
 //                            (run_simulation.py:118-132, pedestrian_state.py:83-92) + PedModeManager.set_mode with its
 //                            detours (ped_mode_manager.py:37-47); called from K3 (fused) or from k4_advance_waypoints.
@@ -107,34 +108,55 @@ struct ModeTickArgs {
     Traffic tr;
     double sim_time;
     unsigned long long* counters;        // [0] pedestrians that entered CROSSING_ROAD this tick, [1] idle wake-ups
+    int* check_list;                     // [n] rows in CHECKING_TRAFFIC this tick (compacted)
+    int* check_count;                    // [1]
 };
 
 constexpr int K4_THREADS = 128;
 constexpr int K4_VEH_TILE = 256;
 
+// Phase 1, one thread per pedestrian: apply_current_mode, the machines' tick, and the list of pedestrians that stand at the
+// kerb (CHECKING_TRAFFIC) -- compacted, so that phase 2 runs on dense warps.  Without vehicles everybody crosses at once
+// (pedestrian_simulation.py:68-73).
 __global__ void __launch_bounds__(K4_THREADS) k4_tick_modes(const ModeTickArgs a) {
-    __shared__ double2 s_center[K4_VEH_TILE], s_vel[K4_VEH_TILE];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < a.n;
-    uint8_t cur = live ? a.mode[i] : (uint8_t)SFM_WALKING_SIDEWALK;
-    if (live) {
-        // pedestrian_state.py:94-95 -- runs BEFORE the machines tick: this tick clamps against the speed the mode had
-        // at the end of the previous tick
-        double4 V = a.vels[i];
-        V.w = a.mm.mode_speed[i];
-        a.vels[i] = V;
-        // ped_mode_manager.py:30-35
-        if (cur == SFM_IDLE && a.mm.next_mode_time[i] <= a.sim_time) {
-            activate_mode(a.mm, i, SFM_WALKING_SIDEWALK, a.sim_time, cur);
-            atomicAdd(a.counters + 1, 1ull);
+    if (i >= a.n) return;
+    uint8_t cur = a.mode[i];
+    // pedestrian_state.py:94-95 -- runs BEFORE the machines tick: this tick clamps against the speed the mode had at the
+    // end of the previous tick
+    double4 V = a.vels[i];
+    V.w = a.mm.mode_speed[i];
+    a.vels[i] = V;
+    // ped_mode_manager.py:30-35
+    if (cur == SFM_IDLE && a.mm.next_mode_time[i] <= a.sim_time) {
+        activate_mode(a.mm, i, SFM_WALKING_SIDEWALK, a.sim_time, cur);
+        atomicAdd(a.counters + 1, 1ull);
+    }
+    if (cur == SFM_CHECKING_TRAFFIC) {
+        if (a.tr.count > 0) {
+            a.check_list[atomicAdd(a.check_count, 1)] = (int)i;           // order is irrelevant: decisions are per pedestrian
+        } else {
+            request_mode(a.mm, i, SFM_CROSSING_ROAD, a.sim_time, cur);
+            atomicAdd(a.counters + 0, 1ull);
         }
     }
-    // pedestrian_simulation.py:67-73: every CHECKING_TRAFFIC pedestrian looks at every vehicle
-    const bool checking = live && cur == SFM_CHECKING_TRAFFIC;
-    bool ready = true;
-    if (__syncthreads_or(checking) && a.tr.count > 0) {
+    a.mode[i] = cur;
+}
+
+// Phase 2, one thread per waiting pedestrian: check_traffic.py:7-61 against every vehicle.  Vehicles are staged in shared
+// memory 256 at a time together with what depends on the vehicle alone (half-length vector heading * extent[0], speed).
+// A vehicle whose swept segment back -> goal cannot touch the pedestrian's path (bounding boxes apart by more than a
+// rounding margin) is dismissed after a handful of operations -- exactly the cases in which the segment test says "no".
+__global__ void __launch_bounds__(K4_THREADS) k4_gap_acceptance(const ModeTickArgs a) {
+    __shared__ double2 s_center[K4_VEH_TILE], s_vel[K4_VEH_TILE], s_half[K4_VEH_TILE];
+    __shared__ double s_speed[K4_VEH_TILE];
+    const int count = *a.check_count;
+    for (int base = blockIdx.x * K4_THREADS; base < count; base += gridDim.x * K4_THREADS) {
+        const int k = base + threadIdx.x;
+        const bool live = k < count;
+        const int64_t i = live ? a.check_list[k] : 0;
         double px = 0.0, py = 0.0, gx = 0.0, gy = 0.0, speed = 1.0, margin = -1.0, time_ped = 0.0;
-        if (checking) {
+        if (live) {
             const double4 L = a.locr[i];
             const double2 w = a.wp[i];
             px = L.x; py = L.y; gx = w.x; gy = w.y;
@@ -142,27 +164,34 @@ __global__ void __launch_bounds__(K4_THREADS) k4_tick_modes(const ModeTickArgs a
             margin = a.mm.safety_margin[i];
             time_ped = __ddiv_rn(norm2d(__dsub_rn(gx, px), __dsub_rn(gy, py)), speed);      // check_traffic.py:27-28
         }
-        const bool looks = checking && !(margin < 0.0);                    // negative margin: cross without looking (:24)
+        const bool looks = live && !(margin < 0.0);                        // negative margin: cross without looking (:24)
+        const double horizon = __dadd_rn(time_ped, margin);
+        const double eps = 1.0e-9 * (1.0 + fabs(px) + fabs(py) + fabs(gx) + fabs(gy));
+        const double x0 = fmin(px, gx) - eps, x1 = fmax(px, gx) + eps, y0 = fmin(py, gy) - eps, y1 = fmax(py, gy) + eps;
+        bool ready = true;
         for (int v0 = 0; v0 < a.tr.count; v0 += K4_VEH_TILE) {
             const int m = min(K4_VEH_TILE, a.tr.count - v0);
             __syncthreads();
             for (int v = threadIdx.x; v < m; v += K4_THREADS) {
-                s_center[v] = a.tr.center[v0 + v];
-                s_vel[v] = a.tr.velocity[v0 + v];
+                const double2 c = a.tr.center[v0 + v], u = a.tr.velocity[v0 + v];
+                const double vs = norm2d(u.x, u.y);
+                const double dn = (vs == 0.0) ? 1.0 : vs;                                      // stateutils.py:88-90
+                s_center[v] = c;
+                s_vel[v] = u;
+                s_half[v] = make_double2(__dmul_rn(__ddiv_rn(u.x, dn), a.tr.ext0_x), __dmul_rn(__ddiv_rn(u.y, dn), a.tr.ext0_y));
+                s_speed[v] = vs;
             }
             __syncthreads();
             if (looks && ready) {
                 for (int v = 0; v < m; ++v) {
-                    const double2 c = s_center[v], u = s_vel[v];
-                    const double vs = norm2d(u.x, u.y);
-                    const double dn = (vs == 0.0) ? 1.0 : vs;                                  // stateutils.py:88-90
-                    const double hx = __dmul_rn(__ddiv_rn(u.x, dn), a.tr.ext0_x), hy = __dmul_rn(__ddiv_rn(u.y, dn), a.tr.ext0_y);
-                    const double fx = __dadd_rn(c.x, hx), fy = __dadd_rn(c.y, hy);           // front (:35)
-                    const double bx = __dsub_rn(c.x, hx), by = __dsub_rn(c.y, hy);           // back  (:36)
-                    const double horizon = __dadd_rn(time_ped, margin);
+                    const double2 c = s_center[v], u = s_vel[v], h = s_half[v];
+                    const double fx = __dadd_rn(c.x, h.x), fy = __dadd_rn(c.y, h.y);         // front (:35)
+                    const double bx = __dsub_rn(c.x, h.x), by = __dsub_rn(c.y, h.y);         // back  (:36)
                     const double tx = __dadd_rn(fx, __dmul_rn(u.x, horizon)), ty = __dadd_rn(fy, __dmul_rn(u.y, horizon));
+                    if (fmax(bx, tx) < x0 || fmin(bx, tx) > x1 || fmax(by, ty) < y0 || fmin(by, ty) > y1) continue;
                     double ix, iy;
                     if (!segment_hit(px, py, gx, gy, bx, by, tx, ty, ix, iy)) continue;
+                    const double vs = s_speed[v];
                     if (vs == 0.0) continue;                                                  // :48-49
                     const double tti_ped = __ddiv_rn(norm2d(__dsub_rn(ix, px), __dsub_rn(iy, py)), speed);
                     const double tti_front = __ddiv_rn(norm2d(__dsub_rn(ix, fx), __dsub_rn(iy, fy)), vs);
@@ -174,12 +203,13 @@ __global__ void __launch_bounds__(K4_THREADS) k4_tick_modes(const ModeTickArgs a
                 }
             }
         }
+        if (live && ready) {
+            uint8_t cur = SFM_CHECKING_TRAFFIC;
+            request_mode(a.mm, i, SFM_CROSSING_ROAD, a.sim_time, cur);
+            a.mode[i] = cur;
+            atomicAdd(a.counters + 0, 1ull);
+        }
     }
-    if (checking && ready) {
-        request_mode(a.mm, i, SFM_CROSSING_ROAD, a.sim_time, cur);
-        atomicAdd(a.counters + 0, 1ull);
-    }
-    if (live) a.mode[i] = cur;
 }
 
 // ---- routes ----------------------------------------------------------------------------------------------------
