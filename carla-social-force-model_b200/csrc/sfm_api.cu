@@ -131,7 +131,6 @@ struct sfm_ctx {
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> event_pool;
     int k1_target_ctas = 148 * 4 * 16;
-    int k1_ir = 2, k1_minb = 5;     // tuning knobs (SFM_K1_IR, SFM_K1_MINB)
     bool k1_first = false;
     bool k2_prune = true;           // SFM_K2_PRUNE=0: cell-list kernels scan every point of an item (no chunk bounds)
     int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
@@ -377,7 +376,7 @@ int launch_stage(sfm_ctx* c) {
 
 int launch_pairs_rows(sfm_ctx* c) {
     if (!c->staged) SFM_TRY(launch_stage(c));
-    const int IR = c->k1_ir;
+    constexpr int IR = 2;
     const int rows_per_cta = K1_THREADS * IR;
     const int itiles = (int)(c->rows_pad / rows_per_cta);
     const int total_tiles = (int)((int64_t)c->world * c->rows_pad / K1_TJ);
@@ -398,11 +397,7 @@ int launch_pairs_rows(sfm_ctx* c) {
             k1_ped_pairs<IRV, false, MINBV><<<grid, K1_THREADS, 0, c->stream>>>(                                        \
                 planes_cur(c), (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
     } while (0)
-    if (IR == 2 && c->k1_minb <= 5) SFM_K1_LAUNCH(2, 5);
-    else if (IR == 2 && c->k1_minb == 6) SFM_K1_LAUNCH(2, 6);
-    else if (IR == 2) SFM_K1_LAUNCH(2, 8);
-    else if (c->k1_minb <= 8) SFM_K1_LAUNCH(1, 8);
-    else SFM_K1_LAUNCH(1, 10);
+    SFM_K1_LAUNCH(2, 5);            // the configuration profiles/tune_k1_r1.log found best for the row kernel
 #undef SFM_K1_LAUNCH
     c->launches += 1;
     c->pair_launches += 1;
@@ -866,8 +861,6 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_OVERLAP")) c->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K1_TARGET_CTAS")) c->k1_target_ctas = std::max(1, std::atoi(env));
     else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
-    if (const char* env = std::getenv("SFM_K1_IR")) c->k1_ir = std::atoi(env) == 1 ? 1 : 2;
-    if (const char* env = std::getenv("SFM_K1_MINB")) c->k1_minb = std::atoi(env);
     if (const char* env = std::getenv("SFM_K1_MODE")) c->k1_rows_mode = std::strcmp(env, "rows") == 0;
     *out = c;
     return 0;

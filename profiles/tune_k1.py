@@ -1,4 +1,5 @@
-"""K1 tuning sweep (rows per thread, min CTAs/SM, grid depth) at N = 65,536 -- prints ms per launch for each variant."""
+"""[historical: the SFM_K1_IR / SFM_K1_MINB knobs of the v2 row kernel were removed after this sweep picked IR=2, MINB=5;
+results in tune_k1_r1.log]  K1 tuning sweep (rows per thread, min CTAs/SM, grid depth) at N = 65,536 -- prints ms per launch for each variant."""
 import itertools
 import os
 import sys
