@@ -238,6 +238,7 @@ def run_ours(args, world, rank, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms_per_step = t.item() / e2e_steps
     e2e_value = n * (n - 1) / (e2e_ms_per_step * 1e-3)
+    e.check_peers()                               # a timed-out flag barrier would have produced garbage: fail loudly
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()

@@ -10,7 +10,8 @@
 //     (k1_sym_finish reads all staged rows) never sees tick k+1's rows arrive.
 // What remains between the kernels is a flag barrier (k7_barrier): every rank stores its epoch into every peer's flag
 // array (release, system scope) and waits until all peers' epochs have arrived (acquire, system scope).  The wait is
-// bounded: after ~2 s of spinning the kernel raises the error word instead of hanging the GPU.
+// bounded: after ~10 s of spinning the kernel raises the error word instead of hanging the GPU, and later barriers
+// return at once (sfm_peer_status reports it; the engine and bench.py turn it into an exception).
 #pragma once
 
 #include "sfm_common.cuh"
@@ -36,11 +37,12 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* addr) {
 __global__ void k7_barrier(PeerPtrs flags, unsigned* own_flags, int world, int rank, unsigned epoch, unsigned* error) {
     const int r = threadIdx.x;
     if (r >= world) return;
+    if (*reinterpret_cast<volatile unsigned*>(error)) return;  // a peer was lost earlier: do not wait again
     __threadfence_system();                                   // everything this rank wrote before the barrier
     st_release_sys(reinterpret_cast<unsigned*>(flags.p[r]) + rank, epoch);
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(own_flags + r) - epoch) < 0) {
-        if (clock64() - t0 > 4000000000LL) {                 // ~2 s at 1.9 GHz: a peer is gone
+        if (clock64() - t0 > 20000000000LL) {                // ~10 s at 1.9 GHz: a peer is gone
             atomicExch(error, 1u);
             break;
         }

@@ -214,3 +214,9 @@ class Engine:
 
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)
+        self.check_peers()
+
+    def check_peers(self):
+        """Raise if a flag barrier of the peer-memory exchange gave up waiting for another rank."""
+        if self.peer and self.ctx.peer_status()['timed_out']:
+            raise native.SfmError('peer-memory exchange: a barrier timed out waiting for another rank; results are invalid')
