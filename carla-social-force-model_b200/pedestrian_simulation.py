@@ -62,18 +62,29 @@ class PedestrianSimulation:
         """Do one step in the simulation."""
         if self.peds.state is None or self.peds.size() == 0:
             return
-        self.peds.apply_current_mode()
-        for mode in self.peds.state['mode']:
+        # apply_current_mode, then every machine's tick (pedestrian_simulation.py:63-65) -- one pass over the mode objects,
+        # which also yields the uint8 codes the device needs (the two steps are independent per pedestrian)
+        state = self.peds.state
+        n = len(state)
+        speeds, codes = np.empty(n), np.empty(n, dtype=np.uint8)
+        for k, mode in enumerate(state['mode']):
             if hasattr(mode, 'tick'):
+                speeds[k] = mode.target_speed
                 mode.tick(sim_time)
-        codes = self.peds.mode_codes()
+                codes[k] = mode.current_mode
+            else:                                  # plain PedMode / int in the mode column
+                speeds[k] = state['target_speed'][k]
+                codes[k] = int(mode)
+        state['target_speed'] = speeds
         for row in np.nonzero(codes == PedMode.CHECKING_TRAFFIC)[0]:
-            ped = self.peds.state[row]
+            ped = state[row]
             ready = True
             if self.dyn_obstacles:
                 ready = check_traffic(ped, self.dyn_obstacles, self.dyn_obs_vel, self.dyn_obs_extent)
             if ready:
                 ped['mode'].set_mode(PedMode.CROSSING_ROAD)
+                codes[row] = ped['mode'].current_mode
+        self._mode_codes = codes
         if self.record_states:
             self.peds.record_current_state(sim_time)
             if self.dyn_obstacles:
@@ -103,7 +114,7 @@ class PedestrianSimulation:
                 self._clear_set(session, f.force_class)
             else:
                 f._bind(session)
-        session.upload_peds(self.peds)
+        session.upload_peds(self.peds, getattr(self, '_mode_codes', None))
         session.ctx.step(1, integrate_positions=False)
         _, vel = session.ctx.download_state()
         self.new_velocities = self.peds.state[['id', 'vel']]     # a view: writes through to state['vel']

@@ -102,11 +102,12 @@ class PedState:
         return np.fromiter((int(getattr(m, 'current_mode', m)) for m in self.state['mode']), dtype=np.uint8,
                            count=self.size())
 
-    def device_columns(self):
+    def device_columns(self, mode_codes=None):
         """Contiguous float64 / uint8 columns in the order ``sfm_upload_state`` takes them."""
         s = self.state
+        codes = self.mode_codes() if mode_codes is None or len(mode_codes) != len(s) else mode_codes
         return (np.ascontiguousarray(s['loc']), np.ascontiguousarray(s['vel']), np.ascontiguousarray(s['next_waypoint']),
-                np.ascontiguousarray(s['radius']), np.ascontiguousarray(s['target_speed']), self.mode_codes())
+                np.ascontiguousarray(s['radius']), np.ascontiguousarray(s['target_speed']), codes)
 
     # ---- recording (pedestrian_state.py:100-107) --------------------------------------------------------------------
     def record_current_state(self, sim_time):

@@ -32,8 +32,8 @@ class Session:
             self.owner = {k: None for k in self.owner}
         return params
 
-    def upload_peds(self, peds):
-        self.ctx.upload_state(*peds.device_columns())
+    def upload_peds(self, peds, mode_codes=None):
+        self.ctx.upload_state(*peds.device_columns(mode_codes))
 
     def bind_set(self, which, owner, version, loader):
         """Make ``owner``'s point set resident for class ``which`` unless it already is (same object, same version)."""
