@@ -19,6 +19,7 @@ using namespace sfm;
 namespace {
 
 thread_local std::string g_error;
+unsigned long long g_alloc_epoch = 0;      // bumped by every device (re)allocation: captured graphs bake pointers in
 
 int fail(const std::string& msg) {
     g_error = msg;
@@ -51,6 +52,7 @@ struct DevBuf {
         size_t want = n + n / 8 + 256;
         SFM_CUDA(cudaMalloc(&p, want * sizeof(T)));
         cap = want;
+        g_alloc_epoch += 1;
         return 0;
     }
     void release() {
@@ -171,6 +173,17 @@ struct sfm_ctx {
     DevBuf<unsigned> flags;                          // [MAX_PEERS] epochs signalled by the peers + [MAX_PEERS] error word
     unsigned epoch = 0;
     int64_t barriers = 0;
+    // ---- CUDA graph of one single-rank tick (sfm_step), opt-in (SFM_GRAPH=1): the ~12 launches of a tick replayed as one
+    //      graph launch; re-captured whenever a pointer, a size or a parameter a kernel argument was built from may have
+    //      changed.  Measured (profiles/small_n_steps_r1.log): 58 -> 55 us per tick at N = 64, 158 -> 145 us at N = 4,096,
+    //      738 -> 785 us at N = 16,384 -- the small-crowd tick is bound by the latency of its chain of dependent kernels on
+    //      the GPU, not by launch overhead on the host, so replay is not the default.
+    bool use_graph = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned long long graph_alloc_epoch = 0, config_epoch = 0, graph_config_epoch = 0;
+    int graph_integrate = -1, graph_warm = 0;
+    cudaStream_t graph_stream = nullptr;
+    int64_t graph_launches = 0, graph_pair_launches = 0, graph_pair_evals = 0, graph_replays = 0;
     bool pairs_pending = false;
     bool step_open = false;         // sfm_step_begin done, sfm_step_end outstanding     // symmetric accumulation launched, finish kernel not yet run
 };
@@ -854,6 +867,7 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_K1_SMEM_PAD")) c->k1_smem_pad = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("SFM_K1_FIRST")) c->k1_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PRUNE")) c->k2_prune = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SFM_GRAPH")) c->use_graph = std::atoi(env) != 0;
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -885,6 +899,7 @@ int sfm_destroy(sfm_ctx* c) {
                 cudaIpcCloseMemHandle(c->peer_flags[r]);
             }
     c->flags.release(); c->check_list.release();
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->cmp4.release(); c->cmp2.release(); c->cmp3.release(); c->cmp1.release(); c->cmpi.release(); c->cmpb.release();
     c->mm_speed.release(); c->mm_initial.release(); c->mm_crossing.release(); c->mm_margin.release();
     c->mm_next_time.release(); c->tr_center.release(); c->tr_vel.release(); c->rt_end.release(); c->rt_cursor.release();
@@ -900,6 +915,7 @@ int sfm_destroy(sfm_ctx* c) {
 
 int sfm_set_stream(sfm_ctx* c, void* cuda_stream) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return 0;
@@ -913,6 +929,7 @@ int sfm_synchronize(sfm_ctx* c) {
 
 int sfm_set_params(sfm_ctx* c, const sfm_params* p) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (!p) return fail("null params");
     if (!(p->step_length > 0.0)) return fail("step_length must be positive");
     if (!(p->tau > 0.0)) return fail("tau must be positive");
@@ -929,6 +946,7 @@ int sfm_set_params(sfm_ctx* c, const sfm_params* p) {
 
 int sfm_set_origin(sfm_ctx* c, double ox, double oy, double oz) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     c->ox = ox; c->oy = oy; c->oz = oz;
     c->origin_set = true;
     c->staged = false;
@@ -937,6 +955,7 @@ int sfm_set_origin(sfm_ctx* c, double ox, double oy, double oz) {
 
 int sfm_set_partition(sfm_ctx* c, int world, int rank, int64_t rows_pad) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (world < 1 || rank < 0 || rank >= world) return fail("bad world / rank");
     if (rows_pad <= 0 || rows_pad % ROW_ALIGN != 0) return fail("rows_pad must be a positive multiple of 256");
     c->world = world; c->rank = rank; c->rows_pad = rows_pad;
@@ -948,6 +967,7 @@ int sfm_set_partition(sfm_ctx* c, int world, int rank, int64_t rows_pad) {
 int sfm_upload_state(sfm_ctx* c, int64_t n, const double* loc, const double* vel, const double* wp3,
                      const double* radius, const double* speed, const uint8_t* mode) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (!c->have_params) return fail("sfm_set_params must be called first");
     if (n < 0 || n > (int64_t)1 << 28) return fail("bad row count");
     if (n > 0 && (!loc || !vel || !wp3 || !radius || !speed || !mode)) return fail("null state array");
@@ -1031,6 +1051,7 @@ int sfm_download_state(sfm_ctx* c, int64_t n, double* loc, double* vel) {
 int sfm_set_borders(sfm_ctx* c, int64_t n_sections, const double* center, const double* length, const int64_t* offsets,
                     const double* points) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (n_sections > 0 && !length) return fail("null section_length");
     return upload_set(c, c->borders, n_sections, center, length, 0.0, nullptr, offsets, points);
 }
@@ -1038,6 +1059,7 @@ int sfm_set_borders(sfm_ctx* c, int64_t n_sections, const double* center, const 
 int sfm_set_obstacles(sfm_ctx* c, int which, int64_t n_obstacles, const double* centers, const double* velocities,
                       const int64_t* offsets, const double* points) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (!c->have_params) return fail("sfm_set_params must be called first");
     if (which != SFM_FORCE_STATIC_OBSTACLE && which != SFM_FORCE_DYNAMIC_OBSTACLE) return fail("bad obstacle class");
     const bool dynamic = which == SFM_FORCE_DYNAMIC_OBSTACLE;
@@ -1108,7 +1130,58 @@ int sfm_step(sfm_ctx* c, int n_steps, int integrate_positions) {
     if (c->n == 0) return 0;                       // pedestrian_simulation.py:60 early-out
     if (c->world > 1)
         return fail("multi-rank contexts step with sfm_step_begin / reduce-scatter / sfm_step_end / all-gather");
-    for (int s = 0; s < n_steps; ++s) SFM_TRY(step_once(c, true, integrate_positions != 0, false));
+    const bool integrate = integrate_positions != 0;
+    for (int s = 0; s < n_steps; ++s) {
+        const bool graphable = c->use_graph && !c->profiling && c->staged && !(c->have_routes && c->routes_fused);
+        if (!graphable) {
+            SFM_TRY(step_once(c, true, integrate, false));
+            c->graph_warm = 0;
+            continue;
+        }
+        const bool fresh = c->graph_exec && c->graph_alloc_epoch == g_alloc_epoch && c->graph_config_epoch == c->config_epoch &&
+                           c->graph_integrate == (int)integrate && c->graph_stream == c->stream;
+        if (fresh) {
+            SFM_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+            c->launches += c->graph_launches; c->pair_launches += c->graph_pair_launches;
+            c->pair_evals += c->graph_pair_evals;
+            c->steps += 1; c->graph_replays += 1;
+            c->perm_valid = false;
+            continue;
+        }
+        if (c->graph_warm < 2) {                    // two eager ticks first: every buffer a tick touches exists afterwards
+            const unsigned long long before = g_alloc_epoch;
+            SFM_TRY(step_once(c, true, integrate, false));
+            c->graph_warm = (before == g_alloc_epoch) ? c->graph_warm + 1 : 0;
+            continue;
+        }
+        // capture one tick (the auxiliary stream joins the capture through the fork / join events)
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        const int64_t l0 = c->launches, p0 = c->pair_launches, e0 = c->pair_evals, st0 = c->steps;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const int rc = step_once(c, true, integrate, false);
+            const cudaError_t end = cudaStreamEndCapture(c->stream, &graph);
+            ok = rc == 0 && end == cudaSuccess && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&c->graph_exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        c->graph_launches = c->launches - l0; c->graph_pair_launches = c->pair_launches - p0;
+        c->graph_pair_evals = c->pair_evals - e0;
+        c->launches = l0; c->pair_launches = p0; c->pair_evals = e0; c->steps = st0;   // nothing ran during the capture
+        if (!ok) {                                   // capture not possible here: stay eager for good
+            cudaGetLastError();
+            c->use_graph = false;
+            c->graph_exec = nullptr;
+            c->join_pending = false;
+            c->step_open = false;
+            SFM_TRY(step_once(c, true, integrate, false));
+            continue;
+        }
+        c->graph_alloc_epoch = g_alloc_epoch; c->graph_config_epoch = c->config_epoch;
+        c->graph_integrate = (int)integrate; c->graph_stream = c->stream;
+        --s;                                         // the tick itself: replay the fresh graph
+    }
     return 0;
 }
 
@@ -1200,6 +1273,7 @@ int sfm_set_mode_machines(sfm_ctx* c, int64_t n, const double* initial_speed, co
                           const double* safety_margin, const double* mode_speed, const double* next_mode_time,
                           double waiting_time) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (n != c->n) return fail("row count differs from the uploaded state");
     if (n > 0 && (!initial_speed || !crossing_speed || !safety_margin || !mode_speed || !next_mode_time))
         return fail("null mode-machine array");
@@ -1286,6 +1360,7 @@ int sfm_download_modes(sfm_ctx* c, int64_t n, uint8_t* mode, double* mode_speed,
 int sfm_set_routes(sfm_ctx* c, int64_t n, const int64_t* offsets, const double* waypoints, const uint8_t* crossing,
                    double distance_threshold, int fused) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (n != c->n) return fail("row count differs from the uploaded state");
     if (!c->have_mm) return fail("sfm_set_mode_machines must be called first (a hand-over requests a mode)");
     if (n > 0 && !offsets) return fail("null route offsets");
@@ -1350,6 +1425,7 @@ int sfm_download_routes(sfm_ctx* c, int64_t n, int64_t* cursor, uint8_t* finishe
 
 int sfm_despawn_finished(sfm_ctx* c, int64_t* n_after, int64_t* n_removed) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (!c->have_routes || !c->have_mm) return fail("sfm_set_routes must be called first");
     if (c->world > 1) return fail("despawning changes the row partition: single-rank contexts only");
     if (c->step_open) return fail("despawn between sfm_step_begin and sfm_step_end");
@@ -1466,6 +1542,7 @@ int launch_vehicle_rings(sfm_ctx* c) {
 int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, const double* yaw_deg,
                      const double* velocities, const double* extents, double resolution, double size_factor) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (!c->have_params) return fail("sfm_set_params must be called first");
     SetStorage& st = c->dyn;
     st.s.count = 0;
@@ -1608,6 +1685,7 @@ int sfm_peer_export(sfm_ctx* c, void* handles) {
 
 int sfm_peer_import(sfm_ctx* c, const void* all_handles) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     if (!all_handles) return fail("null pointer");
     if (!c->flags.p) return fail("sfm_peer_export must be called first");
     const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
@@ -1664,6 +1742,7 @@ int sfm_peer_status(sfm_ctx* c, int64_t* barriers, int* timed_out) {
 
 int sfm_set_profiling(sfm_ctx* c, int enabled) {
     SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;                      // a captured tick graph (sfm_step) must be rebuilt
     SFM_TRY(drain_spans(c));
     c->profiling = enabled != 0;
     return 0;
@@ -1674,7 +1753,9 @@ int sfm_reset_stats(sfm_ctx* c) {
     SFM_TRY(drain_spans(c));
     c->launches = c->steps = c->pair_launches = c->pair_evals = 0;
     for (double& m : c->ms) m = 0.0;
-    c->fixup_zeroed = false;
+    c->graph_replays = 0;
+    if (c->fixup_rows.p) SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, sizeof(unsigned long long), c->stream));
+    c->fixup_zeroed = c->fixup_rows.p != nullptr;
     return 0;
 }
 
@@ -1686,6 +1767,7 @@ int sfm_get_stats(sfm_ctx* c, sfm_stats* out) {
     out->ms_pairs = c->ms[ST_PAIRS]; out->ms_cells = c->ms[ST_CELLS]; out->ms_segments = c->ms[ST_SEGMENTS];
     out->ms_integrate = c->ms[ST_INTEGRATE];
     out->ms_lifecycle = c->ms[ST_LIFECYCLE];
+    out->graph_replays = c->graph_replays;
     out->fixup_rows = 0;
     out->pair_evaluations = c->pair_evals;
     if (c->fixup_rows.p && c->fixup_zeroed) {

@@ -55,7 +55,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [('launches', C.c_int64), ('steps', C.c_int64), ('ms_pairs', C.c_double), ('ms_cells', C.c_double),
                 ('ms_segments', C.c_double), ('ms_integrate', C.c_double), ('pair_launches', C.c_int64),
-                ('fixup_rows', C.c_int64), ('pair_evaluations', C.c_int64), ('ms_lifecycle', C.c_double)]
+                ('fixup_rows', C.c_int64), ('pair_evaluations', C.c_int64), ('ms_lifecycle', C.c_double), ('graph_replays', C.c_int64)]
 
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',

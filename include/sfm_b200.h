@@ -71,6 +71,7 @@ typedef struct {
     int64_t fixup_rows;                   /* rows the degenerate-pair repair path recomputed (0 for healthy crowds) */
     int64_t pair_evaluations;             /* pair terms K1 evaluated (padded slots included; one per unordered pair) */
     double ms_lifecycle;                  /* K4/K5/K6: mode machines, waypoint hand-over, vehicle rings, recorder */
+    int64_t graph_replays;                /* ticks of sfm_step that ran as one CUDA graph launch (SFM_GRAPH=1 enables) */
 } sfm_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -121,6 +122,9 @@ int sfm_enumerate_pairs(sfm_ctx* ctx, int force_class, int64_t capacity, int64_t
 /* ---- the fused tick: replaces PedestrianSimulation.tick's force sum and calculate_new_velocities
  *      (pedestrian_simulation.py:81-83,117-124; stateutils.py:18-23) plus, optionally, the position update the
  *      reference leaves to the CARLA server (run_simulation.py:77-87): x+ = x + dt * v+. --------------------------- */
+/* With SFM_GRAPH=1 a single-rank tick's launches are captured once into a CUDA graph and replayed (re-captured whenever
+ * an allocation, a size or a parameter changes; not while profiling or with fused routes).  Off by default: the tick is
+ * bound by its chain of dependent kernels, not by launch overhead (profiles/small_n_steps_r1.log). */
 int sfm_step(sfm_ctx* ctx, int n_steps, int integrate_positions);
 /* Host-buffer tick: upload loc/vel, one step, download the new velocities (and positions when new_loc != NULL). */
 int sfm_tick_host(sfm_ctx* ctx, int64_t n, const double* loc, const double* vel, double* new_vel, double* new_loc);

@@ -130,3 +130,27 @@ def test_two_rank_partition_emulated_on_one_gpu(sfm_config):
     vel_p = np.concatenate([ranks[r][0].download_state()[1] for r in range(2)])
     np.testing.assert_allclose(loc_p, loc_w, rtol=0, atol=1e-6)       # split geometry differs -> float32 sum order differs
     np.testing.assert_allclose(vel_p, vel_w, rtol=0, atol=2e-5)
+
+
+def test_graph_replay_equals_eager_ticks(sfm_config, monkeypatch):
+    """With SFM_GRAPH=1 sfm_step replays a captured CUDA graph of the tick after two eager ticks; the trajectory is bit-identical to the
+    eager path, and state refreshes / set changes in between are picked up (re-staging, re-capture)."""
+    w = synth.make_config(2, n=1536)
+    monkeypatch.setenv('SFM_GRAPH', '1')                    # opt-in (not the default: see sfm_api.cu)
+    graph = make_context(w, sfm_config)
+    monkeypatch.delenv('SFM_GRAPH')
+    eager = make_context(w, sfm_config)
+    for ctx in (graph, eager):
+        ctx.reset_stats()
+        ctx.step(12, True)
+        loc, vel = ctx.download_state()
+        ctx.update_kinematics(loc + 0.01, vel)             # simulator refresh: re-staged outside the graph
+        ctx.step(5, True)
+        set_vehicles(ctx, w, 7)                            # new vehicle rings: the graph is rebuilt
+        ctx.step(5, True)
+    a, b = graph.download_state(), eager.download_state()
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    sg, se = graph.stats(), eager.stats()
+    assert se['graph_replays'] == 0 and sg['graph_replays'] >= 12
+    assert sg['steps'] == se['steps'] == 22 and sg['launches'] == se['launches']
