@@ -366,8 +366,11 @@ __device__ __forceinline__ void stage_points(float2* __restrict__ sp, const doub
 // takes the items with index % K2_WARPS == k that survive the bounding-box test.  Each warp stages its item's points in its own
 // shared-memory slice (warp-level barriers only), scans them, and keeps a partial force per pedestrian; the partials
 // are combined in warp order at the end, so the summation order is fixed.
+#ifndef SFM_K2_MINB
+#define SFM_K2_MINB 6                  // min CTAs per SM (register cap: 80) of the segment kernels, profiles/k2_minb_sweep_r1.log
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(K2_THREADS, 4) k2_segments(const SegArgs a) {
+__global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const SegArgs a) {
     __shared__ __align__(16) float2 sp[K2_WARPS][K2_CHUNK];
     __shared__ __align__(16) float4 sc[K2_WARPS][2 * K2_PRUNE_MAX];
     __shared__ double2 part[K2_WARPS][32];

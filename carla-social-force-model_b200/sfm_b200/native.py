@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
-LIB_PATH = os.environ.get('SFM_LIB', os.path.join(HERE, 'libsfm_b200.so'))     # SFM_LIB: tuning builds only
+LIB_PATH = os.environ.get('SFM_LIB') or os.path.join(HERE, 'libsfm_b200.so')     # SFM_LIB: tuning builds only
 
 FORCE_CLASSES = ('acceleration_force', 'pedestrian_force', 'border_force', 'static_obstacle_force',
                  'dynamic_obstacle_force')                      # pedestrian_simulation.py:37-48 dict order
