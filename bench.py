@@ -132,7 +132,7 @@ def run_reference(args, world, rank):
     cfg = load_config()
     w, name = build_workload(args, world)
     cores = os.cpu_count() or 1
-    rows_per_core = args.cpu_rows_per_core
+    rows_per_core = max(1, args.cpu_rows_per_core // 4)         # K + W samples of ~2-3 s each
     for _ in range(args.warmup):
         cpu_baseline.time_sample(w, cfg, rows_per_core=max(1, rows_per_core // 8), cores=cores)
     times, rows = [], 0
@@ -340,7 +340,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg4', 'cfg5'])
     ap.add_argument('--peds', dest='n', type=int, default=None, help='override the pedestrian count')
-    ap.add_argument('--cpu-rows-per-core', type=int, default=48)
+    ap.add_argument('--cpu-rows-per-core', type=int, default=384,
+                    help='rows of the CPU sample per host core (cpu_baseline leg: ~10 s; the reference arm uses a quarter per step)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))

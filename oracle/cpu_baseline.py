@@ -22,7 +22,7 @@ def _worker(rows):
     w, scene, dyn, dyn_vel = _SHARED['w'], _SHARED['scene'], _SHARED['dyn'], _SHARED['dyn_vel']
     t0 = time.perf_counter()
     per_class = O.forces_by_class(scene, w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode, dyn, dyn_vel,
-                                  rows=rows)
+                                  rows=rows, chunk=48)             # 48-row chunks: ~0.9 GB of temporaries per worker
     F = O.total_force(per_class, len(rows))
     O.new_velocities(w.vel[rows], F, w.target_speed[rows], scene.dt, scene.max_speed_factor)
     return time.perf_counter() - t0
