@@ -158,3 +158,29 @@ def test_oracle_despawn_reproduces_reference_golden(scenario, sfm_config):
     assert np.array_equal(g['alive'], got['alive']) and np.array_equal(g['mode'], got['mode'])
     assert np.array_equal(g['ids_final'], got['ids_final']) and 0 < len(got['ids_final']) < w.n // 2
     assert np.abs(g['loc_final'] - got['loc_final']).max() <= 1e-9 and np.array_equal(g['wp_final'], got['wp_final'])
+
+
+def test_host_mode_manager_equals_oracle_columns():
+    """The drop-in's table-driven PedModeManager against the array restatement (itself pinned to the reference's
+    objects above) under random tick / request sequences, unknown modes included."""
+    from ped_mode_manager import PedMode, PedModeManager
+    rng = np.random.default_rng(23)
+    n = 48
+    speed, factor, margin = rng.uniform(1, 2, n), rng.uniform(1, 2, n), rng.uniform(-1, 2, n)
+    init = rng.integers(0, 5, n)
+    objs = [PedModeManager(f'p_{i}', speed[i], PedMode(int(init[i])), factor[i], margin[i]) for i in range(n)]
+    cols = LO.Machines.create(speed, init, factor, margin)
+    t = 0.0
+    for _ in range(300):
+        t += rng.uniform(0.0, 1.5)
+        for o in objs:
+            o.tick(t)
+        cols.tick(t)
+        rows = rng.choice(n, size=6, replace=False)
+        wanted = int(rng.integers(0, 6))                       # 5 is not a mode: ignored by both
+        for i in rows:
+            objs[i].set_mode(PedMode(wanted) if wanted < 5 else wanted)
+        cols.set_mode(rows, wanted)
+        assert [int(o.current_mode) for o in objs] == cols.mode.tolist()
+        assert [float(o.target_speed) for o in objs] == cols.target_speed.tolist()
+        assert [float(o.next_mode_time) for o in objs] == cols.next_mode_time.tolist()
