@@ -110,6 +110,7 @@ struct ModeTickArgs {
     unsigned long long* counters;        // [0] pedestrians that entered CROSSING_ROAD this tick, [1] idle wake-ups
     int* check_list;                     // [n] rows in CHECKING_TRAFFIC this tick (compacted)
     int* check_count;                    // [1]
+    uint8_t* blocked;                    // [n] per list entry: some vehicle blocks the crossing
 };
 
 constexpr int K4_THREADS = 128;
@@ -143,72 +144,74 @@ __global__ void __launch_bounds__(K4_THREADS) k4_tick_modes(const ModeTickArgs a
     a.mode[i] = cur;
 }
 
-// Phase 2, one thread per waiting pedestrian: check_traffic.py:7-61 against every vehicle.  Vehicles are staged in shared
-// memory 256 at a time together with what depends on the vehicle alone (half-length vector heading * extent[0], speed).
-// A vehicle whose swept segment back -> goal cannot touch the pedestrian's path (bounding boxes apart by more than a
-// rounding margin) is dismissed after a handful of operations -- exactly the cases in which the segment test says "no".
+// Phase 2, one thread per (waiting pedestrian, tile of 256 vehicles): check_traffic.py:7-61.  grid.y walks the vehicle
+// tiles, so a crowd with few waiting pedestrians still fills the machine; a tile that finds a blocking vehicle raises the
+// pedestrian's flag.  Per tile the vehicles are staged in shared memory together with what depends on the vehicle alone
+// (half-length vector heading * extent[0], speed).  A vehicle whose swept segment back -> goal cannot touch the
+// pedestrian's path (bounding boxes apart by more than a rounding margin) is dismissed after a handful of operations --
+// exactly the cases in which the segment test says "no".
 __global__ void __launch_bounds__(K4_THREADS) k4_gap_acceptance(const ModeTickArgs a) {
     __shared__ double2 s_center[K4_VEH_TILE], s_vel[K4_VEH_TILE], s_half[K4_VEH_TILE];
     __shared__ double s_speed[K4_VEH_TILE];
     const int count = *a.check_count;
+    if ((int)(blockIdx.x * K4_THREADS) >= count) return;
+    const int v0 = blockIdx.y * K4_VEH_TILE;
+    const int m = min(K4_VEH_TILE, a.tr.count - v0);
+    for (int v = threadIdx.x; v < m; v += K4_THREADS) {
+        const double2 c = a.tr.center[v0 + v], u = a.tr.velocity[v0 + v];
+        const double vs = norm2d(u.x, u.y);
+        const double dn = (vs == 0.0) ? 1.0 : vs;                                              // stateutils.py:88-90
+        s_center[v] = c;
+        s_vel[v] = u;
+        s_half[v] = make_double2(__dmul_rn(__ddiv_rn(u.x, dn), a.tr.ext0_x), __dmul_rn(__ddiv_rn(u.y, dn), a.tr.ext0_y));
+        s_speed[v] = vs;
+    }
+    __syncthreads();
     for (int base = blockIdx.x * K4_THREADS; base < count; base += gridDim.x * K4_THREADS) {
         const int k = base + threadIdx.x;
-        const bool live = k < count;
-        const int64_t i = live ? a.check_list[k] : 0;
-        double px = 0.0, py = 0.0, gx = 0.0, gy = 0.0, speed = 1.0, margin = -1.0, time_ped = 0.0;
-        if (live) {
-            const double4 L = a.locr[i];
-            const double2 w = a.wp[i];
-            px = L.x; py = L.y; gx = w.x; gy = w.y;
-            speed = a.mm.crossing_speed[i];
-            margin = a.mm.safety_margin[i];
-            time_ped = __ddiv_rn(norm2d(__dsub_rn(gx, px), __dsub_rn(gy, py)), speed);      // check_traffic.py:27-28
-        }
-        const bool looks = live && !(margin < 0.0);                        // negative margin: cross without looking (:24)
+        if (k >= count) continue;
+        const int64_t i = a.check_list[k];
+        const double margin = a.mm.safety_margin[i];
+        if (margin < 0.0) continue;                                        // crosses without looking (check_traffic.py:24)
+        const double4 L = a.locr[i];
+        const double2 w = a.wp[i];
+        const double px = L.x, py = L.y, gx = w.x, gy = w.y;
+        const double speed = a.mm.crossing_speed[i];
+        const double time_ped = __ddiv_rn(norm2d(__dsub_rn(gx, px), __dsub_rn(gy, py)), speed);      // :27-28
         const double horizon = __dadd_rn(time_ped, margin);
         const double eps = 1.0e-9 * (1.0 + fabs(px) + fabs(py) + fabs(gx) + fabs(gy));
         const double x0 = fmin(px, gx) - eps, x1 = fmax(px, gx) + eps, y0 = fmin(py, gy) - eps, y1 = fmax(py, gy) + eps;
-        bool ready = true;
-        for (int v0 = 0; v0 < a.tr.count; v0 += K4_VEH_TILE) {
-            const int m = min(K4_VEH_TILE, a.tr.count - v0);
-            __syncthreads();
-            for (int v = threadIdx.x; v < m; v += K4_THREADS) {
-                const double2 c = a.tr.center[v0 + v], u = a.tr.velocity[v0 + v];
-                const double vs = norm2d(u.x, u.y);
-                const double dn = (vs == 0.0) ? 1.0 : vs;                                      // stateutils.py:88-90
-                s_center[v] = c;
-                s_vel[v] = u;
-                s_half[v] = make_double2(__dmul_rn(__ddiv_rn(u.x, dn), a.tr.ext0_x), __dmul_rn(__ddiv_rn(u.y, dn), a.tr.ext0_y));
-                s_speed[v] = vs;
-            }
-            __syncthreads();
-            if (looks && ready) {
-                for (int v = 0; v < m; ++v) {
-                    const double2 c = s_center[v], u = s_vel[v], h = s_half[v];
-                    const double fx = __dadd_rn(c.x, h.x), fy = __dadd_rn(c.y, h.y);         // front (:35)
-                    const double bx = __dsub_rn(c.x, h.x), by = __dsub_rn(c.y, h.y);         // back  (:36)
-                    const double tx = __dadd_rn(fx, __dmul_rn(u.x, horizon)), ty = __dadd_rn(fy, __dmul_rn(u.y, horizon));
-                    if (fmax(bx, tx) < x0 || fmin(bx, tx) > x1 || fmax(by, ty) < y0 || fmin(by, ty) > y1) continue;
-                    double ix, iy;
-                    if (!segment_hit(px, py, gx, gy, bx, by, tx, ty, ix, iy)) continue;
-                    const double vs = s_speed[v];
-                    if (vs == 0.0) continue;                                                  // :48-49
-                    const double tti_ped = __ddiv_rn(norm2d(__dsub_rn(ix, px), __dsub_rn(iy, py)), speed);
-                    const double tti_front = __ddiv_rn(norm2d(__dsub_rn(ix, fx), __dsub_rn(iy, fy)), vs);
-                    const double tti_back = __ddiv_rn(norm2d(__dsub_rn(ix, bx), __dsub_rn(iy, by)), vs);
-                    if (__dsub_rn(tti_front, margin) < tti_ped && tti_ped < __dadd_rn(tti_back, margin)) {   // :57
-                        ready = false;
-                        break;
-                    }
-                }
+        for (int v = 0; v < m; ++v) {
+            const double2 c = s_center[v], u = s_vel[v], h = s_half[v];
+            const double fx = __dadd_rn(c.x, h.x), fy = __dadd_rn(c.y, h.y);                 // front (:35)
+            const double bx = __dsub_rn(c.x, h.x), by = __dsub_rn(c.y, h.y);                 // back  (:36)
+            const double tx = __dadd_rn(fx, __dmul_rn(u.x, horizon)), ty = __dadd_rn(fy, __dmul_rn(u.y, horizon));
+            if (fmax(bx, tx) < x0 || fmin(bx, tx) > x1 || fmax(by, ty) < y0 || fmin(by, ty) > y1) continue;
+            double ix, iy;
+            if (!segment_hit(px, py, gx, gy, bx, by, tx, ty, ix, iy)) continue;
+            const double vs = s_speed[v];
+            if (vs == 0.0) continue;                                                          // :48-49
+            const double tti_ped = __ddiv_rn(norm2d(__dsub_rn(ix, px), __dsub_rn(iy, py)), speed);
+            const double tti_front = __ddiv_rn(norm2d(__dsub_rn(ix, fx), __dsub_rn(iy, fy)), vs);
+            const double tti_back = __ddiv_rn(norm2d(__dsub_rn(ix, bx), __dsub_rn(iy, by)), vs);
+            if (__dsub_rn(tti_front, margin) < tti_ped && tti_ped < __dadd_rn(tti_back, margin)) {   // :57
+                a.blocked[k] = 1;
+                break;
             }
         }
-        if (live && ready) {
-            uint8_t cur = SFM_CHECKING_TRAFFIC;
-            request_mode(a.mm, i, SFM_CROSSING_ROAD, a.sim_time, cur);
-            a.mode[i] = cur;
-            atomicAdd(a.counters + 0, 1ull);
-        }
+    }
+}
+
+// Phase 3: every waiting pedestrian no vehicle blocks requests CROSSING_ROAD (pedestrian_simulation.py:72-73).
+__global__ void __launch_bounds__(K4_THREADS) k4_gap_commit(const ModeTickArgs a) {
+    const int count = *a.check_count;
+    for (int k = blockIdx.x * K4_THREADS + threadIdx.x; k < count; k += gridDim.x * K4_THREADS) {
+        if (a.blocked[k]) continue;
+        const int64_t i = a.check_list[k];
+        uint8_t cur = SFM_CHECKING_TRAFFIC;
+        request_mode(a.mm, i, SFM_CROSSING_ROAD, a.sim_time, cur);
+        a.mode[i] = cur;
+        atomicAdd(a.counters + 0, 1ull);
     }
 }
 

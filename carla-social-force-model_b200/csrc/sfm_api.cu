@@ -163,6 +163,7 @@ struct sfm_ctx {
     DevBuf<double4> cmp4; DevBuf<double2> cmp2; DevBuf<double3s> cmp3; DevBuf<double> cmp1; DevBuf<int> cmpi;
     DevBuf<uint8_t> cmpb;                          // scratch columns of sfm_despawn_finished
     DevBuf<int> check_list;                        // [0] count, [1..] rows waiting at the kerb this tick
+    DevBuf<uint8_t> check_blocked;
     std::vector<int> rt_begin;                     // host copy of the routes' first entries (cursor downloads are relative)
     // ---- peer-memory exchange (K7): mapped buffers of the other ranks, flag barrier, double-buffered gather buffer
     bool p2p = false;
@@ -898,7 +899,7 @@ int sfm_destroy(sfm_ctx* c) {
                 cudaIpcCloseMemHandle(c->peer_planes[r]); cudaIpcCloseMemHandle(c->peer_facc[r]);
                 cudaIpcCloseMemHandle(c->peer_flags[r]);
             }
-    c->flags.release(); c->check_list.release();
+    c->flags.release(); c->check_list.release(); c->check_blocked.release();
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->cmp4.release(); c->cmp2.release(); c->cmp3.release(); c->cmp1.release(); c->cmpi.release(); c->cmpb.release();
     c->mm_speed.release(); c->mm_initial.release(); c->mm_crossing.release(); c->mm_margin.release();
@@ -1326,15 +1327,18 @@ int sfm_tick_modes(sfm_ctx* c, double sim_time) {
     a.tr.ext0_x = c->tr_ext0[0]; a.tr.ext0_y = c->tr_ext0[1];
     a.sim_time = sim_time; a.counters = c->life_counters.p;
     SFM_TRY(c->check_list.ensure(c->n + 1));
-    a.check_list = c->check_list.p + 1; a.check_count = c->check_list.p;
+    SFM_TRY(c->check_blocked.ensure(c->n));
+    a.check_list = c->check_list.p + 1; a.check_count = c->check_list.p; a.blocked = c->check_blocked.p;
     SpanGuard g(c, ST_LIFECYCLE);
     SFM_CUDA(cudaMemsetAsync(a.check_count, 0, sizeof(int), c->stream));
+    SFM_CUDA(cudaMemsetAsync(a.blocked, 0, c->n, c->stream));
     k4_tick_modes<<<cdiv(c->n, K4_THREADS), K4_THREADS, 0, c->stream>>>(a);
     c->launches += 1;
     if (a.tr.count > 0) {
-        const int grid = (int)std::min<int64_t>(cdiv(c->n, K4_THREADS), 148 * 8);
-        k4_gap_acceptance<<<grid, K4_THREADS, 0, c->stream>>>(a);
-        c->launches += 1;
+        const int gx = (int)std::min<int64_t>(cdiv(c->n, K4_THREADS), 148 * 4);
+        k4_gap_acceptance<<<dim3(gx, cdiv(a.tr.count, K4_VEH_TILE)), K4_THREADS, 0, c->stream>>>(a);
+        k4_gap_commit<<<gx, K4_THREADS, 0, c->stream>>>(a);
+        c->launches += 2;
     }
     SFM_CUDA(cudaGetLastError());
     return 0;
