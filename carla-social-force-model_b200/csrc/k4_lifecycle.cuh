@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(K4_THREADS) k4_tick_modes(const ModeTickArgs a
 __global__ void __launch_bounds__(K4_THREADS) k4_gap_acceptance(const ModeTickArgs a) {
     __shared__ double2 s_center[K4_VEH_TILE], s_vel[K4_VEH_TILE], s_half[K4_VEH_TILE];
     __shared__ double s_speed[K4_VEH_TILE];
+    __shared__ float4 s_fb[K4_VEH_TILE];          // float32 copies for the dismissal test: (back.x, back.y, front.x, front.y)
+    __shared__ float2 s_uf[K4_VEH_TILE];          //                                         velocity
     const int count = *a.check_count;
     if ((int)(blockIdx.x * K4_THREADS) >= count) return;
     const int v0 = blockIdx.y * K4_VEH_TILE;
@@ -163,8 +165,11 @@ __global__ void __launch_bounds__(K4_THREADS) k4_gap_acceptance(const ModeTickAr
         const double dn = (vs == 0.0) ? 1.0 : vs;                                              // stateutils.py:88-90
         s_center[v] = c;
         s_vel[v] = u;
-        s_half[v] = make_double2(__dmul_rn(__ddiv_rn(u.x, dn), a.tr.ext0_x), __dmul_rn(__ddiv_rn(u.y, dn), a.tr.ext0_y));
+        const double2 h = make_double2(__dmul_rn(__ddiv_rn(u.x, dn), a.tr.ext0_x), __dmul_rn(__ddiv_rn(u.y, dn), a.tr.ext0_y));
+        s_half[v] = h;
         s_speed[v] = vs;
+        s_fb[v] = make_float4((float)(c.x - h.x), (float)(c.y - h.y), (float)(c.x + h.x), (float)(c.y + h.y));
+        s_uf[v] = make_float2((float)u.x, (float)u.y);
     }
     __syncthreads();
     for (int base = blockIdx.x * K4_THREADS; base < count; base += gridDim.x * K4_THREADS) {
@@ -181,7 +186,21 @@ __global__ void __launch_bounds__(K4_THREADS) k4_gap_acceptance(const ModeTickAr
         const double horizon = __dadd_rn(time_ped, margin);
         const double eps = 1.0e-9 * (1.0 + fabs(px) + fabs(py) + fabs(gx) + fabs(gy));
         const double x0 = fmin(px, gx) - eps, x1 = fmax(px, gx) + eps, y0 = fmin(py, gy) - eps, y1 = fmax(py, gy) + eps;
+        // the same box in float32, widened by far more than any float32 rounding of the quantities compared with it
+        // (1e-5 relative to the coordinates involved, 160 float32 ulps): a first, cheap dismissal on the FP32 pipe
+        const float hz = (float)horizon;
+        const float wide = 1.0e-5f * (1.0f + (float)(fabs(px) + fabs(py) + fabs(gx) + fabs(gy)) + fabsf(hz));
+        const float fx0 = (float)x0 - wide, fx1 = (float)x1 + wide, fy0 = (float)y0 - wide, fy1 = (float)y1 + wide;
         for (int v = 0; v < m; ++v) {
+            {
+                const float4 fb = s_fb[v];
+                const float2 uf = s_uf[v];
+                const float txf = fmaf(uf.x, hz, fb.z), tyf = fmaf(uf.y, hz, fb.w);
+                const float grow = 1.0e-5f * (fabsf(fb.x) + fabsf(fb.y) + fabsf(txf) + fabsf(tyf) + (fabsf(uf.x) + fabsf(uf.y)) * fabsf(hz));
+                if ((fmaxf(fb.x, txf) + grow < fx0) | (fminf(fb.x, txf) - grow > fx1) | (fmaxf(fb.y, tyf) + grow < fy0) |
+                    (fminf(fb.y, tyf) - grow > fy1))
+                    continue;
+            }
             const double2 c = s_center[v], u = s_vel[v], h = s_half[v];
             const double fx = __dadd_rn(c.x, h.x), fy = __dadd_rn(c.y, h.y);                 // front (:35)
             const double bx = __dsub_rn(c.x, h.x), by = __dsub_rn(c.y, h.y);                 // back  (:36)

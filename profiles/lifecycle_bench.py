@@ -40,7 +40,8 @@ def main():
     ctx = native.Context(0)
     ctx.set_params(native.params_from_config(cfg, w.step_length))
     mode = rng.choice([1, 2, 4], size=n, p=[0.7, 0.1, 0.2]).astype(np.uint8)        # 20 % waiting at the kerb
-    ctx.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, mode)
+    wp = w.loc + np.column_stack((rng.normal(0.0, 7.0, (n, 2)), np.zeros(n)))           # a road crossing: the far kerb ~10 m away
+    ctx.upload_state(w.loc, w.vel, wp, w.radius, w.target_speed, mode)
     ctx.set_mode_machines(w.target_speed, 1.5 * w.target_speed, rng.uniform(0.5, 2.5, n))
     ctx.set_vehicles(w.veh_center, w.veh_yaw, w.veh_vel, w.veh_extent, w.veh_resolution)
     v = len(w.veh_center)
