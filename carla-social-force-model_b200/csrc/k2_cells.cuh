@@ -239,6 +239,8 @@ struct SegArgs {
     double border_a, border_b;
     int use_radius;
     double2* f_out;                 // [n]
+    int n_groups;                   // ceil(n / 32) pedestrian groups
+    int* work_counter;              // persistent mode: next group to hand out (zeroed before the launch); null: one CTA per group
     long long* emit;                // optional [capacity][3]
     unsigned long long* emit_count;
     long long emit_capacity;
@@ -374,8 +376,20 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
     __shared__ __align__(16) float2 sp[K2_WARPS][K2_CHUNK];
     __shared__ __align__(16) float4 sc[K2_WARPS][2 * K2_PRUNE_MAX];
     __shared__ double2 part[K2_WARPS][32];
+    __shared__ int s_group;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int slot = blockIdx.x * 32 + lane;
+    // Persistent mode (work_counter != null): the grid is a few CTAs per SM that pull pedestrian groups from a counter, so
+    // the kernel occupies a fixed share of every SM and the pair kernel runs beside it for its whole duration.
+    for (bool first = true;; first = false) {
+    if (a.work_counter) {
+        if (tid == 0) s_group = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+    } else if (!first) {
+        break;
+    }
+    const int group = a.work_counter ? s_group : (int)blockIdx.x;
+    if (group >= a.n_groups) break;
+    const int slot = group * 32 + lane;
     const bool active = slot < a.n;
     const int i = active ? a.perm[slot] : -1;
     double px = 0.0, py = 0.0, radius = 0.0, vx = 0.0, vy = 0.0;
@@ -556,6 +570,8 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
             if (md == SFM_CROSSING_ROAD || md == SFM_ROAD_TO_SIDEWALK) { sx = __dmul_rn(sx, 0.0); sy = __dmul_rn(sy, 0.0); }
         }
         a.f_out[i] = make_double2(sx, sy);
+    }
+    __syncthreads();                     // part[] and s_group are reused by the next group
     }
 }
 

@@ -134,6 +134,10 @@ struct sfm_ctx {
     std::vector<cudaEvent_t> event_pool;
     int k1_target_ctas = 148 * 4 * 16;
     bool k1_first = false;
+    int k2_persist = 2;             // SFM_K2_PERSIST: CTAs per SM of the persistent cell-list kernels beside the pair kernel (0: one CTA
+                                    // per group); profiles/k2_persist_sweep_r1.log: 4.54 -> 4.48 ms per tick, 4.71 -> 4.56 ms through host buffers
+    int sm_count = 148;
+    DevBuf<int> k2_counter;
     bool k2_prune = true;           // SFM_K2_PRUNE=0: cell-list kernels scan every point of an item (no chunk bounds)
     int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
                                     // cell-list kernels stay co-resident on every SM (see step_begin)
@@ -680,7 +684,8 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
     return 0;
 }
 
-int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaStream_t strm = nullptr) {
+int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaStream_t strm = nullptr,
+                    bool persistent = false) {
     if (!strm) strm = c->stream;
     SetStorage& st = (cls == SFM_FORCE_BORDER) ? c->borders : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->stat : c->dyn);
     DevBuf<double2>& out = (cls == SFM_FORCE_BORDER) ? c->f_border
@@ -707,9 +712,18 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
     if (emit) {
         a.emit = c->emit.p; a.emit_count = c->emit_count.p; a.emit_capacity = emit_capacity;
     }
+    a.n_groups = cdiv(n, 32);
+    int grid = a.n_groups;
     SpanGuard g(c, ST_SEGMENTS, strm);
-    if (cls == SFM_FORCE_BORDER) k2_segments<0><<<cdiv(n, 32), K2_THREADS, 0, strm>>>(a);
-    else k2_segments<1><<<cdiv(n, 32), K2_THREADS, 0, strm>>>(a);
+    if (persistent && c->k2_persist > 0 && a.n_groups > c->k2_persist * c->sm_count) {
+        // beside the pair kernel: k2_persist CTAs per SM pulling groups from a counter (see k2_cells.cuh)
+        SFM_TRY(c->k2_counter.ensure(4));
+        a.work_counter = c->k2_counter.p + (cls - SFM_FORCE_BORDER);
+        SFM_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), strm));
+        grid = c->k2_persist * c->sm_count;
+    }
+    if (cls == SFM_FORCE_BORDER) k2_segments<0><<<grid, K2_THREADS, 0, strm>>>(a);
+    else k2_segments<1><<<grid, K2_THREADS, 0, strm>>>(a);
     c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     return 0;
@@ -746,11 +760,12 @@ int step_begin(sfm_ctx* c) {
     };
     if (forked && c->k1_first) SFM_TRY(pairs());
     if (any_set && !c->perm_valid) SFM_TRY(rebin_peds(c, st2));
-    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0, st2));
+    if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count)
+        SFM_TRY(launch_segments(c, SFM_FORCE_BORDER, false, 0, st2, forked));
     if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count)
-        SFM_TRY(launch_segments(c, SFM_FORCE_STATIC_OBSTACLE, false, 0, st2));
+        SFM_TRY(launch_segments(c, SFM_FORCE_STATIC_OBSTACLE, false, 0, st2, forked));
     if (P.enable[SFM_FORCE_DYNAMIC_OBSTACLE] && c->dyn.s.count)
-        SFM_TRY(launch_segments(c, SFM_FORCE_DYNAMIC_OBSTACLE, false, 0, st2));
+        SFM_TRY(launch_segments(c, SFM_FORCE_DYNAMIC_OBSTACLE, false, 0, st2, forked));
     if (forked) SFM_CUDA(cudaEventRecord(c->ev_join, st2));
     if (!(forked && c->k1_first)) SFM_TRY(pairs());
     c->step_open = true;
@@ -869,6 +884,8 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_K1_FIRST")) c->k1_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PRUNE")) c->k2_prune = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_GRAPH")) c->use_graph = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SFM_K2_PERSIST")) c->k2_persist = std::max(0, std::atoi(env));
+    c->sm_count = prop.multiProcessorCount;
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -899,7 +916,7 @@ int sfm_destroy(sfm_ctx* c) {
                 cudaIpcCloseMemHandle(c->peer_planes[r]); cudaIpcCloseMemHandle(c->peer_facc[r]);
                 cudaIpcCloseMemHandle(c->peer_flags[r]);
             }
-    c->flags.release(); c->check_list.release(); c->check_blocked.release();
+    c->flags.release(); c->check_list.release(); c->check_blocked.release(); c->k2_counter.release();
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->cmp4.release(); c->cmp2.release(); c->cmp3.release(); c->cmp1.release(); c->cmpi.release(); c->cmpb.release();
     c->mm_speed.release(); c->mm_initial.release(); c->mm_crossing.release(); c->mm_margin.release();
