@@ -137,6 +137,7 @@ struct sfm_ctx {
     int k2_persist = 2;             // SFM_K2_PERSIST: CTAs per SM of the persistent cell-list kernels beside the pair kernel (0: one CTA
                                     // per group); profiles/k2_persist_sweep_r1.log: 4.54 -> 4.48 ms per tick, 4.71 -> 4.56 ms through host buffers
     int sm_count = 148;
+    bool k2_persist_multi = false;  // SFM_K2_PERSIST_MULTI=1: persistent mode on multi-rank contexts too
     DevBuf<int> k2_counter;
     bool k2_prune = true;           // SFM_K2_PRUNE=0: cell-list kernels scan every point of an item (no chunk bounds)
     int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
@@ -715,7 +716,9 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
     a.n_groups = cdiv(n, 32);
     int grid = a.n_groups;
     SpanGuard g(c, ST_SEGMENTS, strm);
-    if (persistent && c->k2_persist > 0 && a.n_groups > c->k2_persist * c->sm_count) {
+    // (single-rank ticks only: on 2 GPUs the persistent mode shortens the device-timed tick 4.43 -> 4.31 ms but lengthens
+    //  the host-buffer tick 4.77 -> 5.50 ms -- measured, not yet understood -- so multi-rank contexts keep one CTA per group)
+    if (persistent && c->k2_persist > 0 && (c->world == 1 || c->k2_persist_multi) && a.n_groups > c->k2_persist * c->sm_count) {
         // beside the pair kernel: k2_persist CTAs per SM pulling groups from a counter (see k2_cells.cuh)
         SFM_TRY(c->k2_counter.ensure(4));
         a.work_counter = c->k2_counter.p + (cls - SFM_FORCE_BORDER);
@@ -885,6 +888,7 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_K2_PRUNE")) c->k2_prune = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_GRAPH")) c->use_graph = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PERSIST")) c->k2_persist = std::max(0, std::atoi(env));
+    if (const char* env = std::getenv("SFM_K2_PERSIST_MULTI")) c->k2_persist_multi = std::atoi(env) != 0;
     c->sm_count = prop.multiProcessorCount;
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
