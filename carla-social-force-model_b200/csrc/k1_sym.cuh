@@ -389,8 +389,9 @@ __global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const Sy
     }
 }
 
-// Fixed-point accumulators -> float64 pair force of the local rows; poisoned rows are recomputed by their warp with the
-// guarded scalar code (numpy's zero-safe semantics), lanes striding over every staged slot.
+// Fixed-point accumulators -> float64 pair force of the local rows.  Rows whose poison counter is set (a degenerate or
+// overflowing pair met the unguarded fast path) are appended to a list; k1_sym_repair recomputes exactly those rows with
+// the guarded scalar code (numpy's zero-safe semantics), one CTA per row striding over every staged slot.
 struct FinishArgs {
     const float* planes;
     int rows_pad, world, own_block, n_local;
@@ -399,70 +400,72 @@ struct FinishArgs {
     int n_peer;                     //     the reduce-scatter is the sum below
     double* f_ped;                  // [n_local][3]
     unsigned long long* fixup_rows;
+    int* bad_list;                  // [n_local] rows to repair
+    int* bad_count;                 // [1], zeroed before the launch
     PairParams pp;
 };
 
-template <bool RADIUS>
 __global__ void __launch_bounds__(256) k1_sym_finish(const FinishArgs a) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool live = row < a.n_local;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    bool bad = false;
-    if (live) {
-        const longlong4 own = *reinterpret_cast<const longlong4*>(a.facc_own + (size_t)row * 4);
-        long long fx = own.x, fy = own.y, fz = own.z, poison = own.w;
-        for (int r = 0; r < a.n_peer; ++r) {            // integer sums: associative, so any order gives the same bits
-            const longlong4 o = *reinterpret_cast<const longlong4*>(a.facc_peer[r] + (size_t)row * 4);
-            fx += o.x; fy += o.y; fz += o.z; poison += o.w;
-        }
-        const double inv = 1.0 / 4294967296.0;
-        sx = (double)fx * inv;
-        sy = (double)fy * inv;
-        sz = (double)fz * inv;
-        bad = poison != 0;
+    if (row >= a.n_local) return;
+    const longlong4 own = *reinterpret_cast<const longlong4*>(a.facc_own + (size_t)row * 4);
+    long long fx = own.x, fy = own.y, fz = own.z, poison = own.w;
+    for (int r = 0; r < a.n_peer; ++r) {            // integer sums: associative, so any order gives the same bits
+        const longlong4 o = *reinterpret_cast<const longlong4*>(a.facc_peer[r] + (size_t)row * 4);
+        fx += o.x; fy += o.y; fz += o.z; poison += o.w;
     }
-    unsigned mask = __ballot_sync(0xffffffffu, bad);
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int r = __shfl_sync(0xffffffffu, row, src);
+    const double inv = 1.0 / 4294967296.0;
+    a.f_ped[3 * (size_t)row + 0] = (double)fx * inv;
+    a.f_ped[3 * (size_t)row + 1] = (double)fy * inv;
+    a.f_ped[3 * (size_t)row + 2] = (double)fz * inv;
+    if (poison != 0) a.bad_list[atomicAdd(a.bad_count, 1)] = row;       // list order is irrelevant: rows are independent
+}
+
+constexpr int KS_REPAIR_THREADS = 256;
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(KS_REPAIR_THREADS) k1_sym_repair(const FinishArgs a) {
+    __shared__ double red[3][KS_REPAIR_THREADS];
+    const int count = *a.bad_count;
+    const int tid = threadIdx.x;
+    const int total = a.world * a.rows_pad;
+    for (int b = blockIdx.x; b < count; b += gridDim.x) {
+        const int r = a.bad_list[b];
         const float* own = a.planes + ((size_t)a.own_block * NPLANES) * a.rows_pad;
         const float xi = own[(size_t)PX * a.rows_pad + r], yi = own[(size_t)PY * a.rows_pad + r];
         const float zi = own[(size_t)PZ * a.rows_pad + r], ri = own[(size_t)PR * a.rows_pad + r];
         const float vxi = own[(size_t)PVX * a.rows_pad + r], vyi = own[(size_t)PVY * a.rows_pad + r];
         const float vzi = own[(size_t)PVZ * a.rows_pad + r];
         const int islot = a.own_block * a.rows_pad + r;
-        const int total = a.world * a.rows_pad;
         double gx = 0.0, gy = 0.0, gz = 0.0;
-        for (int j = lane; j < total; j += 32) {
+        for (int j = tid; j < total; j += KS_REPAIR_THREADS) {
             const int q = j / a.rows_pad;
-            const float* b = a.planes + ((size_t)q * NPLANES) * a.rows_pad + (j - q * a.rows_pad);
+            const float* p = a.planes + ((size_t)q * NPLANES) * a.rows_pad + (j - q * a.rows_pad);
             PairAcc acc = {0.0f, 0.0f, 0.0f};
-            pair_force<RADIUS, true>(xi, yi, zi, ri, vxi, vyi, vzi, b[(size_t)PX * a.rows_pad], b[(size_t)PY * a.rows_pad],
-                                     b[(size_t)PZ * a.rows_pad], b[(size_t)PR * a.rows_pad], b[(size_t)PVX * a.rows_pad],
-                                     b[(size_t)PVY * a.rows_pad], b[(size_t)PVZ * a.rows_pad], j == islot, a.pp, acc);
+            pair_force<RADIUS, true>(xi, yi, zi, ri, vxi, vyi, vzi, p[(size_t)PX * a.rows_pad], p[(size_t)PY * a.rows_pad],
+                                     p[(size_t)PZ * a.rows_pad], p[(size_t)PR * a.rows_pad], p[(size_t)PVX * a.rows_pad],
+                                     p[(size_t)PVY * a.rows_pad], p[(size_t)PVZ * a.rows_pad], j == islot, a.pp, acc);
             gx += (double)acc.gx;
             gy += (double)acc.gy;
             gz += (double)acc.gz;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            gx += __shfl_xor_sync(0xffffffffu, gx, o);
-            gy += __shfl_xor_sync(0xffffffffu, gy, o);
-            gz += __shfl_xor_sync(0xffffffffu, gz, o);
+        red[0][tid] = gx; red[1][tid] = gy; red[2][tid] = gz;
+        __syncthreads();
+        for (int o = KS_REPAIR_THREADS / 2; o > 0; o >>= 1) {        // fixed tree: deterministic
+            if (tid < o) {
+                red[0][tid] += red[0][tid + o];
+                red[1][tid] += red[1][tid + o];
+                red[2][tid] += red[2][tid + o];
+            }
+            __syncthreads();
         }
-        if (lane == src) {
-            sx = -gx;
-            sy = -gy;
-            sz = -gz;
+        if (tid == 0) {
+            a.f_ped[3 * (size_t)r + 0] = -red[0][0];
+            a.f_ped[3 * (size_t)r + 1] = -red[1][0];
+            a.f_ped[3 * (size_t)r + 2] = -red[2][0];
             atomicAdd(a.fixup_rows, 1ull);
         }
-    }
-    if (live) {
-        a.f_ped[3 * (size_t)row + 0] = sx;
-        a.f_ped[3 * (size_t)row + 1] = sy;
-        a.f_ped[3 * (size_t)row + 2] = sz;
+        __syncthreads();
     }
 }
 

@@ -167,6 +167,7 @@ struct sfm_ctx {
     std::vector<double> rec_times;
     DevBuf<double4> cmp4; DevBuf<double2> cmp2; DevBuf<double3s> cmp3; DevBuf<double> cmp1; DevBuf<int> cmpi;
     DevBuf<uint8_t> cmpb;                          // scratch columns of sfm_despawn_finished
+    DevBuf<int> bad_rows;                          // [0] count, [1..] rows the pair-force repair kernel recomputes
     DevBuf<int> check_list;                        // [0] count, [1..] rows waiting at the kerb this tick
     DevBuf<uint8_t> check_blocked;
     std::vector<int> rt_begin;                     // host copy of the routes' first entries (cursor downloads are relative)
@@ -491,10 +492,15 @@ int launch_pairs_finish(sfm_ctx* c) {
         for (int r = 0; r < c->world; ++r)
             if (r != c->rank)
                 f.facc_peer[f.n_peer++] = reinterpret_cast<const long long*>(c->peer_facc[r]) + (size_t)c->rank * c->rows_pad * 4;
+    SFM_TRY(c->bad_rows.ensure(c->n + 1));
+    f.bad_count = c->bad_rows.p; f.bad_list = c->bad_rows.p + 1;
     SpanGuard g(c, ST_PAIRS);
-    if (c->params.use_ped_radius) k1_sym_finish<true><<<cdiv(c->n, 256), 256, 0, c->stream>>>(f);
-    else k1_sym_finish<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(f);
-    c->launches += 1;
+    SFM_CUDA(cudaMemsetAsync(f.bad_count, 0, sizeof(int), c->stream));
+    k1_sym_finish<<<cdiv(c->n, 256), 256, 0, c->stream>>>(f);
+    const int repair_grid = (int)std::min<int64_t>(c->n, (int64_t)c->sm_count * 8);
+    if (c->params.use_ped_radius) k1_sym_repair<true><<<repair_grid, KS_REPAIR_THREADS, 0, c->stream>>>(f);
+    else k1_sym_repair<false><<<repair_grid, KS_REPAIR_THREADS, 0, c->stream>>>(f);
+    c->launches += 2;
     SFM_CUDA(cudaGetLastError());
     c->pairs_pending = false;
     return 0;
@@ -920,7 +926,7 @@ int sfm_destroy(sfm_ctx* c) {
                 cudaIpcCloseMemHandle(c->peer_planes[r]); cudaIpcCloseMemHandle(c->peer_facc[r]);
                 cudaIpcCloseMemHandle(c->peer_flags[r]);
             }
-    c->flags.release(); c->check_list.release(); c->check_blocked.release(); c->k2_counter.release();
+    c->flags.release(); c->bad_rows.release(); c->check_list.release(); c->check_blocked.release(); c->k2_counter.release();
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->cmp4.release(); c->cmp2.release(); c->cmp3.release(); c->cmp1.release(); c->cmpi.release(); c->cmpb.release();
     c->mm_speed.release(); c->mm_initial.release(); c->mm_crossing.release(); c->mm_margin.release();
