@@ -119,6 +119,30 @@ class Engine:
             self._bind_gather()
             self.exchange()
 
+    def load_lifecycle(self, w, life):
+        """Mode machines and routes of this rank's rows on the device; ``tick`` then runs the whole
+        SimulationRunner.tick sequence per call.  ``life`` is a ``synth.Lifecycle`` (or anything with its attributes)."""
+        lo, hi = self.lo, self.hi
+        idle = np.asarray(life.idle[lo:hi], dtype=bool)
+        speed = w.target_speed[lo:hi]
+        self.ctx.update_targets(mode=np.where(idle, 0, w.mode[lo:hi]).astype(np.uint8))
+        self.ctx.set_mode_machines(speed, np.asarray(life.crossing_speed_factor[lo:hi]) * speed,
+                                   life.crossing_safety_margin[lo:hi], np.where(idle, 0.0, speed),
+                                   np.where(idle, 5.0, -1.0), 5.0)
+        self.ctx.set_routes(life.routes[lo:hi], life.waypoint_threshold, fused=True)
+        self._ticks = 0
+
+    def tick(self, vehicles=None):
+        """One headless SimulationRunner.tick: vehicles (the host 6-tuple, replicated on every rank, or the device-resident
+        set advancing itself) -> mode machines + gap acceptance -> forces, velocities, hand-overs, positions."""
+        sim_time = self._ticks * self.step_length
+        if vehicles is not None:
+            self.ctx.set_obstacles(native.DYNAMIC_OBSTACLE, vehicles[1], vehicles[5], vehicles[3])
+            self.ctx.set_traffic(vehicles[1], vehicles[3], vehicles[4])
+        self.ctx.tick_modes(sim_time)
+        self.step(1, True)
+        self._ticks += 1
+
     def set_vehicles(self, dyn_tuple):
         """The 6-tuple of pedestrian_simulation.py:108-115 (ids, centres, headings, velocities, extents, rings)."""
         if dyn_tuple is not None:

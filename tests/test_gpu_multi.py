@@ -63,3 +63,47 @@ def test_two_gpu_engine_matches_single_gpu(tmp_path, sfm_config, n, exchange):
     else:
         np.testing.assert_allclose(loc_p, loc_w, rtol=0, atol=1e-6)
         np.testing.assert_allclose(vel_p, vel_w, rtol=0, atol=2e-5)
+
+
+def _lifecycle_rank(rank, world, port, out_dir):
+    import sys
+    import tomllib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, 'carla-social-force-model_b200')
+    sys.path[:0] = [root, pkg]
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), NCCL_DEBUG='WARN')
+    torch.cuda.set_device(rank)
+    torch.distributed.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from sfm_b200 import engine, synth
+    with open(os.path.join(pkg, 'config', 'sfm_config.toml'), 'rb') as f:
+        cfg = tomllib.load(f)
+    w, life = synth.make_lifecycle()
+    g = np.load(os.path.join(root, 'tests', 'golden', 'lifecycle.npz'))
+    e = engine.Engine(cfg, w.step_length, device=rank)
+    e.load(w)
+    e.load_lifecycle(w, life)
+    for k in range(60):
+        e.tick(w.vehicles_at(k))
+        modes = e.ctx.download_mode_codes()
+        _, _, wp = e.ctx.download_routes()
+        assert np.array_equal(modes, g['mode'][k + 1][e.lo:e.hi]), f'rank {rank}: modes differ after tick {k}'
+        assert np.array_equal(wp, g['wp'][k + 1][e.lo:e.hi]), f'rank {rank}: waypoints differ after tick {k}'
+    e.synchronize()
+    loc, _ = e.local_state()
+    assert np.abs(loc - g['loc'][60][e.lo:e.hi]).max() < 1e-2
+    with open(os.path.join(out_dir, f'ok{rank}'), 'w') as f:
+        f.write('ok')
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_two_gpu_lifecycle_matches_reference_golden(tmp_path):
+    """Mode machines, gap acceptance and waypoint hand-over with the crowd split over two ranks (peer-memory exchange):
+    every rank's rows reproduce the reference's modes and waypoints tick by tick."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_lifecycle_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / 'ok0').exists() and (tmp_path / 'ok1').exists()
