@@ -55,6 +55,21 @@ struct DevBuf {
         g_alloc_epoch += 1;
         return 0;
     }
+    // like ensure(), but the first `keep` elements survive a reallocation (device-to-device copy on `stream`)
+    int grow_keep(size_t n, size_t keep, cudaStream_t stream) {
+        if (n <= cap) return 0;
+        T* old = p;
+        size_t want = n + n / 4 + 256;
+        T* fresh = nullptr;
+        SFM_CUDA(cudaMalloc(&fresh, want * sizeof(T)));
+        if (old && keep) SFM_CUDA(cudaMemcpyAsync(fresh, old, keep * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        SFM_CUDA(cudaStreamSynchronize(stream));
+        if (old) SFM_CUDA(cudaFree(old));
+        p = fresh;
+        cap = want;
+        g_alloc_epoch += 1;
+        return 0;
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -170,6 +185,7 @@ struct sfm_ctx {
     DevBuf<int> bad_rows;                          // [0] count, [1..] rows the pair-force repair kernel recomputes
     DevBuf<int> check_list;                        // [0] count, [1..] rows waiting at the kerb this tick
     DevBuf<uint8_t> check_blocked;
+    int64_t rt_total = 0;                          // waypoints stored in rt_wp / rt_cross
     std::vector<int> rt_begin;                     // host copy of the routes' first entries (cursor downloads are relative)
     // ---- peer-memory exchange (K7): mapped buffers of the other ranks, flag barrier, double-buffered gather buffer
     bool p2p = false;
@@ -1413,6 +1429,7 @@ int sfm_set_routes(sfm_ctx* c, int64_t n, const int64_t* offsets, const double* 
     SFM_CUDA(cudaStreamSynchronize(c->stream));
     SFM_CUDA(cudaMemcpy(c->rt_cursor.p, cursor.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     c->rt_begin = cursor;
+    c->rt_total = total;
     SFM_CUDA(cudaMemcpy(c->rt_end.p, end.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     SFM_CUDA(cudaMemset(c->finished.p, 0, n));
     if (total > 0) {
@@ -1453,6 +1470,84 @@ int sfm_download_routes(sfm_ctx* c, int64_t n, int64_t* cursor, uint8_t* finishe
     return 0;
 }
 
+
+int sfm_append_pedestrians(sfm_ctx* c, int64_t m, const double* loc, const double* vel, const double* wp3,
+                           const double* radius, const double* speed, const uint8_t* mode, const double* initial_speed,
+                           const double* crossing_speed, const double* safety_margin, const double* mode_speed,
+                           const double* next_mode_time, const int64_t* route_offsets, const double* waypoints,
+                           const uint8_t* crossing) {
+    SFM_TRY(check_ctx(c));
+    c->config_epoch += 1;
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (c->world > 1) return fail("spawning changes the row partition: single-rank contexts only");
+    if (c->step_open) return fail("spawn between sfm_step_begin and sfm_step_end");
+    if (m < 0) return fail("negative row count");
+    if (m == 0) return 0;
+    if (!loc || !vel || !wp3 || !radius || !speed || !mode) return fail("null state array");
+    if (c->have_mm && (!initial_speed || !crossing_speed || !safety_margin || !mode_speed || !next_mode_time))
+        return fail("this context carries mode machines: the new pedestrians need theirs");
+    if (c->have_routes && !route_offsets) return fail("this context carries routes: the new pedestrians need theirs");
+    const int64_t n0 = c->n, n1 = c->n + m;
+    if (n1 > (int64_t)1 << 28) return fail("bad row count");
+    cudaStream_t st = c->stream;
+    // per-row tables grow in place (contents of the first n0 rows kept)
+    SFM_TRY(c->locr.grow_keep(n1, n0, st)); SFM_TRY(c->vels.grow_keep(n1, n0, st)); SFM_TRY(c->wp.grow_keep(n1, n0, st));
+    SFM_TRY(c->mode.grow_keep(n1, n0, st)); SFM_TRY(c->next_wp3.grow_keep(3 * n1, 3 * n0, st));
+    SFM_TRY(c->raw_a.ensure(3 * n1)); SFM_TRY(c->raw_b.ensure(3 * n1)); SFM_TRY(c->raw_c.ensure(3 * n1));
+    SFM_TRY(c->raw_d.ensure(n1)); SFM_TRY(c->raw_e.ensure(n1)); SFM_TRY(c->raw_mode.ensure(n1));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_a.p, loc, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, st));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_b.p, vel, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, st));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_c.p, wp3, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, st));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_d.p, radius, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_e.p, speed, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    SFM_CUDA(cudaMemcpyAsync(c->raw_mode.p, mode, m, cudaMemcpyHostToDevice, st));
+    pack_state<<<cdiv(m, 256), 256, 0, st>>>(m, c->raw_a.p, c->raw_b.p, c->raw_c.p, c->raw_d.p, c->raw_e.p, c->raw_mode.p,
+                                              c->locr.p + n0, c->vels.p + n0, c->wp.p + n0, c->mode.p + n0);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    SFM_CUDA(cudaMemcpyAsync(c->next_wp3.p + 3 * n0, c->raw_c.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToDevice, st));
+    if (c->have_mm) {
+        DevBuf<double>* cols[5] = {&c->mm_initial, &c->mm_crossing, &c->mm_margin, &c->mm_speed, &c->mm_next_time};
+        const double* src[5] = {initial_speed, crossing_speed, safety_margin, mode_speed, next_mode_time};
+        for (int k = 0; k < 5; ++k) {
+            SFM_TRY(cols[k]->grow_keep(n1, n0, st));
+            SFM_CUDA(cudaMemcpyAsync(cols[k]->p + n0, src[k], sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (c->have_routes) {
+        const int64_t add = route_offsets[m] - route_offsets[0];
+        if (add < 0 || c->rt_total + add > (int64_t)INT32_MAX) return fail("bad route table");
+        if (add > 0 && (!waypoints || !crossing)) return fail("null waypoint array");
+        std::vector<int> cursor(m), end(m);
+        for (int64_t i = 0; i < m; ++i) {
+            if (route_offsets[i + 1] < route_offsets[i]) return fail("route offsets must be non-decreasing");
+            cursor[i] = (int)(c->rt_total + route_offsets[i] - route_offsets[0]);
+            end[i] = (int)(c->rt_total + route_offsets[i + 1] - route_offsets[0]);
+        }
+        SFM_TRY(c->rt_cursor.grow_keep(n1, n0, st)); SFM_TRY(c->rt_end.grow_keep(n1, n0, st));
+        SFM_TRY(c->finished.grow_keep(n1, n0, st));
+        SFM_TRY(c->rt_wp.grow_keep(3 * std::max<int64_t>(c->rt_total + add, 1), 3 * c->rt_total, st));
+        SFM_TRY(c->rt_cross.grow_keep(std::max<int64_t>(c->rt_total + add, 1), c->rt_total, st));
+        SFM_CUDA(cudaStreamSynchronize(st));
+        SFM_CUDA(cudaMemcpy(c->rt_cursor.p + n0, cursor.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+        SFM_CUDA(cudaMemcpy(c->rt_end.p + n0, end.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+        SFM_CUDA(cudaMemset(c->finished.p + n0, 0, m));
+        if (add > 0) {
+            SFM_CUDA(cudaMemcpy(c->rt_wp.p + 3 * c->rt_total, waypoints + 3 * route_offsets[0], sizeof(double) * 3 * add,
+                                cudaMemcpyHostToDevice));
+            SFM_CUDA(cudaMemcpy(c->rt_cross.p + c->rt_total, crossing + route_offsets[0], add, cudaMemcpyHostToDevice));
+        }
+        c->rt_begin.insert(c->rt_begin.end(), cursor.begin(), cursor.end());
+        c->rt_total += add;
+    }
+    c->n = n1;
+    SFM_TRY(ensure_layout(c, n1));               // the staging planes may have to grow: every slot is restaged
+    c->staged = false;
+    c->perm_valid = false;
+    c->rec_capacity = 0;
+    SFM_CUDA(cudaStreamSynchronize(st));         // host arrays may be released by the caller on return
+    return 0;
+}
 
 int sfm_despawn_finished(sfm_ctx* c, int64_t* n_after, int64_t* n_removed) {
     SFM_TRY(check_ctx(c));

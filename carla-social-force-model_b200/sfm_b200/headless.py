@@ -30,6 +30,18 @@ class HeadlessRunner:
         self.ctx = ctx or native.Context(device)
         c = self.ctx
         c.set_params(native.params_from_config(sfm_config, w.step_length))
+        spawn_tick = getattr(life, 'spawn_tick', None)
+        self.spawn_tick = np.zeros(w.n, dtype=np.int64) if spawn_tick is None else np.asarray(spawn_tick)
+        first = np.nonzero(self.spawn_tick == 0)[0]
+        if len(first) < w.n:                               # late spawners join through sfm_append_pedestrians
+            import copy
+            full, w = w, copy.copy(w)
+            for name in ('loc', 'vel', 'next_waypoint', 'radius', 'target_speed', 'mode'):
+                setattr(w, name, getattr(full, name)[first])
+            life = copy.copy(life)
+            life.routes = [self.life.routes[i] for i in first]
+            for name in ('crossing_speed_factor', 'crossing_safety_margin', 'idle'):
+                setattr(life, name, np.asarray(getattr(self.life, name))[first])
         c.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
         if len(w.borders):
             c.set_borders(w.borders, w.section_center, w.section_length)
@@ -49,14 +61,30 @@ class HeadlessRunner:
         if self.has_vehicles and device_vehicles:
             c.set_vehicles(w.veh_center, w.veh_yaw, w.veh_vel, w.veh_extent, w.veh_resolution)
         self.step_index = 0
-        self.ids = np.arange(w.n)                          # original row of every pedestrian still in the crowd
+        self.ids = first.copy()                            # original row of every pedestrian in the crowd
         self._finished_seen = 0
         self.record_every = record_every
         if record_every:
             c.record_begin(record_capacity)
 
+    def _spawn(self, rows):
+        """PedSpawner.tick -> PedestrianSimulation.spawn_pedestrian (pedestrian_spawner.py:238-241), batched."""
+        w, life = self.w, self.life
+        speed = w.target_speed[rows]
+        idle = np.asarray(life.idle)[rows]
+        machines = (speed, np.asarray(life.crossing_speed_factor)[rows] * speed, np.asarray(life.crossing_safety_margin)[rows],
+                    np.where(idle, 0.0, speed), np.where(idle, self.step_index * self.dt + 5.0, -1.0))
+        self.ctx.append_pedestrians(w.loc[rows], w.vel[rows], w.next_waypoint[rows], w.radius[rows], speed,
+                                    np.where(idle, IDLE, w.mode[rows]).astype(np.uint8), machines,
+                                    [life.routes[i] for i in rows])
+        self.ids = np.concatenate((self.ids, rows))
+
     def tick(self):
         c, k = self.ctx, self.step_index
+        if k > 0:
+            late = np.nonzero(self.spawn_tick == k)[0]
+            if len(late):
+                self._spawn(late)
         if self.has_vehicles:
             if self.device_vehicles:
                 if k > 0:

@@ -29,7 +29,7 @@ SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create'
            'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats',
            # lifecycle
            'sfm_set_mode_machines', 'sfm_set_traffic', 'sfm_tick_modes', 'sfm_download_modes', 'sfm_set_routes',
-           'sfm_advance_waypoints', 'sfm_download_routes', 'sfm_despawn_finished', 'sfm_lifecycle_counters', 'sfm_set_vehicles',
+           'sfm_advance_waypoints', 'sfm_download_routes', 'sfm_append_pedestrians', 'sfm_despawn_finished', 'sfm_lifecycle_counters', 'sfm_set_vehicles',
            'sfm_advance_vehicles', 'sfm_download_vehicles', 'sfm_record_begin', 'sfm_record_frame',
            'sfm_download_frames',
            # peer-memory exchange (K7)
@@ -132,6 +132,7 @@ def lib():
         'sfm_set_routes': (C.c_int, [p_ctx, i64, p_i64, p_d, p_u8, C.c_double, C.c_int]),
         'sfm_advance_waypoints': (C.c_int, [p_ctx]),
         'sfm_download_routes': (C.c_int, [p_ctx, i64, p_i64, p_u8, p_d]),
+        'sfm_append_pedestrians': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d, p_d, p_u8, p_d, p_d, p_d, p_d, p_d, p_i64, p_d, p_u8]),
         'sfm_despawn_finished': (C.c_int, [p_ctx, p_i64, p_i64]),
         'sfm_lifecycle_counters': (C.c_int, [p_ctx, p_i64]),
         'sfm_set_vehicles': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d, C.c_double, C.c_double]),
@@ -451,6 +452,32 @@ class Context:
         cursor, finished, wp = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.uint8), np.empty((n, 3))
         _check(self._lib.sfm_download_routes(self._h, n, _ptr(cursor, C.c_int64), _ptr(finished, C.c_uint8), _ptr(wp)))
         return cursor, finished.astype(bool), wp
+
+    def append_pedestrians(self, loc, vel, next_waypoint, radius, target_speed, mode, machines=None, routes=None):
+        """Spawn ``m`` pedestrians at the end of the table.  ``machines`` = (initial_target_speed, crossing_speed,
+        crossing_safety_margin, mode_target_speed, next_mode_time) columns; ``routes`` = per pedestrian a list of
+        (waypoint(3), crossing_road) tuples -- both required when the context carries them."""
+        m = len(loc)
+        loc, vel, wp = _f64(loc, (m, 3)), _f64(vel, (m, 3)), _f64(next_waypoint, (m, 3))
+        radius, speed = _f64(radius, (m,)), _f64(target_speed, (m,))
+        mode = np.ascontiguousarray(mode, dtype=np.uint8)
+        mach = [None] * 5 if machines is None else [_f64(a, (m,)) for a in machines]
+        offsets = wps = cross = None
+        if routes is not None:
+            sizes = np.fromiter((len(r) for r in routes), dtype=np.int64, count=m)
+            offsets = np.zeros(m + 1, dtype=np.int64)
+            np.cumsum(sizes, out=offsets[1:])
+            wps = np.zeros((max(int(offsets[-1]), 1), 3))
+            cross = np.zeros(max(int(offsets[-1]), 1), dtype=np.uint8)
+            k = 0
+            for r in routes:
+                for w, crossing in r:
+                    wps[k], cross[k] = w, bool(crossing)
+                    k += 1
+        _check(self._lib.sfm_append_pedestrians(self._h, m, _ptr(loc), _ptr(vel), _ptr(wp), _ptr(radius), _ptr(speed),
+                                                _ptr(mode, C.c_uint8), *[_ptr(a) for a in mach],
+                                                _ptr(offsets, C.c_int64), _ptr(wps), _ptr(cross, C.c_uint8)))
+        self.n += m
 
     def despawn_finished(self):
         """Remove the pedestrians that arrived with no waypoint left; returns how many were removed."""

@@ -188,9 +188,10 @@ class Lifecycle:
     idle: np.ndarray                  # bool
     waypoint_threshold: float = 2.0
     despawn_on_arrival: bool = False
+    spawn_tick: np.ndarray = None     # tick at whose start each pedestrian is spawned (None / 0: present from the start)
 
 
-def make_lifecycle(n=48, seed=2001, n_vehicles=3, side=30.0, waypoints_per_ped=3):
+def make_lifecycle(n=48, seed=2001, n_vehicles=3, side=30.0, waypoints_per_ped=3, spawn_late=0, spawn_at=(20, 45)):
     """Small all-forces scene in which every lifecycle event happens within ~6 s: waypoint hand-overs (some requesting a
     road crossing), gap acceptance against crossing vehicles, idle pedestrians waking up, finished routes."""
     rng = np.random.default_rng(seed)
@@ -224,6 +225,11 @@ def make_lifecycle(n=48, seed=2001, n_vehicles=3, side=30.0, waypoints_per_ped=3
     margin = _f32(rng.uniform(0.5, 2.5, size=n))
     margin[rng.random(n) < 0.1] = -1.0                      # crosses without looking (check_traffic.py:24)
     life = Lifecycle(routes, _f32(rng.uniform(1.2, 1.8, size=n)), margin, rng.random(n) < 0.12)
+    if spawn_late:                                          # the last `spawn_late` pedestrians join in two waves
+        tick = np.zeros(n, dtype=np.int64)
+        tick[n - spawn_late:n - spawn_late // 2] = spawn_at[0]
+        tick[n - spawn_late // 2:] = spawn_at[1]
+        life.spawn_tick = tick
     return w, life
 
 

@@ -193,6 +193,17 @@ int sfm_set_routes(sfm_ctx* ctx, int64_t n, const int64_t* offsets, const double
 int sfm_advance_waypoints(sfm_ctx* ctx);
 /* cursor: entries of each pedestrian's route already handed out; finished: arrived with nothing left (run_simulation.py:127). */
 int sfm_download_routes(sfm_ctx* ctx, int64_t n, int64_t* cursor, uint8_t* finished, double* next_waypoint);
+/* Appends m pedestrians to the crowd: PedestrianSimulation.spawn_pedestrian / PedState.add_pedestrian
+ * (pedestrian_simulation.py:99-100, pedestrian_state.py:26-40), batched.  The first six arrays are those of
+ * sfm_upload_state; the five machine arrays (sfm_set_mode_machines) are required when the context carries mode machines,
+ * the route CSR (offsets int64 [m+1], waypoints, crossing; sfm_set_routes) when it carries routes.  Existing rows keep
+ * their indices.  Synchronises the stream.  Single-rank contexts only. */
+int sfm_append_pedestrians(sfm_ctx* ctx, int64_t m, const double* loc, const double* vel, const double* next_waypoint,
+                           const double* radius, const double* target_speed, const uint8_t* mode,
+                           const double* initial_target_speed, const double* crossing_speed,
+                           const double* crossing_safety_margin, const double* mode_target_speed,
+                           const double* next_mode_time, const int64_t* route_offsets, const double* waypoints,
+                           const uint8_t* crossing);
 /* Removes every pedestrian whose `finished` flag is set (run_simulation.py:127-132 with despawn_on_arrival; row order
  * preserved like PedState.remove_pedestrian, pedestrian_state.py:42-43) from all per-row tables and restages.  Returns
  * the new row count; later uploads / downloads use it.  Synchronises the stream.  Single-rank contexts only. */

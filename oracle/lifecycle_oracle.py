@@ -189,23 +189,46 @@ def run_headless(scene, w, life, n_steps, vehicles_at=None, despawn=False):
     update -> arrival test at the positions the forces saw -> x += dt v.
 
     With ``despawn`` pedestrians that arrive with no waypoint left are removed right after the hand-over loop
-    (run_simulation.py:127-132); histories then carry ``ids`` (original row of every surviving pedestrian) per tick and
-    ragged state lists.
+    (run_simulation.py:127-132); with ``life.spawn_tick`` pedestrians join the crowd at the start of their tick
+    (pedestrian_simulation.py:99-100).  Histories then carry ``ids`` (original row of every present pedestrian) per tick
+    and ragged state lists.
 
     Returns per-tick histories (T+1 entries for state, T for decisions)."""
     n = w.n
-    machines = Machines.create(w.target_speed, w.mode, life.crossing_speed_factor, life.crossing_safety_margin)
-    machines.set_mode(np.nonzero(life.idle)[0], IDLE)
-    loc, vel, wp = w.loc.copy(), w.vel.copy(), w.next_waypoint.copy()
-    target_speed = w.target_speed.copy()
-    cursor, finished = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=bool)
-    ids, radius, routes = np.arange(n), w.radius.copy(), list(life.routes)
+    spawn_tick = getattr(life, 'spawn_tick', None)
+    spawn_tick = np.zeros(n, dtype=np.int64) if spawn_tick is None else np.asarray(spawn_tick)
+    ragged = despawn or bool(spawn_tick.any())
+
+    def rows_of(sel):
+        """State columns of the pedestrians ``sel`` as the spawner hands them over (pedestrian_spawner.py:238-241)."""
+        m = Machines.create(w.target_speed[sel], w.mode[sel], np.asarray(life.crossing_speed_factor)[sel],
+                            np.asarray(life.crossing_safety_margin)[sel])
+        m.set_mode(np.nonzero(np.asarray(life.idle)[sel])[0], IDLE)
+        return m, w.loc[sel].copy(), w.vel[sel].copy(), w.next_waypoint[sel].copy(), w.target_speed[sel].copy(), \
+            w.radius[sel].copy(), [life.routes[i] for i in sel]
+
+    ids = np.nonzero(spawn_tick == 0)[0]
+    machines, loc, vel, wp, target_speed, radius, routes = rows_of(ids)
+    cursor, finished = np.zeros(len(ids), dtype=np.int64), np.zeros(len(ids), dtype=bool)
     hist = dict(ids=[ids.copy()], loc=[loc.copy()], vel=[vel.copy()], mode=[machines.mode.copy()], wp=[wp.copy()],
                 target_speed=[], mode_speed=[machines.target_speed.copy()], cursor=[cursor.copy()],
                 finished=[finished.copy()])
     vehicles_at = vehicles_at or w.vehicles_at
     for step in range(n_steps):
         t = step * w.step_length
+        late = np.nonzero(spawn_tick == step)[0] if step > 0 else np.zeros(0, dtype=np.int64)
+        if len(late):                                   # spawned at the start of the tick, appended in index order
+            m2, loc2, vel2, wp2, ts2, rad2, routes2 = rows_of(late)
+            m2.sim_time = machines.sim_time
+            machines = Machines(*(np.concatenate((getattr(machines, f), getattr(m2, f))) for f in
+                                  ('mode', 'target_speed', 'initial_target_speed', 'crossing_speed',
+                                   'crossing_safety_margin', 'next_mode_time')), machines.waiting_time, machines.sim_time)
+            loc, vel, wp = np.concatenate((loc, loc2)), np.concatenate((vel, vel2)), np.concatenate((wp, wp2))
+            target_speed, radius = np.concatenate((target_speed, ts2)), np.concatenate((radius, rad2))
+            routes = routes + routes2
+            cursor = np.concatenate((cursor, np.zeros(len(late), dtype=np.int64)))
+            finished = np.concatenate((finished, np.zeros(len(late), dtype=bool)))
+            ids = np.concatenate((ids, late))
         veh = vehicles_at(step)
         traffic = (veh[1], veh[3], veh[4]) if veh is not None else None
         tick_modes(machines, target_speed, loc, wp, t, traffic)
@@ -228,6 +251,6 @@ def run_headless(scene, w, life, n_steps, vehicles_at=None, despawn=False):
         hist['wp'].append(wp.copy()); hist['target_speed'].append(target_speed.copy())
         hist['mode_speed'].append(machines.target_speed.copy()); hist['cursor'].append(cursor.copy())
         hist['finished'].append(finished.copy())
-    if despawn:
+    if ragged:
         return hist
     return {k: np.array(v) for k, v in hist.items()}

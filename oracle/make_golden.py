@@ -107,6 +107,16 @@ def golden_lifecycle_despawn(ref, cfg):
                         **pack_ragged(out, w.n))
 
 
+def golden_lifecycle_spawn(ref, cfg):
+    """Spawning (two late waves, pedestrian_simulation.py:99-100) and despawning in one run: the crowd goes 34 -> 33 -> 18."""
+    import dataclasses
+    w, life = synth.make_lifecycle(spawn_late=14)
+    life = dataclasses.replace(life, despawn_on_arrival=True)
+    out = ref_loader.run_lifecycle(ref, w, life, cfg, 100, despawn=True)
+    np.savez_compressed(os.path.join(GOLDEN, 'lifecycle_spawn.npz'), digest=lifecycle_digest(w, life),
+                        spawn_tick=life.spawn_tick, **pack_ragged(out, w.n))
+
+
 def golden_output_csv(ref_dir):
     """The four CSV files the reference's own OutputGenerator writes for a tiny recorded scene (output_generator.py)."""
     import importlib.util
@@ -142,6 +152,7 @@ def main():
     if args.only in (None, 'lifecycle'):
         golden_lifecycle(ref, cfg)
         golden_lifecycle_despawn(ref, cfg)
+        golden_lifecycle_spawn(ref, cfg)
     if args.only in (None, 'csv'):
         golden_output_csv(ref_loader.REFERENCE_DIR)
 

@@ -148,21 +148,33 @@ def run_lifecycle(ref, workload, life, sfm_config, n_steps, despawn=False):
     PedMode, Manager = ref.ped_mode_manager.PedMode, ref.ped_mode_manager.PedModeManager
     n = workload.n
     names = [f'p_{i}' for i in range(n)]
-    for i in range(n):
+    spawn_tick = getattr(life, 'spawn_tick', None)
+    spawn_tick = np.zeros(n, dtype=np.int64) if spawn_tick is None else np.asarray(spawn_tick)
+
+    def spawn(i):
         m = Manager(names[i], float(workload.target_speed[i]), PedMode(int(workload.mode[i])),
                     float(life.crossing_speed_factor[i]), float(life.crossing_safety_margin[i]))
         if life.idle[i]:
             m.set_mode(PedMode.IDLE)
         sim.spawn_pedestrian((names[i], i, workload.loc[i], workload.vel[i], workload.next_waypoint[i], m,
                               float(workload.radius[i]), float(workload.target_speed[i])))
+
+    for i in np.nonzero(spawn_tick == 0)[0]:
+        spawn(i)
     waypoint_dict = {names[i]: list(life.routes[i]) for i in range(n)}
     dt = workload.step_length
     codes = lambda: np.array([int(m.current_mode) for m in sim.peds.state['mode']], dtype=np.uint8)   # noqa: E731
     speeds = lambda: np.array([float(m.target_speed) for m in sim.peds.state['mode']])                # noqa: E731
     hist = dict(loc=[sim.peds.state['loc'].copy()], vel=[sim.peds.state['vel'].copy()], mode=[codes()],
                 wp=[sim.peds.state['next_waypoint'].copy()], target_speed=[], mode_speed=[speeds()],
-                remaining=[np.array([len(waypoint_dict[k]) for k in names])])
+                remaining=[np.array([len(waypoint_dict[k]) for k in sim.peds.state['name']])])
+    ragged = despawn or bool(spawn_tick.any())
+    if ragged:
+        hist['ids'] = [sim.peds.state['id'].copy()]
     for step in range(n_steps):
+        if step > 0:
+            for i in np.nonzero(spawn_tick == step)[0]:                        # the spawner runs before the tick
+                spawn(i)
         veh = workload.vehicles_at(step)
         if veh is not None:
             sim.update_dynamic_obstacles(veh)
@@ -176,18 +188,18 @@ def run_lifecycle(ref, workload, life, sfm_config, n_steps, despawn=False):
             elif despawn:                                                      # run_simulation.py:127-132
                 sim.destroy_pedestrian(ped_name)
                 waypoint_dict.pop(ped_name)
-        if despawn:
+        if ragged:
             if sim.peds.size() == 0:
                 break
             nv = sim.peds.state[['id', 'vel']]
-            hist.setdefault('ids', [np.arange(n)]).append(sim.peds.state['id'].copy())
+            hist['ids'].append(sim.peds.state['id'].copy())
         sim.peds.state['loc'] += nv['vel'] * dt
         sim.peds.all_states.clear()
         sim.all_dyn_obs_states.clear()
         hist['loc'].append(sim.peds.state['loc'].copy()); hist['vel'].append(sim.peds.state['vel'].copy())
         hist['mode'].append(codes()); hist['wp'].append(sim.peds.state['next_waypoint'].copy())
         hist['mode_speed'].append(speeds())
-        hist['remaining'].append(np.array([len(waypoint_dict[k]) for k in names if k in waypoint_dict]))
-    if despawn:
+        hist['remaining'].append(np.array([len(waypoint_dict[k]) for k in sim.peds.state['name']]))
+    if ragged:
         return hist
     return {k: np.array(v) for k, v in hist.items()}

@@ -213,3 +213,22 @@ def test_despawn_on_arrival_matches_reference_golden(scenario, sfm_config):
     s = run.snapshot()
     assert np.array_equal(run.ids, g['ids_final']) and np.array_equal(s['wp'], g['wp_final'])
     assert np.abs(s['loc'] - g['loc_final']).max() < 0.1 and np.median(np.abs(s['loc'] - g['loc_final'])) < 1e-4
+
+
+def test_spawn_and_despawn_match_reference_golden(sfm_config):
+    """sfm_append_pedestrians + sfm_despawn_finished in one run: pedestrians join in two waves and leave on arrival; the
+    device crowd has the reference's members, in the reference's row order, with the reference's modes at every tick."""
+    import dataclasses
+    w, life = synth.make_lifecycle(spawn_late=14)
+    life = dataclasses.replace(life, despawn_on_arrival=True)
+    g = np.load(os.path.join(GOLDEN, 'lifecycle_spawn.npz'))
+    run = HeadlessRunner(sfm_config, w, life)
+    assert run.ctx.n == 34
+    for k in range(100):
+        run.tick()
+        alive = np.nonzero(g['alive'][k + 1])[0]
+        assert sorted(run.ids) == alive.tolist() and run.ctx.n == len(alive), f'crowd differs after tick {k}'
+        assert np.array_equal(run.ctx.download_mode_codes(), g['mode'][k + 1][run.ids]), f'modes differ after tick {k}'
+    assert np.array_equal(run.ids, g['ids_final'])
+    s = run.snapshot()
+    assert np.array_equal(s['wp'], g['wp_final']) and np.abs(s['loc'] - g['loc_final']).max() < 0.1

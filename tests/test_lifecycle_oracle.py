@@ -184,3 +184,18 @@ def test_host_mode_manager_equals_oracle_columns():
         assert [int(o.current_mode) for o in objs] == cols.mode.tolist()
         assert [float(o.target_speed) for o in objs] == cols.target_speed.tolist()
         assert [float(o.next_mode_time) for o in objs] == cols.next_mode_time.tolist()
+
+
+def test_oracle_spawn_and_despawn_reproduce_reference_golden(sfm_config):
+    """Two late spawn waves plus despawn on arrival: same crowd membership, modes and final state as the reference."""
+    import dataclasses
+    from oracle.make_golden import pack_ragged
+    w, life = synth.make_lifecycle(spawn_late=14)
+    life = dataclasses.replace(life, despawn_on_arrival=True)
+    scene = O.Scene(sfm_config, w.step_length, w.borders, w.section_center, w.section_length, w.static_obstacles)
+    got = pack_ragged(LO.run_headless(scene, w, life, 100, despawn=True), w.n)
+    g = np.load(os.path.join(GOLDEN, 'lifecycle_spawn.npz'))
+    assert str(g['digest']) == lifecycle_digest(w, life) and np.array_equal(g['spawn_tick'], life.spawn_tick)
+    assert np.array_equal(g['alive'], got['alive']) and np.array_equal(g['mode'], got['mode'])
+    assert g['alive'][0].sum() == 34 and g['alive'][46].sum() > g['alive'][44].sum()        # the second wave arrives
+    assert np.array_equal(g['ids_final'], got['ids_final']) and np.abs(g['loc_final'] - got['loc_final']).max() <= 1e-9
