@@ -64,6 +64,7 @@ class HeadlessRunner:
         self.ids = first.copy()                            # original row of every pedestrian in the crowd
         self._finished_seen = 0
         self.record_every = record_every
+        self.all_dyn_obs_states = {}
         if record_every:
             c.record_begin(record_capacity)
 
@@ -97,6 +98,13 @@ class HeadlessRunner:
         c.tick_modes(sim_time)
         if self.record_every and k % self.record_every == 0:
             c.record_frame(sim_time)                      # after the machines ticked, before the forces (:75)
+            if self.has_vehicles:                         # record_dyn_obstacle_states (pedestrian_simulation.py:129-140)
+                centres = c.download_vehicles()[0] if self.device_vehicles else np.asarray(self.w.vehicles_at(k)[1])
+                st = np.zeros(len(centres), dtype=[('id', 'i4'), ('loc', 'f8', (2,)), ('heading', 'f8'),
+                                                    ('vel', 'f8', (2,)), ('extent', 'f8', (2,))])
+                st['id'] = np.arange(1000, 1000 + len(centres))
+                st['loc'], st['heading'], st['vel'], st['extent'] = centres, self.w.veh_yaw, self.w.veh_vel, self.w.veh_extent
+                self.all_dyn_obs_states[sim_time] = st
         c.step(1, integrate_positions=True)
         if self.life.despawn_on_arrival and c.lifecycle_counters()['finished'] > self._finished_seen:
             # run_simulation.py:127-132.  The counter read-back (32 bytes) is the only per-tick synchronisation; the mask
@@ -109,6 +117,19 @@ class HeadlessRunner:
     def run(self, n_steps):
         for _ in range(n_steps):
             self.tick()
+
+    def write_csv(self, output_path, scenario_name):
+        """The reference's four result files (output_generator.py) from the device-recorded frames of this run."""
+        import types
+        from output_generator import OutputGenerator
+        sim = types.SimpleNamespace(peds=types.SimpleNamespace(all_states={}), all_dyn_obs_states=self.all_dyn_obs_states,
+                                    static_obstacles=list(self.w.static_obstacles), borders=list(self.w.borders))
+        gen = OutputGenerator(sim, output_path, scenario_name)
+        gen.generate_ped_csv(device_frames=self.ctx.download_frames(), ped_ids=self.ids)
+        gen.generate_veh_csv()
+        gen.generate_borders_csv()
+        gen.generate_obstacles_csv()
+        return gen.output_dir
 
     def snapshot(self):
         loc, vel = self.ctx.download_state()

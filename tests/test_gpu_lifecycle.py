@@ -232,3 +232,28 @@ def test_spawn_and_despawn_match_reference_golden(sfm_config):
     assert np.array_equal(run.ids, g['ids_final'])
     s = run.snapshot()
     assert np.array_equal(s['wp'], g['wp_final']) and np.abs(s['loc'] - g['loc_final']).max() < 0.1
+
+
+def test_headless_run_writes_reference_csv_files(scenario, sfm_config, tmp_path):
+    """A recorded device-resident run ends in the reference's four CSV files (output_generator.py:32-110)."""
+    w, life = scenario
+    run = HeadlessRunner(sfm_config, w, life, record_every=5, record_capacity=8)
+    first = None
+    for k in range(40):
+        if k == 5:
+            loc5, vel5 = run.ctx.download_state()
+        run.tick()
+        if k == 5:
+            first = (loc5, vel5, run.ctx.download_frames()[1][1])
+    out = run.write_csv(str(tmp_path), 'headless')
+    ped = open(os.path.join(out, 'pedestrian.csv')).read().splitlines()
+    veh = open(os.path.join(out, 'vehicle.csv')).read().splitlines()
+    assert ped[0] == 'ped_id,frame,time,x,y,v_x,v_y,mode' and len(ped) == 1 + 8 * w.n
+    assert veh[0] == 'veh_id,frame,time,x,y,heading,vel,ext_x,ext_y' and len(veh) == 1 + 8 * len(w.veh_center)
+    # frame 1 was recorded at tick 5, after the machines ticked and before the forces moved anybody (:75-81)
+    row = ped[1 + w.n + 3].split(',')
+    assert row[:2] == ['3', '1'] and float(row[2]) == 0.25
+    assert [float(v) for v in row[3:7]] == [first[0][3, 0], first[0][3, 1], first[1][3, 0], first[1][3, 1]]
+    assert np.array_equal(first[2][:, :2], first[0][:, :2])
+    assert len(open(os.path.join(out, 'borders.csv')).read().splitlines()) == 1 + sum(len(b) for b in w.borders)
+    assert len(open(os.path.join(out, 'obstacles.csv')).read().splitlines()) == 1 + sum(len(r) for _, r in w.static_obstacles)
