@@ -139,7 +139,7 @@ def run_reference(args, world, rank):
     for k in range(args.steps):
         r = cpu_baseline.time_sample(w, cfg, rows_per_core=rows_per_core, cores=cores, seed=k)
         times.append(r['seconds'])
-        rows = r['rows']
+        rows, cores = r['rows'], r['cores']           # the workers actually used (memory-capped on many-core boxes)
     sec = float(np.mean(times))
     value = rows * (w.n - 1) / sec
     sample = f'{rows} of {w.n} rows per step (full tick for those rows against all {w.n} pedestrians), {cores} forked workers'
