@@ -30,6 +30,10 @@ namespace sfm {
 #ifndef SFM_KS_ASIN_TERMS
 #define SFM_KS_ASIN_TERMS 7
 #endif
+#ifndef SFM_KS_ANGLE
+#define SFM_KS_ANGLE 2          // planar tiles: 0 = octant reduction on min(|sin|, |cos|); 1, 2 = first-quadrant angle from
+#endif                          //   (|sin| - |cos|) / sqrt 2 (no min / compare / select), signs by 1: one product + two
+                                //   transfers, 2: two transfers (profiles/tune_k1s_r2*.log: 3.95 -> 3.83 -> 3.75 ms)
 #ifndef SFM_KS_NEGSUB
 #define SFM_KS_NEGSUB 1         // a*b - c*d written as sub2(mul2, mul2): no 64-bit XOR negations (2 LOP3 each)
 #endif
@@ -37,14 +41,15 @@ namespace sfm {
 #define SFM_KS_UNROLL 1
 #endif
 #ifndef SFM_KS_MINB
-#define SFM_KS_MINB 5           // min CTAs per SM handed to __launch_bounds__ (register cap)
+#define SFM_KS_MINB 4           // min CTAs per SM handed to __launch_bounds__ (register cap 128: no spills; 5 -> 96 registers
+                                // spills the fixed-point accumulators and is 1.5-4 % slower, profiles/tune_k1s_r2*.log)
 #endif
 constexpr int KS_UNROLL = SFM_KS_UNROLL;                 // unroll depth of the j-quad loop
 constexpr int KS_IR = SFM_KS_IR;                         // rows per thread
 constexpr int KS_THREADS = K1_TJ / KS_IR;                // one 256-row tile per CTA
 constexpr int KS_WARPS = KS_THREADS / 32;
 constexpr int KS_QUADS = K1_TJ / 4;
-constexpr int KS_PLANES = 8;                             // PX..PVZ + the per-row non-planar flag (PSPARE)
+constexpr int KS_PLANES = NPLANES;                       // every staged plane, the per-row non-planar flag included
 constexpr float KS_FIXED_SCALE = 4294967296.0f;          // 2^32 counts per m/s^2
 constexpr float KS_FIXED_LIMIT = 1.0e9f;                 // |partial| beyond this goes to the repair path
 
@@ -61,6 +66,7 @@ struct SymArgs {
 struct AsinConst {
     f32x2 s0, s1, s2, s3, s4, s5, s6;
 };
+template <bool DIFF_FORM>
 __device__ __forceinline__ AsinConst make_asin_const() {
     AsinConst c;
 #if SFM_KS_ASIN_TERMS == 6
@@ -72,30 +78,56 @@ __device__ __forceinline__ AsinConst make_asin_const() {
     c.s3 = splat2(3.859527037e-02f); c.s4 = splat2(6.176946312e-02f); c.s5 = splat2(-5.651333556e-02f);
     c.s6 = splat2(1.019138768e-01f);
 #endif
+    if (DIFF_FORM) {
+        // asin(t / sqrt 2) = t Q(t^2): coefficient k scaled by 2^-(k + 1/2)
+        f32x2* cs[7] = {&c.s0, &c.s1, &c.s2, &c.s3, &c.s4, &c.s5, &c.s6};
+        float scale = 0.70710678118654752f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            float lo, hi;
+            unpack2(*cs[k], lo, hi);
+            *cs[k] = splat2(lo * scale);
+            scale *= 0.5f;
+        }
+    }
     return c;
 }
 
 // -f_ij for two consecutive j at once: g = (a Dx - b Dy, a Dy + b Dx, a Dz); F_i -= g, F_j += g.
-template <bool RADIUS, bool PLANAR>
-__device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, const f32x2 zi, const f32x2 ri,
-                                            const f32x2 vxi, const f32x2 vyi, const f32x2 vzi, const f32x2 xj,
-                                            const f32x2 yj, const f32x2 zj, const f32x2 rj, const f32x2 vxj,
-                                            const f32x2 vyj, const f32x2 vzj, const PackedConst& c,
+// One row of tile I held by a thread: every value splat over both halves of a packed register.
+struct RowP {
+    f32x2 x, y, z, xl, yl, zl, r, vx, vy, vz;
+};
+
+__device__ __forceinline__ RowP splat_row(const RowF& f) {
+    RowP o;
+    o.x = splat2(f.x); o.y = splat2(f.y); o.z = splat2(f.z); o.xl = splat2(f.xl); o.yl = splat2(f.yl); o.zl = splat2(f.zl);
+    o.r = splat2(f.r); o.vx = splat2(f.vx); o.vy = splat2(f.vy); o.vz = splat2(f.vz);
+    return o;
+}
+
+// SIGN0: reproduce np.sign(0) = 0 (forces.py:108) in the fast path -- only instantiated for epsilon == 0, where theta' = 0
+// is reached by every pair with w parallel to d (e.g. a standing crowd); with epsilon != 0 the event has measure zero.
+template <bool RADIUS, bool PLANAR, bool SIGN0>
+__device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const f32x2 yj, const f32x2 zj,
+                                            const f32x2 xlj, const f32x2 ylj, const f32x2 zlj, const f32x2 rj,
+                                            const f32x2 vxj, const f32x2 vyj, const f32x2 vzj, const PackedConst& c,
                                             const AsinConst& sc, f32x2& gx, f32x2& gy, f32x2& gz) {
+    // d = (hi_j - hi_i) + (lo_j - lo_i): exact lattice difference + remainder (sfm_common.cuh)
     // PLANAR: every pedestrian of both tiles has the same z and no vertical velocity, so d_z = w_z = D_z = 0 exactly
-    const f32x2 dx = sub2(xj, xi), dy = sub2(yj, yi);
+    const f32x2 dx = add2(sub2(xj, I.x), sub2(xlj, I.xl)), dy = add2(sub2(yj, I.y), sub2(ylj, I.yl));
     f32x2 dz = 0ull, wz = 0ull, Dz = 0ull;
     f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
     if (!PLANAR) {
-        dz = sub2(zj, zi);
+        dz = add2(sub2(zj, I.z), sub2(zlj, I.zl));
         d2 = fma2(dz, dz, d2);
     }
     const f32x2 rinv = rsqrt2(d2);
-    const f32x2 wx = sub2(vxi, vxj), wy = sub2(vyi, vyj);
+    const f32x2 wx = sub2(I.vx, vxj), wy = sub2(I.vy, vyj);
     const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy);
     f32x2 D2 = fma2(Dy, Dy, mul2(Dx, Dx));
     if (!PLANAR) {
-        wz = sub2(vzi, vzj);
+        wz = sub2(I.vz, vzj);
         Dz = fma2(dz, rinv, wz);
         D2 = fma2(Dz, Dz, D2);
     }
@@ -110,14 +142,16 @@ __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, cons
     float cl, ch, tl, th;
     unpack2(cross, cl, ch);
     unpack2(dot, tl, th);
-    const float axl = fabsf(tl), ayl = fabsf(cl), axh = fabsf(th), ayh = fabsf(ch);
     constexpr bool ASIN = PLANAR && (SFM_KS_ASIN != 0);
-    f32x2 R = 0ull, q, p;
-    if (ASIN) {
-        // planar: |D_xy| = |D| and |d_xy| = |d|, so sin/cos(theta) = cross/dot * (1/|d|)(1/|D|) -- no reciprocal
+    f32x2 R = 0ull, theta;
+    // (SIGN0 keeps the octant form: it returns theta = +-0 exactly for w parallel to d, which the difference form cannot)
+    if (ASIN && SFM_KS_ANGLE != 0 && !SIGN0) {
+        // first-quadrant angle phi = atan2(|sin|, |cos|) from sqrt2 sin(phi - pi/4) = |sin| - |cos|; then
+        // theta = sign(cross) (pi/2 + sign(dot) (phi - pi/2)) = copysign(pi/2, cross) + sign(cross dot) (phi - pi/2)
         R = mul2(rinv, Dinv);
-        q = mul2(pack2(fminf(axl, ayl), fminf(axh, ayh)), R);
+        const f32x2 q = mul2(pack2(fabsf(cl) - fabsf(tl), fabsf(ch) - fabsf(th)), R);
         const f32x2 s = mul2(q, q);
+        f32x2 p;
 #if SFM_KS_ASIN_TERMS == 6
         p = fma2(sc.s5, s, sc.s4);
 #else
@@ -128,21 +162,46 @@ __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, cons
         p = fma2(p, s, sc.s2);
         p = fma2(p, s, sc.s1);
         p = fma2(p, s, sc.s0);
+        const f32x2 g = fma2(p, q, splat2(-0.78539816339744831f));                 // phi - pi/2 in [-pi/2, 0]
+#if SFM_KS_ANGLE == 1
+        const f32x2 mg = g ^ (mul2(cross, dot) & 0x8000000080000000ULL);
+        const f32x2 h = (cross & 0x8000000080000000ULL) | splat2(1.57079632679489662f);
+        theta = add2(h, mg);
+#else
+        const f32x2 tabs = add2(g ^ (dot & 0x8000000080000000ULL), splat2(1.57079632679489662f));   // |theta| in [0, pi]
+        theta = tabs ^ (cross & 0x8000000080000000ULL);
+#endif
     } else {
-        const f32x2 mxr = pack2(rcp_approx(fmaxf(axl, ayl)), rcp_approx(fmaxf(axh, ayh)));
-        q = mul2(pack2(fminf(axl, ayl), fminf(axh, ayh)), mxr);
-        const f32x2 s = mul2(q, q);
-        p = fma2(c.a7, s, c.a6);
-        p = fma2(p, s, c.a5);
-        p = fma2(p, s, c.a4);
-        p = fma2(p, s, c.a3);
-        p = fma2(p, s, c.a2);
-        p = fma2(p, s, c.a1);
-        p = fma2(p, s, c.a0);
-    }
-    p = mul2(p, q);
-    f32x2 theta;
-    {
+        const float axl = fabsf(tl), ayl = fabsf(cl), axh = fabsf(th), ayh = fabsf(ch);
+        f32x2 q, p;
+        if (ASIN) {
+            // planar: |D_xy| = |D| and |d_xy| = |d|, so sin/cos(theta) = cross/dot * (1/|d|)(1/|D|) -- no reciprocal
+            R = mul2(rinv, Dinv);
+            q = mul2(pack2(fminf(axl, ayl), fminf(axh, ayh)), R);
+            const f32x2 s = mul2(q, q);
+#if SFM_KS_ASIN_TERMS == 6
+            p = fma2(sc.s5, s, sc.s4);
+#else
+            p = fma2(sc.s6, s, sc.s5);
+            p = fma2(p, s, sc.s4);
+#endif
+            p = fma2(p, s, sc.s3);
+            p = fma2(p, s, sc.s2);
+            p = fma2(p, s, sc.s1);
+            p = fma2(p, s, sc.s0);
+        } else {
+            const f32x2 mxr = pack2(rcp_approx(fmaxf(axl, ayl)), rcp_approx(fmaxf(axh, ayh)));
+            q = mul2(pack2(fminf(axl, ayl), fminf(axh, ayh)), mxr);
+            const f32x2 s = mul2(q, q);
+            p = fma2(c.a7, s, c.a6);
+            p = fma2(p, s, c.a5);
+            p = fma2(p, s, c.a4);
+            p = fma2(p, s, c.a3);
+            p = fma2(p, s, c.a2);
+            p = fma2(p, s, c.a1);
+            p = fma2(p, s, c.a0);
+        }
+        p = mul2(p, q);
         float pl, ph;
         unpack2(p, pl, ph);
         theta = pack2(octant_fix(pl, axl, ayl, tl, cl), octant_fix(ph, axh, ayh, th, ch));
@@ -152,7 +211,7 @@ __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, cons
     const f32x2 u2 = mul2(u, u);
     f32x2 y;
     if (RADIUS) {
-        const f32x2 dl = sub2(sub2(mul2(d2, rinv), ri), rj);
+        const f32x2 dl = sub2(sub2(mul2(d2, rinv), I.r), rj);
         y = fma2(mul2(dl, Dinv), c.k_exp, c.log2A);
     } else if (ASIN) {
         y = fma2(mul2(d2, R), c.k_exp, c.log2A);                          // |d| / |D| = d2 (1/|d|)(1/|D|)
@@ -162,7 +221,13 @@ __device__ __forceinline__ void pair_terms2(const f32x2 xi, const f32x2 yi, cons
     const f32x2 e1 = ex2_2(fma2(c.c_nprime_neg, u2, y));
     const f32x2 e2 = ex2_2(fma2(c.c_n_neg, u2, y));
     const f32x2 a = mul2(e1, Dinv);
-    const f32x2 b = mul2(e2, Dinv) | (thp & 0x8000000080000000ULL);      // copysign(e2 / |D|, theta')
+    f32x2 b = mul2(e2, Dinv) | (thp & 0x8000000080000000ULL);            // copysign(e2 / |D|, theta')
+    if (SIGN0) {
+        float bl, bh, hl, hh;
+        unpack2(b, bl, bh);
+        unpack2(thp, hl, hh);
+        b = pack2(hl == 0.0f ? 0.0f : bl, hh == 0.0f ? 0.0f : bh);
+    }
 #if SFM_KS_NEGSUB
     gx = sub2(mul2(a, Dx), mul2(b, Dy));        // ptxas folds the subtraction into FFMA2 with a negated addend
 #else
@@ -177,40 +242,33 @@ __device__ __forceinline__ long long to_fixed(float v) { return __float2ll_rn(v 
 
 // One partner tile against this thread's rows: accumulates -F_i partials in registers (returned in gi) and +g into the
 // warp's private J-side slice.  Lanes are staggered over the j-quads so no two lanes of a warp touch the same j.
-template <bool RADIUS, bool PLANAR>
+template <bool RADIUS, bool PLANAR, bool SIGN0>
 __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], float (*__restrict__ accw)[K1_TJ],
-                                         const int lane, const f32x2 (&xi2)[KS_IR], const f32x2 (&yi2)[KS_IR],
-                                         const f32x2 (&zi2)[KS_IR], const f32x2 (&ri2)[KS_IR],
-                                         const f32x2 (&vxi2)[KS_IR], const f32x2 (&vyi2)[KS_IR],
-                                         const f32x2 (&vzi2)[KS_IR], const PackedConst& pc, const AsinConst& sc,
-                                         float (&gi)[KS_IR][3]) {
+                                         const int lane, const RowP (&I)[KS_IR], const PackedConst& pc,
+                                         const AsinConst& sc, float (&gi)[KS_IR][3]) {
     f32x2 Gx[KS_IR], Gy[KS_IR], Gz[KS_IR];
 #pragma unroll
     for (int r = 0; r < KS_IR; ++r) Gx[r] = Gy[r] = Gz[r] = 0ull;
+    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
 #pragma unroll KS_UNROLL
     for (int step = 0; step < KS_QUADS; ++step) {
         const int j = ((step + lane) & (KS_QUADS - 1)) * 4;          // staggered: distinct j per lane
-        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tl[PX][j]);
-        const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&tl[PY][j]);
-        ulonglong2 Z = make_ulonglong2(0ull, 0ull), VZ = make_ulonglong2(0ull, 0ull), R = make_ulonglong2(0ull, 0ull);
-        if (!PLANAR) {
-            Z = *reinterpret_cast<const ulonglong2*>(&tl[PZ][j]);
-            VZ = *reinterpret_cast<const ulonglong2*>(&tl[PVZ][j]);
-        }
-        if (RADIUS) R = *reinterpret_cast<const ulonglong2*>(&tl[PR][j]);
-        const ulonglong2 VX = *reinterpret_cast<const ulonglong2*>(&tl[PVX][j]);
-        const ulonglong2 VY = *reinterpret_cast<const ulonglong2*>(&tl[PVY][j]);
+        auto ld = [&](int plane) { return *reinterpret_cast<const ulonglong2*>(&tl[plane][j]); };
+        const ulonglong2 X = ld(PX), Y = ld(PY), XL = ld(PXL), YL = ld(PYL);
+        const ulonglong2 Z = PLANAR ? zero : ld(PZ), ZL = PLANAR ? zero : ld(PZL), VZ = PLANAR ? zero : ld(PVZ);
+        const ulonglong2 R = RADIUS ? ld(PR) : zero;
+        const ulonglong2 VX = ld(PVX), VY = ld(PVY);
         f32x2 jx0 = 0ull, jy0 = 0ull, jz0 = 0ull, jx1 = 0ull, jy1 = 0ull, jz1 = 0ull;   // sum over my rows
 #pragma unroll
         for (int r = 0; r < KS_IR; ++r) {
             f32x2 gx, gy, gz;
-            pair_terms2<RADIUS, PLANAR>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.x, Y.x, Z.x, R.x,
-                                        VX.x, VY.x, VZ.x, pc, sc, gx, gy, gz);
+            pair_terms2<RADIUS, PLANAR, SIGN0>(I[r], X.x, Y.x, Z.x, XL.x, YL.x, ZL.x, R.x, VX.x, VY.x, VZ.x, pc, sc, gx, gy,
+                                               gz);
             Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
             jx0 = r ? add2(jx0, gx) : gx; jy0 = r ? add2(jy0, gy) : gy;
             if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz0 = r ? add2(jz0, gz) : gz; }
-            pair_terms2<RADIUS, PLANAR>(xi2[r], yi2[r], zi2[r], ri2[r], vxi2[r], vyi2[r], vzi2[r], X.y, Y.y, Z.y, R.y,
-                                        VX.y, VY.y, VZ.y, pc, sc, gx, gy, gz);
+            pair_terms2<RADIUS, PLANAR, SIGN0>(I[r], X.y, Y.y, Z.y, XL.y, YL.y, ZL.y, R.y, VX.y, VY.y, VZ.y, pc, sc, gx, gy,
+                                               gz);
             Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
             jx1 = r ? add2(jx1, gx) : gx; jy1 = r ? add2(jy1, gy) : gy;
             if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz1 = r ? add2(jz1, gz) : gz; }
@@ -239,7 +297,7 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
     }
 }
 
-template <bool RADIUS>
+template <bool RADIUS, bool SIGN0>
 __global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const SymArgs a) {
     __shared__ __align__(128) float tile[K1_STAGES][KS_PLANES][K1_TJ];
     __shared__ __align__(16) float accj[KS_WARPS][3][K1_TJ];
@@ -283,31 +341,23 @@ __global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const Sy
     // this thread's rows of tile I
     const int qi = I / tiles_per_rank;
     const float* own = a.planes + ((size_t)qi * NPLANES) * a.rows_pad + (size_t)(I - qi * tiles_per_rank) * K1_TJ;
-    float xi[KS_IR], yi[KS_IR], zi[KS_IR], ri[KS_IR], vxi[KS_IR], vyi[KS_IR], vzi[KS_IR];
-    f32x2 xi2[KS_IR], yi2[KS_IR], zi2[KS_IR], ri2[KS_IR], vxi2[KS_IR], vyi2[KS_IR], vzi2[KS_IR];
+    RowF rowf[KS_IR];
+    RowP rowp[KS_IR];
     long long fix[KS_IR][3];
     int bad[KS_IR];
 #pragma unroll
     for (int r = 0; r < KS_IR; ++r) {
-        const int row = r * KS_THREADS + tid;
-        xi[r] = own[(size_t)PX * a.rows_pad + row];
-        yi[r] = own[(size_t)PY * a.rows_pad + row];
-        zi[r] = own[(size_t)PZ * a.rows_pad + row];
-        ri[r] = own[(size_t)PR * a.rows_pad + row];
-        vxi[r] = own[(size_t)PVX * a.rows_pad + row];
-        vyi[r] = own[(size_t)PVY * a.rows_pad + row];
-        vzi[r] = own[(size_t)PVZ * a.rows_pad + row];
-        xi2[r] = splat2(xi[r]); yi2[r] = splat2(yi[r]); zi2[r] = splat2(zi[r]); ri2[r] = splat2(ri[r]);
-        vxi2[r] = splat2(vxi[r]); vyi2[r] = splat2(vyi[r]); vzi2[r] = splat2(vzi[r]);
+        rowf[r] = load_row(own, (size_t)a.rows_pad, (size_t)(r * KS_THREADS + tid));
+        rowp[r] = splat_row(rowf[r]);
         fix[r][0] = fix[r][1] = fix[r][2] = 0;
         bad[r] = 0;
     }
     const PackedConst pc = make_packed_const(a.pp);
-    const AsinConst sc = make_asin_const();
+    const AsinConst sc = make_asin_const<(SFM_KS_ANGLE != 0) && !SIGN0>();
     // planar fast path: K3 flags every staged row whose z (relative to the origin) or vertical velocity is non-zero
     int own_flag = 0;
 #pragma unroll
-    for (int r = 0; r < KS_IR; ++r) own_flag |= (own[(size_t)PSPARE * a.rows_pad + r * KS_THREADS + tid] != 0.0f);
+    for (int r = 0; r < KS_IR; ++r) own_flag |= (own[(size_t)PFLAG * a.rows_pad + r * KS_THREADS + tid] != 0.0f);
     const bool planar_own = __syncthreads_or(own_flag) == 0;
 
     for (int k = 0; k < n_items; ++k) {
@@ -318,7 +368,7 @@ __global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const Sy
         float gi[KS_IR][3];                                   // this tile's -F_i partial per row
         int flag_j = 0;
 #pragma unroll
-        for (int r = 0; r < KS_IR; ++r) flag_j |= (tile[stage][PSPARE][tid + r * KS_THREADS] != 0.0f);
+        for (int r = 0; r < KS_IR; ++r) flag_j |= (tile[stage][PFLAG][tid + r * KS_THREADS] != 0.0f);
         const bool tile_nonplanar = __syncthreads_or(flag_j) != 0;
         if (J == I) {
             // diagonal tile: guarded asymmetric evaluation with self pairs removed, rows of I only
@@ -329,16 +379,15 @@ __global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const Sy
                 acc[r].gx = acc[r].gy = acc[r].gz = 0.0f;
                 self_j[r] = r * KS_THREADS + tid;
             }
-            tile_pairs<KS_IR, RADIUS, true>(reinterpret_cast<const float (*)[K1_TJ]>(&tile[stage][0][0]), xi, yi, zi, ri, vxi,
-                                            vyi, vzi, self_j, a.pp, acc);
+            tile_pairs<KS_IR, RADIUS, true>(tile[stage], rowf, self_j, a.pp, acc);
 #pragma unroll
             for (int r = 0; r < KS_IR; ++r) { gi[r][0] = acc[r].gx; gi[r][1] = acc[r].gy; gi[r][2] = acc[r].gz; }
             __syncthreads();
         } else {
             if (planar_own && !tile_nonplanar)
-                sym_tile<RADIUS, true>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, sc, gi);
+                sym_tile<RADIUS, true, SIGN0>(tile[stage], accj[wid], lane, rowp, pc, sc, gi);
             else
-                sym_tile<RADIUS, false>(tile[stage], accj[wid], lane, xi2, yi2, zi2, ri2, vxi2, vyi2, vzi2, pc, sc, gi);
+                sym_tile<RADIUS, false, SIGN0>(tile[stage], accj[wid], lane, rowp, pc, sc, gi);
             __syncthreads();                                    // every warp's J-side slice is complete
             // flush the J side: sum the warps' slices in fixed order, fixed-point atomics into the global accumulator
             for (int e = tid; e < K1_TJ; e += KS_THREADS) {
@@ -431,20 +480,15 @@ __global__ void __launch_bounds__(KS_REPAIR_THREADS) k1_sym_repair(const FinishA
     const int total = a.world * a.rows_pad;
     for (int b = blockIdx.x; b < count; b += gridDim.x) {
         const int r = a.bad_list[b];
-        const float* own = a.planes + ((size_t)a.own_block * NPLANES) * a.rows_pad;
-        const float xi = own[(size_t)PX * a.rows_pad + r], yi = own[(size_t)PY * a.rows_pad + r];
-        const float zi = own[(size_t)PZ * a.rows_pad + r], ri = own[(size_t)PR * a.rows_pad + r];
-        const float vxi = own[(size_t)PVX * a.rows_pad + r], vyi = own[(size_t)PVY * a.rows_pad + r];
-        const float vzi = own[(size_t)PVZ * a.rows_pad + r];
+        const RowF I = load_row(a.planes + ((size_t)a.own_block * NPLANES) * a.rows_pad, (size_t)a.rows_pad, (size_t)r);
         const int islot = a.own_block * a.rows_pad + r;
         double gx = 0.0, gy = 0.0, gz = 0.0;
         for (int j = tid; j < total; j += KS_REPAIR_THREADS) {
             const int q = j / a.rows_pad;
-            const float* p = a.planes + ((size_t)q * NPLANES) * a.rows_pad + (j - q * a.rows_pad);
+            const RowF J = load_row(a.planes + ((size_t)q * NPLANES) * a.rows_pad, (size_t)a.rows_pad,
+                                    (size_t)(j - q * a.rows_pad));
             PairAcc acc = {0.0f, 0.0f, 0.0f};
-            pair_force<RADIUS, true>(xi, yi, zi, ri, vxi, vyi, vzi, p[(size_t)PX * a.rows_pad], p[(size_t)PY * a.rows_pad],
-                                     p[(size_t)PZ * a.rows_pad], p[(size_t)PR * a.rows_pad], p[(size_t)PVX * a.rows_pad],
-                                     p[(size_t)PVY * a.rows_pad], p[(size_t)PVZ * a.rows_pad], j == islot, a.pp, acc);
+            pair_force<RADIUS, true>(I, J, j == islot, a.pp, acc);
             gx += (double)acc.gx;
             gy += (double)acc.gy;
             gz += (double)acc.gz;

@@ -62,23 +62,33 @@ __device__ __forceinline__ void store_row_everywhere(const StepArgs& a, int64_t 
     for (int r = 0; r < a.n_peer; ++r) store_row(a.planes_peer[r], a.rows_pad, i, v);
 }
 
+// x (float64, origin-relative) -> lattice point hi (multiple of 2^-6 m) + remainder lo, both float32.  lo is taken against
+// the float32 value actually stored, so hi + lo represents x to 2^-31 m even where hi itself had to round (|x| >= 2^18 m).
+__device__ __forceinline__ void split_hi_lo(double x, float& hi, float& lo) {
+    hi = (float)(rint(x * POS_LATTICE) * (1.0 / POS_LATTICE));
+    lo = (float)(x - (double)hi);
+}
+
 __device__ __forceinline__ void stage_row(const StepArgs& a, int64_t i, double x, double y, double z, double r, double vx,
                                           double vy, double vz) {
     float v[NPLANES];
-    v[PX] = (float)(x - a.ox);
-    v[PY] = (float)(y - a.oy);
-    v[PZ] = (float)(z - a.oz);
+    split_hi_lo(x - a.ox, v[PX], v[PXL]);
+    split_hi_lo(y - a.oy, v[PY], v[PYL]);
+    split_hi_lo(z - a.oz, v[PZ], v[PZL]);
     v[PR] = (float)r;
     v[PVX] = (float)(a.lambda_ped * vx);
     v[PVY] = (float)(a.lambda_ped * vy);
     v[PVZ] = (float)(a.lambda_ped * vz);
     // non-planar flag read by the symmetric pair kernel (its z-free fast path needs z == origin and v_z == 0)
-    v[PSPARE] = (v[PZ] != 0.0f || v[PVZ] != 0.0f) ? 1.0f : 0.0f;
+    v[PFLAG] = (v[PZ] != 0.0f || v[PZL] != 0.0f || v[PVZ] != 0.0f) ? 1.0f : 0.0f;
     store_row_everywhere(a, i, v);
 }
 
 __device__ __forceinline__ void stage_pad(const StepArgs& a, int64_t i) {
-    const float v[NPLANES] = {PAD_POS, PAD_POS, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float v[NPLANES];
+#pragma unroll
+    for (int p = 0; p < NPLANES; ++p) v[p] = 0.0f;
+    v[PX] = v[PY] = PAD_POS;
     store_row_everywhere(a, i, v);
 }
 

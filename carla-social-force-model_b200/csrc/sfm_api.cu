@@ -93,6 +93,8 @@ struct SetStorage {
     DevBuf<float> tol;
     DevBuf<int> chunk_first;
     DevBuf<float4> chunk;
+    double threshold = 0.0;        // perception_threshold the cutoffs / bracket widths / grid of this set were built from
+    bool stale = false;            // sfm_set_params changed that threshold afterwards: the set must be uploaded again
     void release() {
         tol.release(); chunk_first.release(); chunk.release();
         center.release(); velocity.release(); point.release(); cutoff.release(); offset.release();
@@ -122,7 +124,6 @@ struct sfm_ctx {
     DevBuf<double2> wp;
     DevBuf<uint8_t> mode;
     DevBuf<float> planes;           // [world][NPLANES][rows_pad]
-    DevBuf<float4> partial;         // [nsplit][rows_pad]
     int nsplit = 1;
     DevBuf<double2> f_border, f_static, f_dynamic;
     DevBuf<double> f_total, f_accel, f_ped;
@@ -157,7 +158,6 @@ struct sfm_ctx {
     bool k2_prune = true;           // SFM_K2_PRUNE=0: cell-list kernels scan every point of an item (no chunk bounds)
     int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
                                     // cell-list kernels stay co-resident on every SM (see step_begin)
-    int k1_rows_mode = 0;           // SFM_K1_MODE=rows: ordered-pair row kernel instead of the symmetric one
     DevBuf<long long> facc;         // [world * rows_pad][4] fixed-point force accumulators + poison counter
     // ---- lifecycle: mode machines, traffic, routes, device-generated vehicle rings, recorder
     DevBuf<double> mm_speed, mm_initial, mm_crossing, mm_margin, mm_next_time;
@@ -410,53 +410,6 @@ int launch_stage(sfm_ctx* c) {
     return 0;
 }
 
-int launch_pairs_rows(sfm_ctx* c) {
-    if (!c->staged) SFM_TRY(launch_stage(c));
-    constexpr int IR = 2;
-    const int rows_per_cta = K1_THREADS * IR;
-    const int itiles = (int)(c->rows_pad / rows_per_cta);
-    const int total_tiles = (int)((int64_t)c->world * c->rows_pad / K1_TJ);
-    int nsplit = std::max(1, cdiv(c->k1_target_ctas, itiles));
-    nsplit = std::min(nsplit, std::min(total_tiles, 512));
-    c->nsplit = nsplit;
-    SFM_TRY(c->partial.ensure((size_t)nsplit * c->rows_pad));
-    const PairParams pp = make_pair_params(c->params.ped);
-    SpanGuard g(c, ST_PAIRS);
-    dim3 grid(itiles, nsplit);
-    const bool rad = c->params.use_ped_radius != 0;
-#define SFM_K1_LAUNCH(IRV, MINBV)                                                                                      \
-    do {                                                                                                               \
-        if (rad)                                                                                                       \
-            k1_ped_pairs<IRV, true, MINBV><<<grid, K1_THREADS, 0, c->stream>>>(                                         \
-                planes_cur(c), (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
-        else                                                                                                           \
-            k1_ped_pairs<IRV, false, MINBV><<<grid, K1_THREADS, 0, c->stream>>>(                                        \
-                planes_cur(c), (int)c->rows_pad, total_tiles, c->rank, c->partial.p, (int)c->rows_pad, pp);              \
-    } while (0)
-    SFM_K1_LAUNCH(2, 5);            // the configuration profiles/tune_k1_r1.log found best for the row kernel
-#undef SFM_K1_LAUNCH
-    c->launches += 1;
-    c->pair_launches += 1;
-    c->pair_evals += (int64_t)c->rows_pad * c->world * c->rows_pad;
-    SFM_CUDA(cudaGetLastError());
-    // reduce the split partials (and repair rows the unguarded fast path poisoned)
-    SFM_TRY(c->f_ped.ensure((size_t)3 * std::max<int64_t>(c->n, 1)));
-    SFM_TRY(c->fixup_rows.ensure(1));
-    if (!c->fixup_zeroed) {
-        SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, sizeof(unsigned long long), c->stream));
-        c->fixup_zeroed = true;
-    }
-    ReduceArgs ra{};
-    ra.planes = planes_cur(c); ra.rows_pad = (int)c->rows_pad; ra.world = c->world; ra.own_block = c->rank;
-    ra.n_local = (int)c->n; ra.partial = c->partial.p; ra.nsplit = nsplit; ra.f_ped = c->f_ped.p;
-    ra.fixup_rows = c->fixup_rows.p; ra.pp = pp;
-    if (c->params.use_ped_radius) k1_reduce_fixup<true><<<cdiv(c->n, 256), 256, 0, c->stream>>>(ra);
-    else k1_reduce_fixup<false><<<cdiv(c->n, 256), 256, 0, c->stream>>>(ra);
-    c->launches += 1;
-    SFM_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // Symmetric pair kernel, phase 1: zero the fixed-point accumulators and add every tile pair this rank owns.
 int launch_pairs_accumulate(sfm_ctx* c) {
     if (!c->staged && c->p2p) return fail("peer-memory contexts restage collectively: call sfm_stage on every rank first");
@@ -477,8 +430,12 @@ int launch_pairs_accumulate(sfm_ctx* c) {
     dim3 grid(own_tiles, nsplit);
     // experiment knob: extra dynamic shared memory caps the pair kernel's CTAs per SM while cell-list kernels are in flight
     const int pad = c->join_pending ? c->k1_smem_pad : 0;
-    if (c->params.use_ped_radius) k1_sym_pairs<true><<<grid, KS_THREADS, pad, c->stream>>>(a);
-    else k1_sym_pairs<false><<<grid, KS_THREADS, pad, c->stream>>>(a);
+    // SIGN0 variant: np.sign(0) = 0 reproduced in the fast path, needed only when epsilon == 0 (k1_sym.cuh)
+    const bool rad = c->params.use_ped_radius != 0, sign0 = a.pp.eps_gamma == 0.0f;
+    if (rad && sign0) k1_sym_pairs<true, true><<<grid, KS_THREADS, pad, c->stream>>>(a);
+    else if (rad) k1_sym_pairs<true, false><<<grid, KS_THREADS, pad, c->stream>>>(a);
+    else if (sign0) k1_sym_pairs<false, true><<<grid, KS_THREADS, pad, c->stream>>>(a);
+    else k1_sym_pairs<false, false><<<grid, KS_THREADS, pad, c->stream>>>(a);
     c->launches += 1;
     c->pair_launches += 1;
     for (int t = 0; t < own_tiles; ++t) {        // pair terms this launch evaluates: half shell + the diagonal tile
@@ -523,7 +480,6 @@ int launch_pairs_finish(sfm_ctx* c) {
 }
 
 int launch_pairs(sfm_ctx* c) {
-    if (c->k1_rows_mode) return launch_pairs_rows(c);
     SFM_TRY(launch_pairs_accumulate(c));
     return launch_pairs_finish(c);
 }
@@ -584,6 +540,7 @@ int build_set_grid(sfm_ctx* c, SetStorage& st, int64_t count, const double* cent
         y0 = std::min(y0, centers[2 * i + 1]); y1 = std::max(y1, centers[2 * i + 1]);
     }
     double cell = std::max(max_cut, 1e-3);
+    if (!std::isfinite(cell)) cell = std::max(std::max(x1 - x0, y1 - y0) * 2.0, 1.0);      // everything in one cell
     for (;;) {
         const double nx = std::floor((x1 - x0) / cell) + 1.0, ny = std::floor((y1 - y0) / cell) + 1.0;
         if (nx * ny <= 1048576.0 && nx <= 4096.0 && ny <= 4096.0) break;
@@ -640,7 +597,8 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
     double max_cut = 0.0;
     for (int64_t i = 0; i < count; ++i) {
         cut[i] = cutoffs ? cutoffs[i] : uniform_cut;
-        if (std::isfinite(cut[i])) max_cut = std::max(max_cut, cut[i]);
+        // an infinite cutoff reaches every pedestrian (forces.py:149-150 accepts it everywhere): one grid cell
+        if (!std::isnan(cut[i])) max_cut = std::max(max_cut, cut[i]);
     }
     for (int64_t i = 0; i <= count; ++i) off[i] = (int)offsets[i];
     std::vector<float> tol(count);
@@ -715,6 +673,9 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
                                                      : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->f_static : c->f_dynamic);
     const int n = (int)c->n;
     SFM_TRY(out.ensure(n));
+    if (st.s.count && st.stale)
+        return fail("perception_threshold changed after this obstacle set was uploaded (its cutoffs and cell grid are built "
+                    "from it): call sfm_set_obstacles / sfm_set_vehicles again");
     if (st.s.count == 0) {       // forces.py:140-141, :209-210: zeros
         SpanGuard g(c, ST_SEGMENTS, strm);
         k2_zero<<<cdiv(n, 256), 256, 0, strm>>>(out.p, n);
@@ -781,7 +742,7 @@ int step_begin(sfm_ctx* c) {
     }
     auto pairs = [&]() -> int {
         if (!P.enable[SFM_FORCE_PEDESTRIAN]) return 0;
-        return c->k1_rows_mode ? launch_pairs_rows(c) : launch_pairs_accumulate(c);
+        return launch_pairs_accumulate(c);
     };
     if (forked && c->k1_first) SFM_TRY(pairs());
     if (any_set && !c->perm_valid) SFM_TRY(rebin_peds(c, st2));
@@ -912,14 +873,15 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_K2_PERSIST")) c->k2_persist = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("SFM_K2_PERSIST_MULTI")) c->k2_persist_multi = std::atoi(env) != 0;
     c->sm_count = prop.multiProcessorCount;
-    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SFM_CUDA(cudaFuncSetAttribute(k1_sym_pairs<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char* env = std::getenv("SFM_OVERLAP")) c->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K1_TARGET_CTAS")) c->k1_target_ctas = std::max(1, std::atoi(env));
     else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
-    if (const char* env = std::getenv("SFM_K1_MODE")) c->k1_rows_mode = std::strcmp(env, "rows") == 0;
     *out = c;
     return 0;
 }
@@ -931,7 +893,7 @@ int sfm_destroy(sfm_ctx* c) {
     for (auto& sp : c->spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     c->locr.release(); c->vels.release(); c->wp.release(); c->mode.release(); c->planes.release();
-    c->partial.release(); c->f_border.release(); c->f_static.release(); c->f_dynamic.release();
+    c->f_border.release(); c->f_static.release(); c->f_dynamic.release();
     c->f_total.release(); c->f_accel.release(); c->f_ped.release();
     c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
@@ -982,6 +944,11 @@ int sfm_set_params(sfm_ctx* c, const sfm_params* p) {
         if (!(m->gamma > 0.0) || !(m->A > 0.0)) return fail("Moussaid parameters gamma and A must be positive");
     if (!(p->border_b != 0.0)) return fail("border_force.b must be non-zero");
     const bool lambda_changed = !c->have_params || c->params.ped.lambda_weight != p->ped.lambda_weight;
+    // the obstacle sets bake the perception threshold into their cutoffs, bracket widths and cell grid (upload_set)
+    if (c->stat.s.count && p->static_obs.perception_threshold != c->stat.threshold) c->stat.stale = true;
+    if (c->dyn.s.count && p->dynamic_obs.perception_threshold != c->dyn.threshold) c->dyn.stale = true;
+    if (c->stat.s.count && p->static_obs.perception_threshold == c->stat.threshold) c->stat.stale = false;
+    if (c->dyn.s.count && p->dynamic_obs.perception_threshold == c->dyn.threshold) c->dyn.stale = false;
     c->params = *p;
     c->have_params = true;
     if (lambda_changed) c->staged = false;
@@ -1109,7 +1076,10 @@ int sfm_set_obstacles(sfm_ctx* c, int which, int64_t n_obstacles, const double* 
     const bool dynamic = which == SFM_FORCE_DYNAMIC_OBSTACLE;
     if (dynamic) c->have_vehicles = false;       // host-provided rings replace a device-generated vehicle set
     const double thr = dynamic ? c->params.dynamic_obs.perception_threshold : c->params.static_obs.perception_threshold;
-    return upload_set(c, dynamic ? c->dyn : c->stat, n_obstacles, centers, nullptr, thr, velocities, offsets, points);
+    SetStorage& st = dynamic ? c->dyn : c->stat;
+    st.threshold = thr;
+    st.stale = false;
+    return upload_set(c, st, n_obstacles, centers, nullptr, thr, velocities, offsets, points);
 }
 
 int sfm_force(sfm_ctx* c, int cls, int64_t n, double* out) {
@@ -1121,7 +1091,7 @@ int sfm_force(sfm_ctx* c, int cls, int64_t n, double* out) {
     if (!out) return fail("null output");
     SFM_TRY(ensure_force_buffers(c));
     if (cls == SFM_FORCE_ACCELERATION || cls == SFM_FORCE_PEDESTRIAN) {
-        if (cls == SFM_FORCE_PEDESTRIAN && c->world > 1 && !c->k1_rows_mode)
+        if (cls == SFM_FORCE_PEDESTRIAN && c->world > 1)
             return fail("the per-class pedestrian force of a multi-rank context needs the reduce-scatter; use the step API");
         if (cls == SFM_FORCE_PEDESTRIAN) SFM_TRY(launch_pairs(c));
         StepArgs a = step_args(c);
@@ -1689,6 +1659,8 @@ int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, cons
     SFM_TRY(st.offset.ensure(n_vehicles + 1)); SFM_TRY(st.point.ensure(np));
     SFM_TRY(c->veh_extent.ensure(n_vehicles)); SFM_TRY(c->veh_yaw.ensure(n_vehicles));
     const double thr = c->params.dynamic_obs.perception_threshold;
+    st.threshold = thr;
+    st.stale = false;
     std::vector<double> cut(n_vehicles, thr);
     std::vector<float> tol(n_vehicles);
     for (int64_t v = 0; v < n_vehicles; ++v)          // ring points lie within size_factor * max(extent) of the centre
@@ -1710,7 +1682,7 @@ int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, cons
     s.point = st.point.p; s.n_points = np;
     c->veh_size_factor = size_factor;
     c->tr_ext0[0] = extents[0]; c->tr_ext0[1] = extents[1];
-    SFM_TRY(build_set_grid(c, st, n_vehicles, centers, std::isfinite(thr) ? thr : 0.0));
+    SFM_TRY(build_set_grid(c, st, n_vehicles, centers, std::isnan(thr) ? 0.0 : thr));
     s.count = n_vehicles;
     c->have_vehicles = true;
     return launch_vehicle_rings(c);
@@ -1840,7 +1812,6 @@ int sfm_step_peer(sfm_ctx* c, int n_steps, int integrate_positions) {
     SFM_TRY(check_ctx(c));
     if (!c->p2p) return fail("the peer-memory exchange is not set up (sfm_peer_export / sfm_peer_import)");
     if (!c->have_params) return fail("sfm_set_params must be called first");
-    if (c->k1_rows_mode) return fail("the peer-memory exchange needs the symmetric pair kernel");
     for (int s = 0; s < n_steps; ++s) {
         SFM_TRY(step_begin(c));                          // pair accumulation into this rank's accumulator + cell-list forces
         SFM_TRY(launch_barrier(c));                      // every rank's accumulator is complete

@@ -10,11 +10,18 @@ namespace sfm {
 
 // ---- staged float32 planes read by the all-pairs kernel -------------------------------------------------------------
 // Gather buffer layout: [world][NPLANES][rows_pad] float32.  One rank block is what a rank contributes to the per-step
-// all-gather (32 B per pedestrian row).  Planes: position relative to the origin, radius, lambda * velocity.
-constexpr int NPLANES = 8;
-enum Plane { PX = 0, PY = 1, PZ = 2, PR = 3, PVX = 4, PVY = 5, PVZ = 6, PSPARE = 7 };
+// all-gather (44 B per pedestrian row).
+//
+// Positions are staged as float32 PAIRS (double-single): x - origin = hi + lo with hi on the 2^-6 m lattice (exact in
+// float32 while |x - origin| < 2^18 m) and |lo| <= 2^-7 m.  The pair kernel forms d = (hi_j - hi_i) + (lo_j - lo_i): the
+// first difference is exact (both operands are lattice points), the second is exact to 2^-31 m, so d carries one float32
+// rounding RELATIVE TO |d| -- independent of how far the crowd is from the origin.  (A single float32 per coordinate
+// rounds to 1.5e-5 m at |x| >= 256 m, which alone breaks the 1e-4 / 1e-5 force tolerance on integrated states.)
+constexpr int NPLANES = 11;
+enum Plane { PX = 0, PY = 1, PZ = 2, PXL = 3, PYL = 4, PZL = 5, PR = 6, PVX = 7, PVY = 8, PVZ = 9, PFLAG = 10 };
 constexpr int ROW_ALIGN = 256;              // rows_pad granularity == j-tile length of the pair kernel
 constexpr float PAD_POS = 1.0e15f;          // padded rows sit this far away: exp(-dist/B) underflows to exactly 0
+constexpr double POS_LATTICE = 64.0;        // hi parts are multiples of 1 / POS_LATTICE metres
 
 // Parameters of the float32 Moussaid evaluation, pre-folded on the host (see k1_ped_pairs.cuh for the algebra).
 struct PairParams {

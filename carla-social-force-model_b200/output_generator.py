@@ -37,19 +37,24 @@ class OutputGenerator:
         """pedestrian.csv: ped_id,frame,time,x,y,v_x,v_y,mode  (output_generator.py:32-52).
 
         ``device_frames`` = (times [F], xyv [F, n, 4], mode [F, n]) as ``Context.download_frames`` returns them, with
-        ``ped_ids`` [n] the integer suffixes of the pedestrian names; default: the host snapshots in ``peds.all_states``.
+        ``ped_ids`` [n] the integer suffixes of the pedestrian names -- or a list of (times, xyv, mode, ids) segments when
+        the crowd changed during the run (``HeadlessRunner.recorded_frames``: one segment per row set, frame numbers run
+        on); default: the host snapshots in ``peds.all_states``.
         """
         with self._open('pedestrian.csv') as f:
             writer = csv.writer(f)
             writer.writerow(['ped_id', 'frame', 'time', 'x', 'y', 'v_x', 'v_y', 'mode'])
             if device_frames is not None:
-                times, xyv, mode = device_frames
-                ids = np.asarray(ped_ids).tolist()
-                for frame, sim_time in enumerate(np.asarray(times).tolist()):
-                    cols = xyv[frame]
-                    writer.writerows(zip(ids, [frame] * len(ids), [sim_time] * len(ids), cols[:, 0].tolist(),
-                                         cols[:, 1].tolist(), cols[:, 2].tolist(), cols[:, 3].tolist(),
-                                         mode[frame].tolist()))
+                segments = device_frames if isinstance(device_frames, list) else [tuple(device_frames) + (ped_ids,)]
+                frame = 0
+                for times, xyv, mode, seg_ids in segments:
+                    ids = np.asarray(seg_ids).tolist()
+                    for k, sim_time in enumerate(np.asarray(times).tolist()):
+                        cols = xyv[k]
+                        writer.writerows(zip(ids, [frame] * len(ids), [sim_time] * len(ids), cols[:, 0].tolist(),
+                                             cols[:, 1].tolist(), cols[:, 2].tolist(), cols[:, 3].tolist(),
+                                             mode[k].tolist()))
+                        frame += 1
                 return
             for frame, (sim_time, state) in enumerate(self.ped_states.items()):
                 n = len(state)

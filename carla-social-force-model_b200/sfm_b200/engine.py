@@ -3,7 +3,7 @@
 Rows shard: each rank owns the state, the cell-list forces and the integration of a contiguous row block.  The pair
 force is evaluated once per unordered pair by exactly one rank (half-shell over 256-row tiles), so a step has two
 exchanges: an integer reduce-scatter of the fixed-point force accumulators (32 B per pedestrian) and an all-gather of
-each rank's staged block (32 B per pedestrian).  Two transports:
+each rank's staged block (44 B per pedestrian: 11 float32 planes).  Two transports:
 
 * ``exchange='peer'`` (default on one box): the library maps every rank's buffers through CUDA IPC once, and the two
   collectives are folded into its own kernels -- ``k1_sym_finish`` pulls the partial accumulators over NVLink, K3 pushes
@@ -86,6 +86,7 @@ class Engine:
         self.bounds = None
         self._gather = None
         self.device_vehicles = False
+        self._ticks = 0                     # ticks stepped since load(): sim_time and the vehicle clock
 
     # ---- set-up ---------------------------------------------------------------------------------------------------
     def load(self, w, device_vehicles=False):
@@ -105,6 +106,7 @@ class Engine:
             self.ctx.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles],
                                    [r for _, r in w.static_obstacles])
         self.device_vehicles = bool(device_vehicles) and w.veh_center is not None and len(w.veh_center) > 0
+        self._ticks = 0
         if self.device_vehicles:
             # the vehicle set lives on the device (replicated on every rank): centres advance ballistically and the
             # ellipse rings are regenerated there every tick (obstacles.py:269-281,297-329) -- no per-tick upload
@@ -130,18 +132,25 @@ class Engine:
                                    life.crossing_safety_margin[lo:hi], np.where(idle, 0.0, speed),
                                    np.where(idle, 5.0, -1.0), 5.0)
         self.ctx.set_routes(life.routes[lo:hi], life.waypoint_threshold, fused=True)
-        self._ticks = 0
 
     def tick(self, vehicles=None):
         """One headless SimulationRunner.tick: vehicles (the host 6-tuple, replicated on every rank, or the device-resident
-        set advancing itself) -> mode machines + gap acceptance -> forces, velocities, hand-overs, positions."""
+        set advancing itself) -> mode machines + gap acceptance -> forces, velocities, hand-overs, positions.  Gap
+        acceptance and the dynamic-obstacle force see the SAME vehicle state, as in the reference (run_simulation.py:92-102)."""
         sim_time = self._ticks * self.step_length
         if vehicles is not None:
             self.ctx.set_obstacles(native.DYNAMIC_OBSTACLE, vehicles[1], vehicles[5], vehicles[3])
             self.ctx.set_traffic(vehicles[1], vehicles[3], vehicles[4])
+        self._advance_vehicles()
         self.ctx.tick_modes(sim_time)
-        self.step(1, True)
+        self._step_once(True)
         self._ticks += 1
+
+    def _advance_vehicles(self):
+        """Device-resident vehicles move at the top of a tick -- the simulator integrates the world before the SFM tick
+        (run_simulation.py:77-95) -- and tick 0 sees the uploaded state, exactly like the host path ``vehicles_at(k)``."""
+        if self.device_vehicles and self._ticks > 0:
+            self.ctx.advance_vehicles(self.step_length)
 
     def set_vehicles(self, dyn_tuple):
         """The 6-tuple of pedestrian_simulation.py:108-115 (ids, centres, headings, velocities, extents, rings)."""
@@ -190,9 +199,11 @@ class Engine:
     def step(self, n_steps=1, integrate_positions=True):
         if self.device_vehicles:
             for _ in range(n_steps):
-                self.ctx.advance_vehicles(self.step_length)
+                self._advance_vehicles()
                 self._step_once(integrate_positions)
+                self._ticks += 1
             return
+        self._ticks += n_steps
         if self.world == 1:
             self.ctx.step(n_steps, integrate_positions)
             return
@@ -215,8 +226,8 @@ class Engine:
 
     def tick_host(self, loc, vel, new_vel, new_loc=None):
         """One tick with host buffers for this rank's rows (H2D, kernels, D2H inside the call)."""
-        if self.device_vehicles:
-            self.ctx.advance_vehicles(self.step_length)
+        self._advance_vehicles()
+        self._ticks += 1
         if self.world == 1:
             self.ctx.tick_host(loc, vel, new_vel, new_loc)
             return

@@ -64,9 +64,34 @@ class HeadlessRunner:
         self.ids = first.copy()                            # original row of every pedestrian in the crowd
         self._finished_seen = 0
         self.record_every = record_every
+        self.record_capacity = record_capacity
         self.all_dyn_obs_states = {}
+        self._segments = []                                # recorded frames of earlier row sets: (times, xyv, mode, ids)
         if record_every:
             c.record_begin(record_capacity)
+
+    def _flush_recorder(self):
+        """The device recorder holds frames of ONE row count.  Before the crowd changes (spawn / despawn) the frames
+        recorded so far move to the host together with the ids they belong to (pedestrian_state.py:100-104 keeps a full
+        snapshot per tick, so the reference records across spawns and despawns); ``_rearm_recorder`` follows the change."""
+        if not self.record_every:
+            return
+        times, xyv, mode = self.ctx.download_frames()
+        if len(times):
+            self._segments.append((times, xyv, mode, self.ids.copy()))
+
+    def _rearm_recorder(self):
+        if self.record_every:
+            self.ctx.record_begin(self.record_capacity)
+
+    def recorded_frames(self):
+        """Every frame recorded so far as a list of (times [F], xyv [F, n, 4], mode [F, n], ids [n]) segments."""
+        out = list(self._segments)
+        if self.record_every:
+            times, xyv, mode = self.ctx.download_frames()
+            if len(times):
+                out.append((times, xyv, mode, self.ids.copy()))
+        return out
 
     def _spawn(self, rows):
         """PedSpawner.tick -> PedestrianSimulation.spawn_pedestrian (pedestrian_spawner.py:238-241), batched."""
@@ -85,7 +110,9 @@ class HeadlessRunner:
         if k > 0:
             late = np.nonzero(self.spawn_tick == k)[0]
             if len(late):
+                self._flush_recorder()
                 self._spawn(late)
+                self._rearm_recorder()
         if self.has_vehicles:
             if self.device_vehicles:
                 if k > 0:
@@ -110,8 +137,10 @@ class HeadlessRunner:
             # run_simulation.py:127-132.  The counter read-back (32 bytes) is the only per-tick synchronisation; the mask
             # is fetched only on ticks on which somebody actually finished.
             _, finished, _ = c.download_routes()
+            self._flush_recorder()
             self.ids = self.ids[~finished]
             self._finished_seen += c.despawn_finished()
+            self._rearm_recorder()
         self.step_index += 1
 
     def run(self, n_steps):
@@ -125,7 +154,7 @@ class HeadlessRunner:
         sim = types.SimpleNamespace(peds=types.SimpleNamespace(all_states={}), all_dyn_obs_states=self.all_dyn_obs_states,
                                     static_obstacles=list(self.w.static_obstacles), borders=list(self.w.borders))
         gen = OutputGenerator(sim, output_path, scenario_name)
-        gen.generate_ped_csv(device_frames=self.ctx.download_frames(), ped_ids=self.ids)
+        gen.generate_ped_csv(device_frames=self.recorded_frames())
         gen.generate_veh_csv()
         gen.generate_borders_csv()
         gen.generate_obstacles_csv()

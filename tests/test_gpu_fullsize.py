@@ -70,3 +70,77 @@ def test_cfg5_full_size_row_sample_and_third_law(sfm_config):
     total, scale = np.abs(f_ped.sum(axis=0)), np.abs(f_ped).sum(axis=0)
     assert (total[:2] <= 1e-6 * scale[:2]).all() and total[2] == 0.0
     assert ctx.stats()['fixup_rows'] == 0
+
+
+# ---- parity on EVOLVED states: after integrated ticks positions leave the float32 lattice ------------------------------
+def _evolved_rows(loc, n_uniform, n_far):
+    """Uniformly spaced rows plus the rows farthest from the staging origin (where float32 staging would be coarsest)."""
+    centre = np.round((loc[:, :2].min(axis=0) + loc[:, :2].max(axis=0)) * 0.5)
+    far = np.argsort(-np.abs(loc[:, :2] - centre).max(axis=1))[:n_far]
+    return np.unique(np.concatenate([np.linspace(0, len(loc) - 1, n_uniform).astype(np.int64), far]))
+
+
+@pytest.mark.parametrize('cfg_id,ticks,n_uniform,n_far,chunk', [(3, 10, 48, 32, 16), (5, 10, 32, 32, 4)])
+def test_pair_force_on_evolved_state(sfm_config, cfg_id, ticks, n_uniform, n_far, chunk):
+    """10 integrated ticks, then the pair force of the float64 state the engine itself produced (forces.py:74-117 on
+    pedestrian_state.py:17 float64 fields) on >= 64 rows incl. the 32 farthest from the origin: 1e-4 rel + 1e-5 abs."""
+    w = synth.make_config(cfg_id)
+    ctx = make_context(w, sfm_config) if cfg_id == 3 else None
+    if ctx is None:
+        ctx = native.Context(0)
+        ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+        ctx.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+    ctx.step(ticks, True)
+    loc, vel = ctx.download_state()
+    assert np.abs(loc - w.loc).max() > 0.1                                   # the crowd really moved ...
+    assert (loc[:, :2].astype(np.float32).astype(np.float64) != loc[:, :2]).mean() > 0.9    # ... off the float32 lattice
+    rows = _evolved_rows(loc, n_uniform, n_far)
+    assert len(rows) >= 60
+    pp = O.moussaid_params(sfm_config['pedestrian_force'], O.PED_DEFAULTS)
+    want, risk = O.pedestrian_force(loc, vel, w.radius, pp, False, rows=rows, chunk=chunk, return_risk=True)
+    got = ctx.force(native.PEDESTRIAN)
+    assert_forces_close(got[rows], want, risk=risk, name=f'pedestrian_force after {ticks} ticks of cfg{cfg_id}')
+    # the integer accumulators conserve momentum on any state
+    total, scale = np.abs(got.sum(axis=0)), np.abs(got).sum(axis=0)
+    assert (total[:2] <= 1e-6 * scale[:2]).all()
+
+
+@pytest.mark.parametrize('offset', [(0.0, 0.0), (512.123456789, -498.87654321), (98765.4321, 123456.789)])
+@pytest.mark.parametrize('explicit_origin', [False, True])
+def test_pair_force_independent_of_origin(sfm_config, offset, explicit_origin):
+    """Non-float32-exact coordinates far from (0, 0), with and without sfm_set_origin: the staged (hi, lo) pairs make the
+    pair force independent of where the crowd sits (every row of N = 4,096 against the oracle)."""
+    w = synth.make_config(2)
+    rng = np.random.default_rng(7)
+    loc = w.loc.copy()
+    loc[:, :2] += rng.uniform(-0.03, 0.03, size=(w.n, 2)) + np.asarray(offset)
+    vel = w.vel + rng.normal(0, 1e-3, size=w.vel.shape) * [1, 1, 0]
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+    if explicit_origin:
+        ctx.set_origin(float(np.round(offset[0])), float(np.round(offset[1])), 0.0)
+    ctx.upload_state(loc, vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+    pp = O.moussaid_params(sfm_config['pedestrian_force'], O.PED_DEFAULTS)
+    want, risk = O.pedestrian_force(loc, vel, w.radius, pp, False, return_risk=True)
+    assert_forces_close(ctx.force(native.PEDESTRIAN), want, risk=risk, name=f'offset {offset}')
+
+
+def test_sign_of_zero_angle(sfm_config):
+    """theta' == 0 gives np.sign(0) = 0, i.e. no tangential force (forces.py:108).  With epsilon = 0
+    every pair of a standing crowd has theta' = 0 exactly; the fast path must not hand out +-f_theta there."""
+    cfg = dict(sfm_config, pedestrian_force=dict(sfm_config['pedestrian_force'], epsilon=0.0))
+    w = synth.make_config(2)
+    vel = np.zeros_like(w.vel)
+    vel[::7] = w.vel[::7]                       # a few walkers among a standing crowd
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(cfg, w.step_length))
+    ctx.upload_state(w.loc, vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+    pp = O.moussaid_params(cfg['pedestrian_force'], O.PED_DEFAULTS)
+    # `risk` counts 2 |f_theta| of pairs near the discontinuity: exactly 0 for the standing pairs (their f_theta is 0), so
+    # they get no slack -- a fast path that ignored sign(0) = 0 would miss by A exp(-d/B) per pair
+    want, risk = O.pedestrian_force(w.loc, vel, w.radius, pp, False, return_risk=True)
+    got = ctx.force(native.PEDESTRIAN)
+    assert_forces_close(got, want, risk=risk, name='epsilon = 0')
+    standing = np.ones(w.n, dtype=bool)
+    standing[::7] = False
+    assert np.abs(want[standing]).max() > 1e-2 and ctx.stats()['fixup_rows'] == 0

@@ -197,6 +197,35 @@ def test_headless_loop_with_device_vehicles(scenario, sfm_config):
     assert np.array_equal(got_c, centres[steps - 1])
 
 
+def test_engine_tick_with_device_vehicles_equals_headless_runner(scenario, sfm_config):
+    """Engine.tick / Engine.step with device-resident vehicles use ONE vehicle state per tick for the gap acceptance and
+    the dynamic-obstacle force (run_simulation.py:92-102), tick 0 seeing the uploaded state: bit-identical to the
+    HeadlessRunner sequence (which the test above pins to the oracle), tick by tick."""
+    from sfm_b200.engine import Engine
+    w, life = scenario
+    run = HeadlessRunner(sfm_config, w, life, device_vehicles=True)
+    eng = Engine(sfm_config, w.step_length, device=0)
+    eng.load(w, device_vehicles=True)
+    eng.load_lifecycle(w, life)
+    # (different staging origins -- (0, 0) vs the crowd centre -- on purpose: the (hi, lo) staging is origin-independent)
+    for k in range(40):
+        run.tick()
+        eng.tick()
+        s = run.snapshot()
+        loc, vel = eng.local_state()
+        assert np.array_equal(eng.ctx.download_mode_codes(), s['mode']), f'modes differ after tick {k}'
+        assert np.array_equal(loc, s['loc']) and np.array_equal(vel, s['vel']), f'state differs after tick {k}'
+        assert np.array_equal(eng.ctx.download_vehicles()[0], run.ctx.download_vehicles()[0])
+    # Engine.step (no mode machines) keeps the same vehicle clock
+    eng2 = Engine(sfm_config, w.step_length, device=0)
+    eng2.load(w, device_vehicles=True)
+    eng2.step(3, True)
+    want = w.veh_center.copy()
+    for _ in range(2):
+        want = want + w.veh_vel * w.step_length
+    assert np.array_equal(eng2.ctx.download_vehicles()[0], want)       # 3 ticks = states 0, 1, 2
+
+
 def test_despawn_on_arrival_matches_reference_golden(scenario, sfm_config):
     """sfm_despawn_finished: the device removes the pedestrians the reference destroys, at the same ticks, keeps the row
     order, and the shrinking crowd keeps producing the reference's modes."""
@@ -257,3 +286,37 @@ def test_headless_run_writes_reference_csv_files(scenario, sfm_config, tmp_path)
     assert np.array_equal(first[2][:, :2], first[0][:, :2])
     assert len(open(os.path.join(out, 'borders.csv')).read().splitlines()) == 1 + sum(len(b) for b in w.borders)
     assert len(open(os.path.join(out, 'obstacles.csv')).read().splitlines()) == 1 + sum(len(r) for _, r in w.static_obstacles)
+
+
+def test_recording_across_spawn_and_despawn(sfm_config, tmp_path):
+    """The reference records a full snapshot every tick whatever happens to the crowd (pedestrian_state.py:100-104): frames
+    recorded before a spawn / despawn survive it, every frame carries the ids of the crowd it shows, and pedestrian.csv
+    has one row per pedestrian per frame with running frame numbers."""
+    import dataclasses
+    w, life = synth.make_lifecycle(spawn_late=14)
+    life = dataclasses.replace(life, despawn_on_arrival=True)
+    ticks = 100
+    run = HeadlessRunner(sfm_config, w, life, record_every=1, record_capacity=ticks)
+    twin = HeadlessRunner(sfm_config, w, life)                     # same run, no recorder: supplies the expected frames
+    want = []
+    for k in range(ticks):
+        before, ids = twin.ctx.download_state(), twin.ids.copy()
+        late = np.nonzero(twin.spawn_tick == k)[0] if k > 0 else np.zeros(0, dtype=np.int64)
+        want.append((np.concatenate((ids, late)), np.concatenate((before[0][:, :2], w.loc[late][:, :2])),
+                     np.concatenate((before[1][:, :2], w.vel[late][:, :2]))))
+        twin.tick()
+        run.tick()
+    segments = run.recorded_frames()
+    assert len(segments) > 3                                       # the crowd changed several times
+    frames = [(ids, xyv[f]) for times, xyv, mode, ids in segments for f in range(len(times))]
+    times = np.concatenate([s[0] for s in segments])
+    assert len(frames) == ticks and np.allclose(times, np.arange(ticks) * w.step_length)
+    for k, ((ids, xyv), (want_ids, want_xy, want_v)) in enumerate(zip(frames, want)):
+        assert np.array_equal(ids, want_ids), f'frame {k}: crowd differs'
+        assert np.array_equal(xyv[:, :2], want_xy) and np.array_equal(xyv[:, 2:], want_v), f'frame {k}: state differs'
+    assert np.array_equal(run.ids, twin.ids)
+    out = run.write_csv(str(tmp_path), 'spawn_despawn')
+    ped = open(os.path.join(out, 'pedestrian.csv')).read().splitlines()
+    assert len(ped) == 1 + sum(len(ids) for ids, _ in frames)
+    last = ped[-1].split(',')
+    assert int(last[1]) == ticks - 1 and int(last[0]) == frames[-1][0][-1]
