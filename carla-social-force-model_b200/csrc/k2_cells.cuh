@@ -21,6 +21,16 @@
 // included.  So the (pedestrian, item, nearest point) triplets equal the reference's exactly, and the forces (float64,
 // reference operation order) agree to a few ulp.
 //
+// Direct path (items with a chord record, i.e. every host-uploaded item): the item's points are modelled as UNIFORMLY
+// spaced on the chord from its first to its last point, g_k = a + k/(P-1) u, with E >= max_k |q_k - g_k| measured at
+// upload (float64, against the float32-rounded a and u, plus the pedestrian's own float32 rounding).  With kappa the
+// unclamped projection index of the pedestrian on the chord line, k* = clamp(round(kappa)), D* = |p - g_k*| and spacing s,
+//     dist(p, q_k) <= min_k dist(p, q_k)   ==>   |p - g_k| <= D* + 2E   ==>   (k - kappa)^2 <= (k* - kappa)^2 + 4E(D* + E)/s^2,
+// so the float64 argmin -- exact ties included -- lies in an index window around kappa that is 1-2 points wide for a
+// straight section (E ~ rounding) and grows with curvature; windows wider than 8 points (any lane of the warp) fall back
+// to the chunk-pruned float32 scan below.  Inside the window the distances are evaluated with numpy's float64 arithmetic
+// directly -- no float32 stage, no staging in shared memory: ~100 instructions per (pedestrian, item) instead of ~1,300.
+//
 // Why the bracket is a superset: coordinates are taken relative to the item's centre c in float64 and rounded once to
 // float32, |x~ - (x - c)| <= 2^-24 |x - c|; with M >= every |component| involved (M = max(cutoff, ring extent), per item,
 // computed at upload) a difference carries <= 3.1 * 2^-24 M and the squared distance <= 42 * 2^-24 M^2 =: Delta of
@@ -231,6 +241,7 @@ struct SegArgs {
     const float* tol;               // [count] float32 bracket width of the two-stage nearest-point search
     const int* chunk_first;         // [count] first entry of the item's pruning chunks in `chunk`, or -1 (may be null)
     const float4* chunk;            // two float4 per chunk: (a_x, a_y, u_x, u_y), (1/|u|^2, deviation, -, -), centre-relative
+    const float4* chord0;           // [count] two float4 per item: (a_x, a_y, u_x, u_y), (1/|u|^2, E, P-1, 1/(P-1)); may be null
     CellGrid grid;
     const int* cell_start;
     const int* cell_item;
@@ -241,6 +252,7 @@ struct SegArgs {
     double2* f_out;                 // [n]
     int n_groups;                   // ceil(n / 32) pedestrian groups
     int* work_counter;              // persistent mode: next group to hand out (zeroed before the launch); null: one CTA per group
+    unsigned long long* eval_count; // optional [2]: (pedestrian, item) pairs inside the cutoff, sum of their point counts
     long long* emit;                // optional [capacity][3]
     unsigned long long* emit_count;
     long long emit_capacity;
@@ -273,10 +285,11 @@ __device__ __forceinline__ double2 segment_force(const SegArgs& a, double px, do
         const double Dv = (Dn == 0.0) ? 1.0 : Dn;
         const double tx = __ddiv_rn(Dx, Dv), ty = __ddiv_rn(Dy, Dv);
         const double nx = __dmul_rn(ty, -1.0), ny = tx;
-        double th = __dsub_rn(atan2(ey, ex), atan2(ty, tx));                 // stateutils.py:104-112
-        const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
-        if (th > PI) th = __dsub_rn(th, TWO_PI);
-        if (th < -PI) th = __dadd_rn(th, TWO_PI);
+        // stateutils.py:104-112: angle(e) - angle(t) wrapped once into [-pi, pi] == atan2(t x e, t . e): one atan2 instead
+        // of two (equal to the reference's difference to a few ulp; exactly 0 when e == t, e.g. a standing pedestrian
+        // before a static obstacle, so sign(theta') keeps the reference's value there)
+        double th = atan2(__dsub_rn(__dmul_rn(tx, ey), __dmul_rn(ty, ex)), __dadd_rn(__dmul_rn(tx, ex), __dmul_rn(ty, ey)));
+        if (Dn == 0.0 || nrm == 0.0) th = __dsub_rn(atan2(ey, ex), atan2(ty, tx));   // zero vectors: numpy's atan2(0, 0) = 0 terms
         const double B = __dmul_rn(a.mp.gamma, Dn);
         th = __dadd_rn(th, __dmul_rn(B, -a.mp.epsilon));
         const double base = __ddiv_rn(__dmul_rn(-1.0, dl), B);
@@ -311,8 +324,13 @@ constexpr int K2_PRUNE_CHUNK = 16;      // points per pruning chunk (chord + dev
 constexpr int K2_PRUNE_MAX = K2_CHUNK / K2_PRUNE_CHUNK;      // chunk tables cover items that fit one staging pass
 constexpr float K2_FAR = 1.0e18f;       // pad value: d2 = 2e36, finite, never a candidate
 
-// smallest squared distance over sp[q0 .. q1) (q0, q1 multiples of 4)
-__device__ __forceinline__ float scan_min(const float2* __restrict__ sp, int q0, int q1, float pxf, float pyf, float m1) {
+// One pass over sp[q0 .. q1) (q0, q1 multiples of 4; base0 = global index of sp[0]): keeps the running minimum m1 of the
+// squared distances and an index window [lo, hi] that contains EVERY point with d2 <= (final m1) + tol.  Invariant: a
+// point enters the window when it is within tol of the running minimum (which only decreases, so nothing that ends within
+// tol of the final minimum is ever skipped); the window restarts only when a group's minimum undercuts the running one
+// by more than tol -- everything seen before is then > final minimum + tol.
+__device__ __forceinline__ void scan_pass(const float2* __restrict__ sp, int q0, int q1, float pxf, float pyf, float tol,
+                                          int base0, float& m1, int& lo, int& hi) {
 #pragma unroll 2
     for (int q = q0; q < q1; q += 4) {
         const float4 A = *reinterpret_cast<const float4*>(&sp[q]);
@@ -321,23 +339,11 @@ __device__ __forceinline__ float scan_min(const float2* __restrict__ sp, int q0,
         const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
         const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
         const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
-        m1 = fminf(fminf(m1, d0), fminf(d1, fminf(d2, d3)));
-    }
-    return m1;
-}
-
-// index window [lo, hi] (global point indices, base = index of sp[0]) of the points with d2 <= thr in sp[q0 .. q1)
-__device__ __forceinline__ void scan_window(const float2* __restrict__ sp, int q0, int q1, float pxf, float pyf, float thr,
-                                            int base0, int& lo, int& hi) {
-#pragma unroll 2
-    for (int q = q0; q < q1; q += 4) {
-        const float4 A = *reinterpret_cast<const float4*>(&sp[q]);
-        const float4 B = *reinterpret_cast<const float4*>(&sp[q + 2]);
-        const float ax = pxf - A.x, ay = pyf - A.y, bx = pxf - A.z, by = pyf - A.w;
-        const float cx = pxf - B.x, cy = pyf - B.y, ex = pxf - B.z, ey = pyf - B.w;
-        const float d0 = fmaf(ax, ax, ay * ay), d1 = fmaf(bx, bx, by * by);
-        const float d2 = fmaf(cx, cx, cy * cy), d3 = fmaf(ex, ex, ey * ey);
-        if (fminf(fminf(d0, d1), fminf(d2, d3)) <= thr) {
+        const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+        if (m4 <= m1 + tol) {
+            if (m4 < m1 - tol) { lo = 0x7fffffff; hi = -1; }
+            m1 = fminf(m1, m4);
+            const float thr = m1 + tol;
             const int base = base0 + q;
             if (d0 <= thr) { lo = min(lo, base); hi = max(hi, base); }
             if (d1 <= thr) { lo = min(lo, base + 1); hi = max(hi, base + 1); }
@@ -451,16 +457,71 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                 const double cxs = __shfl_sync(0xffffffffu, cen_l.x, src), cys = __shfl_sync(0xffffffffu, cen_l.y, src);
                 const double cut = __shfl_sync(0xffffffffu, cut_l, src);
                 const int o0 = __shfl_sync(0xffffffffu, o0_l, src), o1 = __shfl_sync(0xffffffffu, o1_l, src);
-                // the reference's filter, bit for bit: norm(loc - centre) < cutoff  (forces.py:149-150, :222-223)
-                const bool pass = active && (norm2_np(__dsub_rn(px, cxs), __dsub_rn(py, cys)) < cut);
-                if (!__any_sync(0xffffffffu, pass)) continue;
-                // Nearest point, stage 1 (float32, all lanes in lock step over the staged points): the smallest squared
-                // distance m1, then the index window [lo, hi] of every point within tol of it.
-                const float tol = __shfl_sync(0xffffffffu, tol_l, src);
+                // the reference's filter, bit for bit: norm(loc - centre) < cutoff  (forces.py:149-150, :222-223) -- decided in
+                // float32 on centre-relative coordinates unless the squared distance sits within 1e-5 (relative) of cutoff^2,
+                // 40x the float32 evaluation error; only that margin takes the float64 test
                 const float pxf = (float)(px - cxs), pyf = (float)(py - cys);
+                bool pass;
+                {
+                    const float cutf = (float)cut, c2 = cutf * cutf, d2f = fmaf(pxf, pxf, pyf * pyf);
+                    if (cutf > 0.0f && d2f < c2 * 0.99999f) pass = true;
+                    else if (cutf > 0.0f && d2f > c2 * 1.00001f) pass = false;
+                    else pass = norm2_np(__dsub_rn(px, cxs), __dsub_rn(py, cys)) < cut;
+                    pass = pass && active;
+                }
+                if (!__any_sync(0xffffffffu, pass)) continue;
+                const int np = o1 - o0;
+                if (a.eval_count) {
+                    const int hits = __popc(__ballot_sync(0xffffffffu, pass));
+                    if (lane == 0) {
+                        atomicAdd(a.eval_count, (unsigned long long)hits);
+                        atomicAdd(a.eval_count + 1, (unsigned long long)hits * (unsigned long long)np);
+                    }
+                }
+                int best_q = o0;
+                // ---- direct path: index window around the projection on the item's chord (header), float64 inside it
+                bool direct = false;
+                int k_lo = 0, k_cnt = 0;
+                if (a.chord0) {
+                    const float4 c0 = __ldg(&a.chord0[2 * s]), c1 = __ldg(&a.chord0[2 * s + 1]);
+                    const float wx = pxf - c0.x, wy = pyf - c0.y, nm1 = c1.z;
+                    const float kap = fmaf(wx, c0.z, wy * c0.w) * c1.x * nm1;
+                    const float ks = fminf(fmaxf(rintf(kap), 0.0f), nm1);
+                    const float fr = ks * c1.w;
+                    const float gx = fmaf(-fr, c0.z, wx), gy = fmaf(-fr, c0.w, wy);
+                    const float Ds = sqrtf(fmaf(gx, gx, gy * gy));
+                    const float del = kap - ks;
+                    const float Q = 4.0f * c1.y * (Ds + c1.y) * (nm1 * nm1) * c1.x;
+                    const float rho = fmaf(sqrtf(fmaf(del, del, Q)), 1.001f, 0.004f);
+                    const float lo_f = fminf(fmaxf(ceilf(kap - rho), 0.0f), ks), hi_f = fmaxf(fminf(floorf(kap + rho), nm1), ks);
+                    const bool ok = (c1.x > 0.0f || nm1 == 0.0f) && (hi_f - lo_f) < 8.0f;          // NaN / inf -> false
+                    direct = __all_sync(0xffffffffu, !pass || ok);
+                    if (direct && pass) {
+                        k_lo = (int)lo_f;
+                        k_cnt = (int)hi_f - k_lo + 1;
+                    }
+                }
+                if (direct) {
+                    double best = __longlong_as_double(0x7ff0000000000000LL);
+                    for (int j = 0; __any_sync(0xffffffffu, j < k_cnt); ++j) {
+                        if (j < k_cnt) {
+                            const int q = o0 + k_lo + j;
+                            const double2 P = a.point[q];
+                            const double d = norm2_np(__dsub_rn(px, P.x), __dsub_rn(py, P.y));
+                            if (d < best) {                 // strict: first index on exact ties (forces.py:154, :228)
+                                best = d;
+                                best_q = q;
+                            }
+                        }
+                    }
+                    if (pass && !(best < __longlong_as_double(0x7ff0000000000000LL)))
+                        best_q = exact_argmin(a.point, o0, o1, px, py);            // non-finite coordinates: full scan
+                } else {
+                // Nearest point, stage 1 (float32, all lanes in lock step over the staged points): the smallest squared
+                // distance m1 and the index window [lo, hi] of every point within tol of it, in one pass.
+                const float tol = __shfl_sync(0xffffffffu, tol_l, src);
                 float m1 = 3.0e38f;
                 int lo = 0x7fffffff, hi = -1;
-                const int np = o1 - o0;
                 const int cf = __shfl_sync(0xffffffffu, cf_l, src);
                 if (cf >= 0) {
                     // Pruned search (items with a chunk table: 48 .. 256 points).  Every run of 16 points is covered by
@@ -515,31 +576,21 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                     __syncwarp();
                     for (unsigned mm = need; mm; mm &= mm - 1) {
                         const int q0 = (__ffs(mm) - 1) * K2_PRUNE_CHUNK;
-                        m1 = scan_min(sp[wid], q0, q0 + K2_PRUNE_CHUNK, pxf, pyf, m1);
-                    }
-                    const float thr = m1 + tol;
-                    for (unsigned mm = need; mm; mm &= mm - 1) {
-                        const int q0 = (__ffs(mm) - 1) * K2_PRUNE_CHUNK;
-                        scan_window(sp[wid], q0, q0 + K2_PRUNE_CHUNK, pxf, pyf, thr, o0, lo, hi);
+                        scan_pass(sp[wid], q0, q0 + K2_PRUNE_CHUNK, pxf, pyf, tol, o0, m1, lo, hi);
                     }
                 } else {
-                    const bool one_chunk = np <= K2_CHUNK;
-                    for (int phase = 0; phase < 2; ++phase) {
-                        const float thr = m1 + tol;
-                        for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
-                            const int m = min(K2_CHUNK, o1 - c0);
-                            const int m4 = (m + 3) & ~3;
-                            if (phase == 0 || !one_chunk) stage_points(sp[wid], a.point, c0, m, 4, cxs, cys, lane);
-                            if (phase == 0) m1 = scan_min(sp[wid], 0, m4, pxf, pyf, m1);
-                            else scan_window(sp[wid], 0, m4, pxf, pyf, thr, c0, lo, hi);
-                        }
+                    for (int c0 = o0; c0 < o1; c0 += K2_CHUNK) {
+                        const int m = min(K2_CHUNK, o1 - c0);
+                        stage_points(sp[wid], a.point, c0, m, 4, cxs, cys, lane);
+                        scan_pass(sp[wid], 0, (m + 3) & ~3, pxf, pyf, tol, c0, m1, lo, hi);
                     }
                 }
-                int best_q = o0;
-                if (pass) {
+                if (pass)
                     // stage 2: numpy's exact arithmetic over the bracket (first index on exact ties, forces.py:154, :228)
                     best_q = (hi < lo) ? exact_argmin(a.point, o0, o1, px, py)        // non-finite coordinates: full scan
                                        : exact_argmin(a.point, lo, min(hi + 1, o1), px, py);
+                }
+                if (pass) {
                     const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
                                                           KIND ? a.velocity[s] : make_double2(0.0, 0.0));
                     fx = __dadd_rn(fx, f.x);

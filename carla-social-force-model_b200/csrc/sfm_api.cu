@@ -92,11 +92,11 @@ struct SetStorage {
     DevBuf<unsigned> key, key_tmp;
     DevBuf<float> tol;
     DevBuf<int> chunk_first;
-    DevBuf<float4> chunk;
+    DevBuf<float4> chunk, chord0;
     double threshold = 0.0;        // perception_threshold the cutoffs / bracket widths / grid of this set were built from
     bool stale = false;            // sfm_set_params changed that threshold afterwards: the set must be uploaded again
     void release() {
-        tol.release(); chunk_first.release(); chunk.release();
+        tol.release(); chunk_first.release(); chunk.release(); chord0.release();
         center.release(); velocity.release(); point.release(); cutoff.release(); offset.release();
         cell_start.release(); cell_item.release(); val_tmp.release(); key.release(); key_tmp.release();
     }
@@ -128,6 +128,10 @@ struct sfm_ctx {
     DevBuf<double2> f_border, f_static, f_dynamic;
     DevBuf<double> f_total, f_accel, f_ped;
     DevBuf<double> raw_a, raw_b, raw_c, raw_d, raw_e;   // upload / download scratch
+    DevBuf<uint8_t> rec_bytes;      // sfm_tick_records: the caller's AoS table as uploaded
+    DevBuf<double4> rec_out;        //                   (new velocity, target speed) per pedestrian
+    double4* rec_pinned = nullptr;  //                   pinned landing zone of rec_out
+    size_t rec_pinned_cap = 0;
     DevBuf<uint8_t> raw_mode;
     // pedestrian binning
     CellGrid ped_grid{};
@@ -156,6 +160,7 @@ struct sfm_ctx {
     bool k2_persist_multi = false;  // SFM_K2_PERSIST_MULTI=1: persistent mode on multi-rank contexts too
     DevBuf<int> k2_counter;
     bool k2_prune = true;           // SFM_K2_PRUNE=0: cell-list kernels scan every point of an item (no chunk bounds)
+    bool k2_direct = true;          // SFM_K2_DIRECT=0: no chord-projection windows (every item takes the float32 scan)
     int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
                                     // cell-list kernels stay co-resident on every SM (see step_begin)
     DevBuf<long long> facc;         // [world * rows_pad][4] fixed-point force accumulators + poison counter
@@ -285,6 +290,39 @@ __global__ void unpack_state(int64_t n, const double4* locr, const double4* vels
         const double4 V = vels[i];
         vel[3 * i] = V.x; vel[3 * i + 1] = V.y; vel[3 * i + 2] = V.z;
     }
+}
+
+// ---- the reference's AoS pedestrian table (pedestrian_state.py:17-19, 132-byte records) on the device ----------------
+// Fields sit at 4-byte-aligned offsets of a 4-byte-aligned stride: float64 values are read as two 32-bit halves.
+__device__ __forceinline__ double load_f64_u32(const uint8_t* p) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    return __hiloint2double((int)q[1], (int)q[0]);
+}
+
+struct RecordLayout {
+    int64_t stride, off_loc, off_vel, off_wp, off_radius, off_speed;
+};
+
+// records -> master state.  take_speed: the target speed comes from the record too (host-managed modes); otherwise the
+// device keeps its own (K4a applies the mode machines' speed).
+__global__ void unpack_records(int64_t n, const uint8_t* rec, RecordLayout L, int take_speed, double4* locr, double4* vels,
+                               double2* wp, double* next_wp3) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* r = rec + i * L.stride;
+    locr[i] = make_double4(load_f64_u32(r + L.off_loc), load_f64_u32(r + L.off_loc + 8), load_f64_u32(r + L.off_loc + 16),
+                           load_f64_u32(r + L.off_radius));
+    const double speed = take_speed ? load_f64_u32(r + L.off_speed) : vels[i].w;
+    vels[i] = make_double4(load_f64_u32(r + L.off_vel), load_f64_u32(r + L.off_vel + 8), load_f64_u32(r + L.off_vel + 16), speed);
+    const double wx = load_f64_u32(r + L.off_wp), wy = load_f64_u32(r + L.off_wp + 8), wz = load_f64_u32(r + L.off_wp + 16);
+    wp[i] = make_double2(wx, wy);
+    next_wp3[3 * i] = wx; next_wp3[3 * i + 1] = wy; next_wp3[3 * i + 2] = wz;
+}
+
+// (new velocity, target speed the clamp used) per pedestrian, one 32-byte item each: the D2H payload of the record tick
+__global__ void pack_velocities(int64_t n, const double4* vels, double4* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = vels[i];
 }
 
 __global__ void expand_xy(int64_t n, const double2* f, double* out) {
@@ -641,6 +679,32 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
             chunk.push_back(make_float4(inv, devf, 0.0f, 0.0f));
         }
     }
+    // Whole-item chord records of the direct path (k2_cells.cuh): first point a, chord u to the last point, 1/|u|^2, and E >=
+    // the largest distance of any point from its uniformly spaced model position a + k/(P-1) u -- measured in float64
+    // against the float32-rounded a and u the kernel will use, plus the pedestrian's own float32 rounding (4 * 2^-24 * M).
+    std::vector<float4> chord0(2 * (size_t)count);
+    for (int64_t i = 0; i < count; ++i) {
+        const int64_t b = offsets[i], e = offsets[i + 1], P = e - b;
+        const double cx = centers[2 * i], cy = centers[2 * i + 1];
+        const float ax = (float)(points[2 * b] - cx), ay = (float)(points[2 * b + 1] - cy);
+        const float ux = (float)(points[2 * (e - 1)] - points[2 * b]), uy = (float)(points[2 * (e - 1) + 1] - points[2 * b + 1]);
+        const double uu = (double)ux * ux + (double)uy * uy;
+        double M = std::isfinite(cut[i]) ? std::fabs(cut[i]) : 0.0, E = 0.0;
+        for (int64_t q = b; q < e; ++q) {
+            const double rx = points[2 * q] - cx, ry = points[2 * q + 1] - cy;
+            M = std::max(M, std::max(std::fabs(rx), std::fabs(ry)));
+            const double f = P > 1 ? (double)(q - b) / (double)(P - 1) : 0.0;
+            E = std::max(E, std::hypot(rx - ((double)ax + f * ux), ry - ((double)ay + f * uy)));
+        }
+        const double Em = E * 1.0001 + 8.0 * std::ldexp(1.0, -24) * M;
+        float inv = (uu > 0.0 && P > 1) ? (float)(1.0 / uu) : 0.0f;
+        float Ef = std::nextafter((float)Em, INFINITY);
+        if (!std::isfinite(Em) || !std::isfinite((double)inv) || !std::isfinite(cut[i]) || P > (1 << 22)) { inv = 0.0f; Ef = 0.0f; }
+        const float nm1 = (inv > 0.0f) ? (float)(P - 1) : (P == 1 && std::isfinite(Em) ? 0.0f : 1.0f);   // 1 with inv = 0: direct path off
+        chord0[2 * i] = make_float4(ax, ay, ux, uy);
+        chord0[2 * i + 1] = make_float4(inv, Ef, nm1, nm1 > 0.0f ? 1.0f / nm1 : 0.0f);
+    }
+    SFM_TRY(st.chord0.ensure(chord0.size()));
     SFM_TRY(st.chunk_first.ensure(count));
     SFM_TRY(st.chunk.ensure(std::max<size_t>(chunk.size(), 1)));
     // synchronous copies from pageable host memory: the inputs may be temporaries of the caller
@@ -655,6 +719,8 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
     SFM_CUDA(cudaMemcpy(st.chunk_first.p, chunk_first.data(), sizeof(int) * count, cudaMemcpyHostToDevice));
     if (!chunk.empty())
         SFM_CUDA(cudaMemcpy(st.chunk.p, chunk.data(), sizeof(float4) * chunk.size(), cudaMemcpyHostToDevice));
+    SFM_CUDA(cudaMemcpy(st.chord0.p, chord0.data(), sizeof(float4) * chord0.size(), cudaMemcpyHostToDevice));
+    s.chord0 = st.chord0.p;
     s.tol = st.tol.p;
     s.chunk_first = st.chunk_first.p;
     s.chunk = st.chunk.p;
@@ -666,7 +732,7 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
 }
 
 int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaStream_t strm = nullptr,
-                    bool persistent = false) {
+                    bool persistent = false, unsigned long long* eval_count = nullptr) {
     if (!strm) strm = c->stream;
     SetStorage& st = (cls == SFM_FORCE_BORDER) ? c->borders : (cls == SFM_FORCE_STATIC_OBSTACLE ? c->stat : c->dyn);
     DevBuf<double2>& out = (cls == SFM_FORCE_BORDER) ? c->f_border
@@ -688,11 +754,13 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
     a.locr = c->locr.p; a.vels = c->vels.p; a.mode = c->mode.p; a.perm = c->perm.p; a.n = n;
     a.center = st.s.center; a.cutoff = st.s.cutoff; a.velocity = st.s.velocity; a.offset = st.s.offset;
     a.point = st.s.point; a.tol = st.s.tol; a.chunk_first = c->k2_prune ? st.s.chunk_first : nullptr; a.chunk = st.s.chunk;
+    a.chord0 = c->k2_direct ? st.s.chord0 : nullptr;
     a.grid = st.s.grid; a.cell_start = st.s.cell_start; a.cell_item = st.s.cell_item;
     a.mp = make_moussaid_d(cls == SFM_FORCE_DYNAMIC_OBSTACLE ? c->params.dynamic_obs : c->params.static_obs);
     a.border_a = c->params.border_a; a.border_b = c->params.border_b;
     a.use_radius = c->params.use_ped_radius;
     a.f_out = out.p;
+    a.eval_count = eval_count;
     if (emit) {
         a.emit = c->emit.p; a.emit_count = c->emit_count.p; a.emit_capacity = emit_capacity;
     }
@@ -826,6 +894,43 @@ int compact_column(sfm_ctx* c, DevBuf<T>& col, DevBuf<T>& scratch, int64_t n, co
 
 }  // namespace
 
+namespace {
+
+int tick_modes_impl(sfm_ctx* c, double sim_time) {
+    if (!c->have_mm) return fail("sfm_set_mode_machines must be called first");
+    c->sim_time = sim_time;
+    if (c->n == 0) return 0;
+    SFM_TRY(ensure_life_counters(c));
+    ModeTickArgs a{};
+    a.n = c->n; a.locr = c->locr.p; a.vels = c->vels.p; a.wp = c->wp.p; a.mode = c->mode.p;
+    a.mm = mode_machines(c);
+    if (c->have_vehicles) {                      // device-resident vehicle set (sfm_set_vehicles)
+        a.tr.count = (int)c->dyn.s.count; a.tr.center = c->dyn.s.center; a.tr.velocity = c->dyn.s.velocity;
+    } else {
+        a.tr.count = c->tr_count; a.tr.center = c->tr_center.p; a.tr.velocity = c->tr_vel.p;
+    }
+    a.tr.ext0_x = c->tr_ext0[0]; a.tr.ext0_y = c->tr_ext0[1];
+    a.sim_time = sim_time; a.counters = c->life_counters.p;
+    SFM_TRY(c->check_list.ensure(c->n + 1));
+    SFM_TRY(c->check_blocked.ensure(c->n));
+    a.check_list = c->check_list.p + 1; a.check_count = c->check_list.p; a.blocked = c->check_blocked.p;
+    SpanGuard g(c, ST_LIFECYCLE);
+    SFM_CUDA(cudaMemsetAsync(a.check_count, 0, sizeof(int), c->stream));
+    SFM_CUDA(cudaMemsetAsync(a.blocked, 0, c->n, c->stream));
+    k4_tick_modes<<<cdiv(c->n, K4_THREADS), K4_THREADS, 0, c->stream>>>(a);
+    c->launches += 1;
+    if (a.tr.count > 0) {
+        const int gx = (int)std::min<int64_t>(cdiv(c->n, K4_THREADS), 148 * 4);
+        k4_gap_acceptance<<<dim3(gx, cdiv(a.tr.count, K4_VEH_TILE)), K4_THREADS, 0, c->stream>>>(a);
+        k4_gap_commit<<<gx, K4_THREADS, 0, c->stream>>>(a);
+        c->launches += 2;
+    }
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
 int sfm_abi_version(void) { return SFM_ABI_VERSION; }
@@ -869,6 +974,7 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_K1_SMEM_PAD")) c->k1_smem_pad = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("SFM_K1_FIRST")) c->k1_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PRUNE")) c->k2_prune = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SFM_K2_DIRECT")) c->k2_direct = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_GRAPH")) c->use_graph = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PERSIST")) c->k2_persist = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("SFM_K2_PERSIST_MULTI")) c->k2_persist_multi = std::atoi(env) != 0;
@@ -896,6 +1002,8 @@ int sfm_destroy(sfm_ctx* c) {
     c->f_border.release(); c->f_static.release(); c->f_dynamic.release();
     c->f_total.release(); c->f_accel.release(); c->f_ped.release();
     c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
+    c->rec_bytes.release(); c->rec_out.release();
+    if (c->rec_pinned) cudaFreeHost(c->rec_pinned);
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
     c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release(); c->facc.release();
     if (c->p2p)
@@ -1125,7 +1233,7 @@ int sfm_enumerate_pairs(sfm_ctx* c, int cls, int64_t capacity, int64_t* triplets
     *count = 0;
     if (c->n == 0) return 0;
     SFM_TRY(c->emit.ensure((size_t)3 * std::max<int64_t>(capacity, 1)));
-    SFM_TRY(c->emit_count.ensure(1));
+    SFM_TRY(c->emit_count.ensure(2));
     SFM_CUDA(cudaMemsetAsync(c->emit_count.p, 0, sizeof(unsigned long long), c->stream));
     SFM_TRY(launch_segments(c, cls, true, capacity));
     unsigned long long total = 0;
@@ -1134,6 +1242,24 @@ int sfm_enumerate_pairs(sfm_ctx* c, int cls, int64_t capacity, int64_t* triplets
     *count = (int64_t)total;
     const int64_t got = std::min<int64_t>((int64_t)total, capacity);
     if (got > 0) SFM_CUDA(cudaMemcpy(triplets, c->emit.p, sizeof(long long) * 3 * got, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int sfm_count_point_evaluations(sfm_ctx* c, int cls, int64_t* pairs, int64_t* point_evaluations) {
+    SFM_TRY(check_ctx(c));
+    if (cls != SFM_FORCE_BORDER && cls != SFM_FORCE_STATIC_OBSTACLE && cls != SFM_FORCE_DYNAMIC_OBSTACLE)
+        return fail("only the cutoff-limited classes evaluate point sets");
+    if (!pairs || !point_evaluations) return fail("null pointer");
+    *pairs = *point_evaluations = 0;
+    if (c->n == 0) return 0;
+    SFM_TRY(c->emit_count.ensure(2));
+    SFM_CUDA(cudaMemsetAsync(c->emit_count.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    SFM_TRY(launch_segments(c, cls, false, 0, nullptr, false, c->emit_count.p));
+    unsigned long long v[2] = {0, 0};
+    SFM_CUDA(cudaMemcpyAsync(v, c->emit_count.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    *pairs = (int64_t)v[0];
+    *point_evaluations = (int64_t)v[1];
     return 0;
 }
 
@@ -1221,6 +1347,84 @@ int sfm_tick_host(sfm_ctx* c, int64_t n, const double* loc, const double* vel, d
         SFM_CUDA(cudaMemcpyAsync(new_loc, c->raw_a.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     SFM_CUDA(cudaMemcpyAsync(new_vel, c->raw_b.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_tick_records(sfm_ctx* c, int64_t n, void* records, int64_t stride, const int64_t* offsets5, double sim_time,
+                     int tick_modes, int64_t* counters4) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (c->world > 1) return fail("the record tick serves the single-process drop-in (one rank)");
+    if (n == 0) return 0;
+    if (!records || !offsets5) return fail("null pointer");
+    RecordLayout L{stride, offsets5[0], offsets5[1], offsets5[2], offsets5[3], offsets5[4]};
+    const int64_t offs[5] = {L.off_loc, L.off_vel, L.off_wp, L.off_radius, L.off_speed};
+    const int64_t widths[5] = {24, 24, 24, 8, 8};
+    if (stride <= 0 || stride % 4 != 0 || (reinterpret_cast<uintptr_t>(records) & 3u) != 0)
+        return fail("records must be 4-byte aligned with a positive stride that is a multiple of 4");
+    for (int k = 0; k < 5; ++k)
+        if (offs[k] < 0 || offs[k] % 4 != 0 || offs[k] + widths[k] > stride) return fail("bad field offset");
+    if (tick_modes && !c->have_mm) return fail("sfm_set_mode_machines must be called first");
+    const size_t span = (size_t)(n - 1) * stride + (size_t)std::max<int64_t>(offs[0] + 24, std::max<int64_t>(offs[1] + 24,
+                            std::max<int64_t>(offs[2] + 24, std::max<int64_t>(offs[3] + 8, offs[4] + 8))));
+    SFM_TRY(c->rec_bytes.ensure(span + 8));
+    SFM_TRY(c->rec_out.ensure(n));
+    if (c->rec_pinned_cap < (size_t)n) {
+        if (c->rec_pinned) SFM_CUDA(cudaFreeHost(c->rec_pinned));
+        c->rec_pinned = nullptr;
+        c->rec_pinned_cap = 0;
+        SFM_CUDA(cudaMallocHost(&c->rec_pinned, sizeof(double4) * ((size_t)n + n / 8 + 256)));
+        c->rec_pinned_cap = (size_t)n + n / 8 + 256;
+    }
+    // 1. the table as it lies in host memory (one copy; the unused columns ride along), unpacked on the device
+    SFM_CUDA(cudaMemcpyAsync(c->rec_bytes.p, records, span, cudaMemcpyHostToDevice, c->stream));
+    unpack_records<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->rec_bytes.p, L, tick_modes ? 0 : 1, c->locr.p, c->vels.p,
+                                                         c->wp.p, c->next_wp3.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->staged = false;
+    c->perm_valid = false;
+    // 2. pedestrian_simulation.py:63-73 on the device: apply_current_mode, the machines' tick, gap acceptance
+    if (tick_modes) SFM_TRY(tick_modes_impl(c, sim_time));
+    // 3. pedestrian_simulation.py:81-83: forces, sum, new velocities (positions are the simulator's business)
+    SFM_TRY(step_once(c, true, false, false));
+    // 4. new velocities (+ the target speed of this tick) back into the table: state[['id','vel']] is a view of it
+    pack_velocities<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vels.p, c->rec_out.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    SFM_CUDA(cudaMemcpyAsync(c->rec_pinned, c->rec_out.p, sizeof(double4) * n, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    if (counters4 && c->life_counters.p)
+        SFM_CUDA(cudaMemcpyAsync(cnt, c->life_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    uint8_t* base = static_cast<uint8_t*>(records);
+    for (int64_t i = 0; i < n; ++i) {
+        const double4 v = c->rec_pinned[i];
+        uint8_t* r = base + i * stride;
+        std::memcpy(r + L.off_vel, &v.x, 24);
+        if (tick_modes) std::memcpy(r + L.off_speed, &v.w, 8);       // apply_current_mode (pedestrian_state.py:94-95)
+    }
+    if (counters4) for (int k = 0; k < 4; ++k) counters4[k] = (int64_t)cnt[k];
+    return 0;
+}
+
+int sfm_host_column_gather(const void* records, int64_t stride, int64_t offset, int64_t width, int64_t n, void* packed) {
+    if (n < 0 || width <= 0 || (n > 0 && (!records || !packed))) return fail("bad column description");
+    const uint8_t* base = static_cast<const uint8_t*>(records) + offset;
+    uint8_t* out = static_cast<uint8_t*>(packed);
+    for (int64_t i = 0; i < n; ++i) std::memcpy(out + i * width, base + i * stride, (size_t)width);
+    return 0;
+}
+
+int sfm_host_column_equal(const void* records, int64_t stride, int64_t offset, int64_t width, int64_t n,
+                          const void* packed, int* equal) {
+    if (!equal || n < 0 || width <= 0 || (n > 0 && (!records || !packed))) return fail("bad column description");
+    const uint8_t* base = static_cast<const uint8_t*>(records) + offset;
+    const uint8_t* want = static_cast<const uint8_t*>(packed);
+    *equal = 1;
+    for (int64_t i = 0; i < n; ++i)
+        if (std::memcmp(base + i * stride, want + i * width, (size_t)width) != 0) { *equal = 0; break; }
     return 0;
 }
 
@@ -1325,36 +1529,7 @@ int sfm_set_traffic(sfm_ctx* c, int64_t n_vehicles, const double* centers, const
 
 int sfm_tick_modes(sfm_ctx* c, double sim_time) {
     SFM_TRY(check_ctx(c));
-    if (!c->have_mm) return fail("sfm_set_mode_machines must be called first");
-    c->sim_time = sim_time;
-    if (c->n == 0) return 0;
-    SFM_TRY(ensure_life_counters(c));
-    ModeTickArgs a{};
-    a.n = c->n; a.locr = c->locr.p; a.vels = c->vels.p; a.wp = c->wp.p; a.mode = c->mode.p;
-    a.mm = mode_machines(c);
-    if (c->have_vehicles) {                      // device-resident vehicle set (sfm_set_vehicles)
-        a.tr.count = (int)c->dyn.s.count; a.tr.center = c->dyn.s.center; a.tr.velocity = c->dyn.s.velocity;
-    } else {
-        a.tr.count = c->tr_count; a.tr.center = c->tr_center.p; a.tr.velocity = c->tr_vel.p;
-    }
-    a.tr.ext0_x = c->tr_ext0[0]; a.tr.ext0_y = c->tr_ext0[1];
-    a.sim_time = sim_time; a.counters = c->life_counters.p;
-    SFM_TRY(c->check_list.ensure(c->n + 1));
-    SFM_TRY(c->check_blocked.ensure(c->n));
-    a.check_list = c->check_list.p + 1; a.check_count = c->check_list.p; a.blocked = c->check_blocked.p;
-    SpanGuard g(c, ST_LIFECYCLE);
-    SFM_CUDA(cudaMemsetAsync(a.check_count, 0, sizeof(int), c->stream));
-    SFM_CUDA(cudaMemsetAsync(a.blocked, 0, c->n, c->stream));
-    k4_tick_modes<<<cdiv(c->n, K4_THREADS), K4_THREADS, 0, c->stream>>>(a);
-    c->launches += 1;
-    if (a.tr.count > 0) {
-        const int gx = (int)std::min<int64_t>(cdiv(c->n, K4_THREADS), 148 * 4);
-        k4_gap_acceptance<<<dim3(gx, cdiv(a.tr.count, K4_VEH_TILE)), K4_THREADS, 0, c->stream>>>(a);
-        k4_gap_commit<<<gx, K4_THREADS, 0, c->stream>>>(a);
-        c->launches += 2;
-    }
-    SFM_CUDA(cudaGetLastError());
-    return 0;
+    return tick_modes_impl(c, sim_time);
 }
 
 int sfm_download_modes(sfm_ctx* c, int64_t n, uint8_t* mode, double* mode_speed, double* next_mode_time,
@@ -1677,7 +1852,8 @@ int sfm_set_vehicles(sfm_ctx* c, int64_t n_vehicles, const double* centers, cons
     SFM_CUDA(cudaMemcpy(st.tol.p, tol.data(), sizeof(float) * n_vehicles, cudaMemcpyHostToDevice));
     SegmentSet& s = st.s;
     s.tol = st.tol.p;
-    s.chunk_first = nullptr;                       // rings are regenerated every tick: no chunk tables
+    s.chunk_first = nullptr;                       // rings are regenerated every tick: no chunk / chord tables
+    s.chord0 = nullptr;
     s.center = st.center.p; s.cutoff = st.cutoff.p; s.velocity = st.velocity.p; s.offset = st.offset.p;
     s.point = st.point.p; s.n_points = np;
     c->veh_size_factor = size_factor;

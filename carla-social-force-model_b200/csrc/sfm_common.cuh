@@ -56,6 +56,7 @@ struct SegmentSet {
     float* tol = nullptr;       // [count]  float32 bracket width of the two-stage nearest-point search (k2_cells.cuh)
     int* chunk_first = nullptr; // [count]  first pruning chunk of the item in `chunk`, -1 = none (null: no tables)
     float4* chunk = nullptr;    // two float4 per chunk of 16 points: chord + deviation (k2_cells.cuh)
+    float4* chord0 = nullptr;   // two float4 per item: whole-item chord + uniform-spacing deviation (k2_cells.cuh, direct path)
     CellGrid grid{};
     int* cell_start = nullptr;  // [nx * ny + 1]
     int* cell_item = nullptr;   // [count]  set items ordered by (cell, index)

@@ -2,8 +2,20 @@
 
 ``tick`` keeps the reference sequence (pedestrian_simulation.py:57-83): mode bookkeeping -> gap acceptance -> recording
 -> force sum -> new velocities.  The arithmetic (all enabled forces, their sum in dict order, the Euler velocity update
-and the speed clamp) is one fused device pass (``sfm_step`` with ``integrate_positions = 0``); as in the reference,
-positions are left to the simulator that consumes the velocities (run_simulation.py:77-87).
+and the speed clamp) is one fused device pass; as in the reference, positions are left to the simulator that consumes the
+velocities (run_simulation.py:77-87).
+
+Three ways through ``tick``, chosen per call:
+
+* **resident** (every ``mode`` entry a stock ``PedModeManager``, the stock force dict, ``record_states=False``): the
+  parameters, the point sets, the pedestrian rows and the mode machines stay on the device between ticks; one
+  ``sfm_tick_records`` call hands the structured ``PedState.state`` array over as it lies in memory, runs the mode
+  bookkeeping (K4a), the forces and the velocity update there and writes the new velocities back into the table.  No
+  interpreter loop over pedestrians anywhere; the host objects are refreshed only on ticks on which a machine changed mode.
+* **columnar** (same, with ``record_states=True``): the machines tick as array operations on their ``ModeTable``, gap
+  acceptance runs on the host for the pedestrians at the kerb, the snapshot is taken where the reference takes it (:76),
+  then the same device call without the mode step.
+* **generic** (anything else in the ``mode`` column or a hand-composed force dict): the reference's per-object sequence.
 """
 import numpy as np
 
@@ -35,6 +47,8 @@ class PedestrianSimulation:
         self.step_length = step_length
         self.forces = self.init_forces()
         self.new_velocities = None
+        self._dyn_version = 0                       # bumped by update_dynamic_obstacles: the device traffic set is stale
+        self._life_counters = None
 
     def init_forces(self):
         """Ordered dict of the enabled force objects (pedestrian_simulation.py:32-55); order = summation order."""
@@ -62,8 +76,12 @@ class PedestrianSimulation:
         """Do one step in the simulation."""
         if self.peds.state is None or self.peds.size() == 0:
             return
-        # apply_current_mode, then every machine's tick (pedestrian_simulation.py:63-65) -- one pass over the mode objects,
-        # which also yields the uint8 codes the device needs (the two steps are independent per pedestrian)
+        table = self.peds.mode_table()
+        if table is not None and self._fusable() and self._uniform_waiting_time(table):
+            self._tick_table(table, sim_time)
+            return
+        # generic path: apply_current_mode, then every machine's tick (pedestrian_simulation.py:63-65) -- one pass over the
+        # mode objects, which also yields the uint8 codes the device needs
         state = self.peds.state
         n = len(state)
         speeds, codes = np.empty(n), np.empty(n, dtype=np.uint8)
@@ -94,17 +112,16 @@ class PedestrianSimulation:
         else:                                  # hand-composed force dicts: per-class device forces, summed on the host
             self.calculate_new_velocities(sum(f.get_force(self.peds) for f in self.forces.values()))
 
-    def _fusable(self):
-        names = list(self.forces)
-        return all(n in _NATIVE_ORDER and isinstance(f, forces.Force) and f.force_class == _NATIVE_ORDER[n]
-                   for n, f in self.forces.items()) and names == sorted(names, key=_NATIVE_ORDER.get)
+    @staticmethod
+    def _uniform_waiting_time(table):
+        w = table.columns['waiting_time']
+        return bool((w == w[0]).all())
 
-    def _fused_velocities(self):
-        session = get_session()
+    def _bind_device(self, session):
+        """Parameters and point sets of this simulation resident on the device -- uploads only what is not there yet."""
         params = native.params_from_config(self.sfm_config, self.step_length,
                                            enable={name: name in self.forces for name in native.FORCE_CLASSES})
-        session.ctx.set_params(params)
-        session.params_key = None                  # the per-class objects re-bind their (all-enabled) view on next use
+        session.set_params(params)
         for f in self.forces.values():
             empty_set = (isinstance(f, forces.ObstacleForce) and (f.obstacle_locs is None or f.obstacle_locs.size == 0)) \
                 or (isinstance(f, forces.BorderForce) and len(f.borders) == 0)
@@ -114,6 +131,63 @@ class PedestrianSimulation:
                 self._clear_set(session, f.force_class)
             else:
                 f._bind(session)
+
+    def _tick_table(self, table, sim_time):
+        """The resident / columnar paths (module docstring): no interpreter loop over pedestrians."""
+        state = self.peds.state
+        session = get_session()
+        ctx = session.ctx
+        self._bind_device(session)
+        cols = table.columns
+        on_device = not self.record_states                  # the mode bookkeeping of :63-73 runs in K4a
+        if session.resident_table is not table or ctx.n != len(state):
+            ctx.upload_state(*self.peds.device_columns(cols['current_mode']))
+            session.resident_table, session.machines_version, session.traffic_version = table, None, None
+            self._life_counters = None
+        if not on_device:
+            # columnar host path: apply_current_mode, tick, gap acceptance for the pedestrians at the kerb, snapshot
+            state['target_speed'] = cols['target_speed']                                      # :63
+            table.tick(sim_time)                                                               # :64-65
+            waiting = np.nonzero(cols['current_mode'] == PedMode.CHECKING_TRAFFIC)[0]
+            if len(waiting) and self.dyn_obstacles:                                            # :67-73
+                waiting = [r for r in waiting
+                           if check_traffic(state[r], self.dyn_obstacles, self.dyn_obs_vel, self.dyn_obs_extent)]
+            if len(waiting):
+                table.request_crossing(np.asarray(waiting, dtype=np.int64))
+            self.peds.record_current_state(sim_time)                                          # :76
+            if self.dyn_obstacles:
+                self.record_dyn_obstacle_states(sim_time)
+            ctx.update_targets(mode=cols['current_mode'])
+            ctx.tick_records(state, sim_time, tick_modes=False)
+        else:
+            if session.machines_version != table.version:   # a fresh table, or writes through the objects (set_mode)
+                ctx.update_targets(mode=cols['current_mode'])
+                ctx.set_mode_machines(cols['initial_target_speed'], cols['crossing_speed'], cols['crossing_safety_margin'],
+                                      cols['target_speed'], cols['next_mode_time'], float(cols['waiting_time'][0]))
+                session.machines_version = table.version
+            if session.traffic_version != self._dyn_version:
+                centres = [c for c, _ in self.dyn_obstacles]
+                ctx.set_traffic(centres, self.dyn_obs_vel if len(centres) else [], self.dyn_obs_extent if len(centres) else [])
+                session.traffic_version = self._dyn_version
+            before = self._life_counters
+            counters = ctx.tick_records(state, sim_time, tick_modes=True)
+            cols['sim_time'][:] = sim_time
+            if before is None or counters[0] != before[0] or counters[1] != before[1]:
+                m = ctx.download_modes()                    # somebody started crossing or woke up: refresh the host objects
+                cols['current_mode'][:] = m['mode']
+                cols['target_speed'][:] = m['mode_target_speed']
+                cols['next_mode_time'][:] = m['next_mode_time']
+            self._life_counters = counters
+        self.new_velocities = state[['id', 'vel']]          # a view: the device call wrote state['vel'] (SURVEY 3.2)
+
+    def _fusable(self):
+        names = list(self.forces)
+        return all(n in _NATIVE_ORDER and isinstance(f, forces.Force) and f.force_class == _NATIVE_ORDER[n]
+                   for n, f in self.forces.items()) and names == sorted(names, key=_NATIVE_ORDER.get)
+
+    def _fused_velocities(self):
+        session = get_session()
+        self._bind_device(session)
         session.upload_peds(self.peds, getattr(self, '_mode_codes', None))
         session.ctx.step(1, integrate_positions=False)
         _, vel = session.ctx.download_state()
@@ -161,6 +235,7 @@ class PedestrianSimulation:
         (self.dyn_obs_ids, obstacle_pos, self.dyn_obs_heading, self.dyn_obs_vel, self.dyn_obs_extent,
          borders) = dynamic_obstacles
         self.dyn_obstacles = list(zip(obstacle_pos, borders))
+        self._dyn_version += 1
         if 'dynamic_obstacle_force' in self.forces and self.dyn_obstacles:
             self.forces['dynamic_obstacle_force'].update_obstacles(self.dyn_obstacles)
             self.forces['dynamic_obstacle_force'].update_obstacle_velocities(self.dyn_obs_vel)

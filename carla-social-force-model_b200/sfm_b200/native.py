@@ -18,13 +18,14 @@ LIB_PATH = os.environ.get('SFM_LIB') or os.path.join(HERE, 'libsfm_b200.so')    
 FORCE_CLASSES = ('acceleration_force', 'pedestrian_force', 'border_force', 'static_obstacle_force',
                  'dynamic_obstacle_force')                      # pedestrian_simulation.py:37-48 dict order
 ACCELERATION, PEDESTRIAN, BORDER, STATIC_OBSTACLE, DYNAMIC_OBSTACLE = range(5)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/sfm_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create', 'sfm_destroy', 'sfm_set_stream',
            'sfm_synchronize', 'sfm_set_params', 'sfm_set_origin', 'sfm_set_partition', 'sfm_upload_state',
            'sfm_update_kinematics', 'sfm_update_targets', 'sfm_download_state', 'sfm_set_borders', 'sfm_set_obstacles',
-           'sfm_force', 'sfm_enumerate_pairs', 'sfm_step', 'sfm_tick_host', 'sfm_download_force',
+           'sfm_force', 'sfm_enumerate_pairs', 'sfm_count_point_evaluations', 'sfm_step', 'sfm_tick_host', 'sfm_tick_records',
+           'sfm_host_column_gather', 'sfm_host_column_equal', 'sfm_download_force',
            'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_stage', 'sfm_step_begin', 'sfm_step_end',
            'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats',
            # lifecycle
@@ -113,8 +114,12 @@ def lib():
         'sfm_set_obstacles': (C.c_int, [p_ctx, C.c_int, i64, p_d, p_d, p_i64, p_d]),
         'sfm_force': (C.c_int, [p_ctx, C.c_int, i64, p_d]),
         'sfm_enumerate_pairs': (C.c_int, [p_ctx, C.c_int, i64, p_i64, p_i64]),
+        'sfm_count_point_evaluations': (C.c_int, [p_ctx, C.c_int, p_i64, p_i64]),
         'sfm_step': (C.c_int, [p_ctx, C.c_int, C.c_int]),
         'sfm_tick_host': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d]),
+        'sfm_tick_records': (C.c_int, [p_ctx, i64, C.c_void_p, i64, p_i64, C.c_double, C.c_int, p_i64]),
+        'sfm_host_column_gather': (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p]),
+        'sfm_host_column_equal': (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p, C.POINTER(C.c_int)]),
         'sfm_download_force': (C.c_int, [p_ctx, i64, p_d]),
         'sfm_download_class_force': (C.c_int, [p_ctx, C.c_int, i64, p_d]),
         'sfm_gather_buffer': (C.c_int, [p_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
@@ -171,6 +176,21 @@ def _f64(a, shape=None):
 
 def _ptr(a, ctype=C.c_double):
     return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+def column_gather(state, field, width):
+    """Raw bytes of one column of a structured array as a packed uint8 [n, width] array (works for object columns)."""
+    out = np.empty((len(state), width), dtype=np.uint8)
+    _check(lib().sfm_host_column_gather(C.c_void_p(state.ctypes.data), state.strides[0], state.dtype.fields[field][1],
+                                        width, len(state), C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def column_equal(state, field, packed):
+    same = C.c_int()
+    _check(lib().sfm_host_column_equal(C.c_void_p(state.ctypes.data), state.strides[0], state.dtype.fields[field][1],
+                                       packed.shape[1], len(state), C.c_void_p(packed.ctypes.data), C.byref(same)))
+    return bool(same.value)
 
 
 def pack_point_set(rings):
@@ -334,12 +354,29 @@ class Context:
         t = buf[:count.value]
         return t[np.lexsort((t[:, 1], t[:, 0]))]
 
+    def count_point_evaluations(self, force_class):
+        """-> (pairs inside the cutoff, distances the reference's argmin ranges over) for a cell-list class."""
+        pairs, evals = C.c_int64(), C.c_int64()
+        _check(self._lib.sfm_count_point_evaluations(self._h, force_class, C.byref(pairs), C.byref(evals)))
+        return pairs.value, evals.value
+
     def step(self, n_steps=1, integrate_positions=True):
         _check(self._lib.sfm_step(self._h, int(n_steps), int(bool(integrate_positions))))
 
     def tick_host(self, loc, vel, new_vel, new_loc=None):
         """Host-buffer tick; arrays must be C-contiguous float64 [n, 3] (pinned memory makes the copies asynchronous)."""
         _check(self._lib.sfm_tick_host(self._h, self.n, _ptr(loc), _ptr(vel), _ptr(new_vel), _ptr(new_loc)))
+
+    def tick_records(self, state, sim_time, tick_modes):
+        """One drop-in tick on the structured pedestrian table ``state`` (in place: new velocities land in ``state['vel']``,
+        and with ``tick_modes`` the applied target speeds in ``state['target_speed']``).  Returns the lifecycle counters."""
+        fields = state.dtype.fields
+        offsets = np.array([fields[k][1] for k in ('loc', 'vel', 'next_waypoint', 'radius', 'target_speed')], dtype=np.int64)
+        counters = np.zeros(4, dtype=np.int64)
+        _check(self._lib.sfm_tick_records(self._h, len(state), C.c_void_p(state.ctypes.data), state.strides[0],
+                                          _ptr(offsets, C.c_int64), float(sim_time), int(bool(tick_modes)),
+                                          _ptr(counters, C.c_int64)))
+        return counters
 
     def download_force(self, out=None):
         out = np.empty((self.n, 3)) if out is None else out

@@ -18,22 +18,35 @@ class Session:
     def __init__(self, device):
         self.ctx = native.Context(device)
         self.params_key = None
+        self.thresholds = None
         self.owner = {native.BORDER: None, native.STATIC_OBSTACLE: None, native.DYNAMIC_OBSTACLE: None}
         self.set_version = {native.BORDER: None, native.STATIC_OBSTACLE: None, native.DYNAMIC_OBSTACLE: None}
+        self.resident_table = None          # ModeTable whose pedestrian rows (and machines) are on the device
+        self.machines_version = None        # ... and the table version its device mirror reflects
+        self.traffic_version = None
+
+    def set_params(self, params):
+        """Make ``params`` the context's parameters unless they already are.  Point sets stay resident across parameter
+        changes -- only a changed perception threshold invalidates them (their cutoffs are built from it)."""
+        key = bytes(params)
+        if key == self.params_key:
+            return
+        self.ctx.set_params(params)
+        self.params_key = key
+        thresholds = (params.static_obs.perception_threshold, params.dynamic_obs.perception_threshold)
+        if thresholds != self.thresholds:
+            self.owner = {k: None for k in self.owner}
+            self.thresholds = thresholds
 
     def bind_params(self, sfm_config, step_length):
         params = native.params_from_config(sfm_config, step_length,
                                            enable={name: True for name in native.FORCE_CLASSES})
-        key = bytes(params)
-        if key != self.params_key:
-            # a changed perception threshold invalidates resident obstacle sets (their cutoff is baked in)
-            self.ctx.set_params(params)
-            self.params_key = key
-            self.owner = {k: None for k in self.owner}
+        self.set_params(params)
         return params
 
     def upload_peds(self, peds, mode_codes=None):
         self.ctx.upload_state(*peds.device_columns(mode_codes))
+        self.resident_table = None          # a full upload drops the device-side mode machines
 
     def bind_set(self, which, owner, version, loader):
         """Make ``owner``'s point set resident for class ``which`` unless it already is (same object, same version)."""

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SFM_ABI_VERSION 2
+#define SFM_ABI_VERSION 3
 
 typedef struct sfm_ctx sfm_ctx;
 
@@ -118,6 +118,10 @@ int sfm_force(sfm_ctx* ctx, int force_class, int64_t n, double* out);
 /* Neighbour enumeration of a cutoff-limited class (border / static / dynamic): writes up to `capacity` triplets
  * (pedestrian row, section-or-obstacle index, nearest point index) in unspecified order and the total count. */
 int sfm_enumerate_pairs(sfm_ctx* ctx, int force_class, int64_t capacity, int64_t* triplets, int64_t* count);
+/* Work the reference does for a cutoff-limited class on the current state: `pairs` = (pedestrian, item) pairs inside the
+ * cutoff (forces.py:149-151, :222-225), `point_evaluations` = the sum of those items' point counts, i.e. the distances
+ * np.argmin ranges over (forces.py:154, :228).  The denominator of the distance-evaluations/s figure in bench.py. */
+int sfm_count_point_evaluations(sfm_ctx* ctx, int force_class, int64_t* pairs, int64_t* point_evaluations);
 
 /* ---- the fused tick: replaces PedestrianSimulation.tick's force sum and calculate_new_velocities
  *      (pedestrian_simulation.py:81-83,117-124; stateutils.py:18-23) plus, optionally, the position update the
@@ -128,6 +132,23 @@ int sfm_enumerate_pairs(sfm_ctx* ctx, int force_class, int64_t capacity, int64_t
 int sfm_step(sfm_ctx* ctx, int n_steps, int integrate_positions);
 /* Host-buffer tick: upload loc/vel, one step, download the new velocities (and positions when new_loc != NULL). */
 int sfm_tick_host(sfm_ctx* ctx, int64_t n, const double* loc, const double* vel, double* new_vel, double* new_loc);
+/* PedestrianSimulation.tick's device half on the reference's own pedestrian table (pedestrian_simulation.py:57-83): the
+ * structured array `PedState.state` (pedestrian_state.py:17-19) is handed over as it lies in memory -- `records` points at
+ * row 0, `stride` is the record size in bytes, `field_offsets` = byte offsets of loc, vel, next_waypoint, radius,
+ * target_speed (4-byte aligned).  One H2D copy of the table, then on the device: unpack; with `tick_modes` the mode
+ * bookkeeping of :63-73 (apply_current_mode, PedModeManager.tick, check_traffic -- needs sfm_set_mode_machines, and
+ * sfm_set_traffic when vehicles exist); all enabled forces, their sum, the velocity update and clamp of :81-83,117-124.
+ * The new velocities are written into the records' vel field (what `state[['id','vel']]` aliases, :123-124) and, with
+ * `tick_modes`, the target speed the clamp used into target_speed (pedestrian_state.py:94-95).  counters4 (may be NULL)
+ * receives sfm_lifecycle_counters after the tick, so the caller knows whether any machine changed mode.  Row count and
+ * mode codes are those of the last sfm_upload_state / sfm_update_targets. */
+int sfm_tick_records(sfm_ctx* ctx, int64_t n, void* records, int64_t stride, const int64_t* field_offsets,
+                     double sim_time, int tick_modes, int64_t* counters4);
+/* Host-side helpers for AoS tables (no device work): copy one column out of / compare it with a packed array.  The
+ * drop-in uses them on the `mode` column (object pointers) to notice that the table holds other objects than before. */
+int sfm_host_column_gather(const void* records, int64_t stride, int64_t offset, int64_t width, int64_t n, void* packed);
+int sfm_host_column_equal(const void* records, int64_t stride, int64_t offset, int64_t width, int64_t n,
+                          const void* packed, int* equal);
 /* Total force / one class's force of the most recent step, [n][3]. */
 int sfm_download_force(sfm_ctx* ctx, int64_t n, double* out);
 int sfm_download_class_force(sfm_ctx* ctx, int force_class, int64_t n, double* out);

@@ -81,3 +81,88 @@ def test_spawn_despawn_between_ticks(sfm_config):
     empty = pedestrian_simulation.PedestrianSimulation([], np.empty((0, 2), dtype=object), [], sfm_config, 0.05)
     empty.tick(0.0)                                                  # no pedestrians: early-out
     assert empty.get_new_velocities() is None
+
+
+class _OpaqueMode(PedModeManager):
+    """A subclass is not a *stock* PedModeManager: a table containing one takes the generic per-object path."""
+    __slots__ = ()
+
+
+def _lifecycle_sim(w, life, cfg, record_states, opaque=False):
+    reset_session()
+    sim = pedestrian_simulation.PedestrianSimulation(list(w.borders), w.section_info(), list(w.static_obstacles), cfg,
+                                                     w.step_length, record_states=record_states)
+    cls = _OpaqueMode if opaque else PedModeManager
+    for i in range(w.n):
+        mode = cls(f'p_{i}', float(w.target_speed[i]), PedMode(int(w.mode[i])), float(life.crossing_speed_factor[i]),
+                   float(life.crossing_safety_margin[i]))
+        if life.idle[i]:
+            mode.set_mode(PedMode.IDLE)
+        sim.spawn_pedestrian((f'p_{i}', i, w.loc[i], w.vel[i], w.next_waypoint[i], mode, w.radius[i], w.target_speed[i]))
+    return sim
+
+
+def _drive(sim, w, life, steps):
+    """SimulationRunner.tick with CARLA stubbed (run_simulation.py:77-132): vehicles -> tick -> move -> waypoint hand-over."""
+    routes = {f'p_{i}': list(r) for i, r in enumerate(life.routes)}
+    log = []
+    for k in range(steps):
+        sim.update_dynamic_obstacles(w.vehicles_at(k))
+        sim.tick(k * w.step_length)
+        nv = sim.get_new_velocities()
+        assert np.shares_memory(nv, sim.peds.state)
+        for name in sim.get_arrived_peds(life.waypoint_threshold):          # arrival at the positions the forces saw
+            if routes[name]:
+                sim.peds.update_next_waypoint(name, routes[name].pop(0))
+        sim.peds.state['loc'] += nv['vel'] * w.step_length
+        log.append((sim.peds.mode_codes().copy(), sim.peds.state['vel'].copy(), sim.peds.state['target_speed'].copy(),
+                    np.array([float(m.next_mode_time) for m in sim.peds.state['mode']])))
+    return log
+
+
+def test_resident_columnar_and_generic_ticks_agree(sfm_config):
+    """The three ways through PedestrianSimulation.tick (device-resident K4a, columnar host machines, per-object generic)
+    produce the same modes, target speeds, wake-up times and velocities tick by tick on the lifecycle scene: idle
+    pedestrians waking up, gap acceptance against moving vehicles, hand-overs requesting crossings."""
+    w, life = synth.make_lifecycle()
+    steps = 80
+    generic = _drive(_lifecycle_sim(w, life, sfm_config, record_states=False, opaque=True), w, life, steps)
+    columnar_sim = _lifecycle_sim(w, life, sfm_config, record_states=True)
+    columnar = _drive(columnar_sim, w, life, steps)
+    resident_sim = _lifecycle_sim(w, life, sfm_config, record_states=False)
+    resident = _drive(resident_sim, w, life, steps)
+    assert resident_sim.peds.mode_table() is not None and len(columnar_sim.get_states()) == steps
+    seen = set()
+    for k in range(steps):
+        for other, name in ((columnar, 'columnar'), (resident, 'resident')):
+            for a, b, what in zip(generic[k], other[k], ('modes', 'velocities', 'target speeds', 'wake-up times')):
+                assert np.array_equal(a, b), f'{name} path: {what} differ at tick {k}'
+        seen.update(generic[k][0].tolist())
+    assert seen == {0, 1, 2, 3, 4}                               # every mode occurred
+    snap = columnar_sim.get_states()[0.0]
+    assert snap['mode'].dtype == object and len(snap) == w.n           # recorded like pedestrian_state.py:100-104
+
+
+def test_resident_tick_keeps_sets_and_rows_on_device(sfm_config):
+    """Steady-state resident ticks upload the pedestrian table and nothing else: no parameter, point-set or full-state
+    upload, no interpreter loop (the launch count per tick is constant and small)."""
+    w = synth.make_config(2)
+    sim = build_sim(w, sfm_config, record_states=False)
+    from sfm_b200.session import get_session
+    sim.tick(0.0)
+    ctx = get_session().ctx
+    sim.tick(0.05)
+    ctx.reset_stats()
+    for k in range(5):
+        sim.tick(0.1 + 0.05 * k)
+    s = ctx.stats()
+    assert s['steps'] == 5 and s['launches'] <= 5 * 24, s
+    # the velocities are the reference's: same state through the per-class force objects and the host-side update
+    state = sim.peds.state.copy()
+    F = sum(f.get_force(sim.peds) for f in sim.forces.values())
+    sim.peds.state['vel'] = state['vel']
+    sim.calculate_new_velocities(F)
+    want = sim.get_new_velocities()['vel'].copy()
+    sim.peds.state['vel'] = state['vel']
+    sim.tick(1.0)
+    assert np.abs(sim.peds.state['vel'] - want).max() < 1e-6

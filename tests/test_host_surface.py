@@ -124,3 +124,61 @@ def test_check_traffic_gap_acceptance():
     assert check_traffic(ped, near, np.array([[0.0, 0.0]]), extents) is True           # parked
     mode.crossing_safety_margin = -1.0
     assert check_traffic(ped, near, np.array([[2.0, 0.0]]), extents) is True           # negative margin: no check
+
+
+def test_mode_table_equals_standalone_machines():
+    """A PedModeManager adopted into a ModeTable behaves exactly like a standalone one: same modes, speeds and wake-up
+    times under random requests and ticks, through the objects and through the table's vectorised tick."""
+    rng = np.random.default_rng(11)
+    n = 200
+    PM = ped_mode_manager.PedMode
+
+    def make():
+        return [ped_mode_manager.PedModeManager(f'p{i}', 1.0 + 0.01 * i, PM(int(rng2.integers(0, 5))), 1.5, 1.0)
+                for i in range(n)]
+    rng2 = np.random.default_rng(5)
+    alone = make()
+    rng2 = np.random.default_rng(5)
+    tabled = make()
+    table = ped_mode_manager.ModeTable(tabled)
+    assert all(m._table is table for m in tabled)
+    for step in range(300):
+        t = 0.05 * step
+        for k in rng.integers(0, n, size=6):
+            wanted = PM(int(rng.integers(0, 5)))
+            alone[k].set_mode(wanted)
+            tabled[k].set_mode(wanted)
+        for m in alone:
+            m.tick(t)
+        table.tick(t)
+        got = [(int(m.current_mode), float(m.target_speed), float(m.next_mode_time), float(m.sim_time)) for m in tabled]
+        want = [(int(m.current_mode), float(m.target_speed), float(m.next_mode_time), float(m.sim_time)) for m in alone]
+        assert got == want, step
+    assert table.version > 0
+    table.release()                                 # the objects take their values back and keep working
+    assert all(m._table is None for m in tabled)
+    assert [int(m.current_mode) for m in tabled] == [int(m.current_mode) for m in alone]
+    tabled[0].set_mode(PM.IDLE)
+    assert tabled[0].current_mode == PM.IDLE and tabled[0].target_speed == 0
+
+
+def test_ped_state_adopts_and_tracks_mode_objects():
+    cfg = {}
+    ps = pedestrian_state.PedState(cfg)
+    PM = ped_mode_manager.PedMode
+    modes = [ped_mode_manager.PedModeManager(f'p{i}', 1.2, PM.WALKING_SIDEWALK, 1.5, 1.0) for i in range(50)]
+    ps.add_pedestrians([f'p{i}' for i in range(50)], np.arange(50), np.zeros((50, 3)), np.zeros((50, 3)),
+                       np.zeros((50, 3)), modes, np.full(50, 0.3), np.full(50, 1.2))
+    table = ps.mode_table()
+    assert table is not None and ps.mode_table() is table           # same objects -> same table
+    modes[7].set_mode(PM.CROSSING_ROAD)
+    assert ps.mode_codes()[7] == PM.CHECKING_TRAFFIC
+    ps.apply_current_mode()
+    assert ps.state['target_speed'][7] == 0.0 and ps.state['target_speed'][8] == 1.2
+    ps.remove_pedestrian('p7')                                       # the row set changed: a new table, p7 stands alone
+    table2 = ps.mode_table()
+    assert table2 is not table and modes[7]._table is None and modes[7].current_mode == PM.CHECKING_TRAFFIC
+    assert modes[8]._table is table2 and modes[8]._row == 7
+    ps.state['mode'][3] = PM.WALKING_SIDEWALK                        # a plain enum in the column: no table, generic path
+    assert ps.mode_table() is None and modes[4]._table is None
+    assert ps.mode_codes()[3] == PM.WALKING_SIDEWALK
