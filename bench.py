@@ -359,8 +359,8 @@ def run_ours(args, world, rank, local_rank):
     if world > 1:
         # NCCL only carries the set-up traffic (handle table, barriers, the gathers of `parity`) unless SFM_EXCHANGE=nccl;
         # its INIT lines (rank / nranks / transport) go to stderr so the communicator is observable, stdout stays one line
-        os.environ.setdefault('NCCL_DEBUG', os.environ.get('SFM_NCCL_DEBUG', 'INFO'))
-        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+        os.environ['NCCL_DEBUG'] = os.environ.get('SFM_NCCL_DEBUG', 'INFO')     # (an inherited VERSION / WARN level would
+        os.environ['NCCL_DEBUG_SUBSYS'] = os.environ.get('SFM_NCCL_DEBUG_SUBSYS', 'INIT')     #  print its banner on stdout)
         os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     job = Job(world, rank, local_rank)
