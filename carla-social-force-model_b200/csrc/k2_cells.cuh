@@ -68,8 +68,9 @@ __global__ void k2_item_keys(const double2* __restrict__ center, int count, Cell
     val[s] = s;
 }
 
-// Stable LSD radix sort of (key, val) by one CTA; each thread owns a contiguous run of the input, so equal keys keep
-// their input (= index) order without any atomics.
+// Stable LSD radix sort of (key, val) by one CTA (sets of a few thousand items: one launch, lowest latency); each thread
+// owns a contiguous run of the input, so equal keys keep their input (= index) order without any atomics.  Larger sets
+// take the many-CTA sort below (sfm_api.cu: sort_items).
 __global__ void __launch_bounds__(SORT_THREADS) k2_radix_sort(unsigned* key_a, int* val_a, unsigned* key_b, int* val_b,
                                                               int count, int key_bits) {
     constexpr int R = 1 << SORT_RADIX_BITS;
@@ -142,6 +143,120 @@ __global__ void __launch_bounds__(SORT_THREADS) k2_radix_sort(unsigned* key_a, i
             val_a[i] = vin[i];
         }
     }
+}
+
+// ---- the same sort for large sets: stable LSD radix sort over many CTAs, 8-bit digits -----------------------------
+// One CTA owns a contiguous run of MSORT_TILE items.  Per pass: (1) per-CTA digit histograms, written digit-major so that
+// (2) one exclusive scan over [digit][CTA] yields every CTA's first output slot per digit, (3) a stable scatter -- the CTA
+// walks its run in sub-tiles of 256 items; inside a sub-tile an item's rank among equal digits is its rank inside the warp
+// (match.any + popc of the lower lanes) plus the counts of the lower warps, so equal keys keep their input order and the
+// result is deterministic: no atomics on global memory anywhere.
+constexpr int MSORT_THREADS = 256;
+constexpr int MSORT_ITEMS = 16;
+constexpr int MSORT_TILE = MSORT_THREADS * MSORT_ITEMS;
+constexpr int MSORT_BITS = 8;
+constexpr int MSORT_R = 1 << MSORT_BITS;
+
+__global__ void __launch_bounds__(MSORT_THREADS) k2_msort_hist(const unsigned* __restrict__ key, int count, int shift,
+                                                              int* __restrict__ hist, int nblk) {
+    __shared__ int h[MSORT_R];
+    const int tid = threadIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * MSORT_TILE;
+    for (int t = 0; t < MSORT_ITEMS; ++t) {
+        const int i = base + t * MSORT_THREADS + tid;
+        if (i < count) atomicAdd(&h[(key[i] >> shift) & (MSORT_R - 1)], 1);      // shared-memory counter: order-free
+    }
+    __syncthreads();
+    hist[tid * nblk + blockIdx.x] = h[tid];
+}
+
+__global__ void __launch_bounds__(MSORT_THREADS) k2_msort_scatter(const unsigned* __restrict__ kin, const int* __restrict__ vin,
+                                                                 unsigned* __restrict__ kout, int* __restrict__ vout,
+                                                                 int count, int shift, const int* __restrict__ first_slot,
+                                                                 int nblk) {
+    constexpr int W = MSORT_THREADS / 32;
+    __shared__ int slot[MSORT_R];                 // next output slot of this CTA per digit
+    __shared__ int cnt[W][MSORT_R];               // per warp: items of each digit in the current sub-tile
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    slot[tid] = first_slot[tid * nblk + blockIdx.x];
+    const int base = blockIdx.x * MSORT_TILE;
+    for (int t = 0; t < MSORT_ITEMS; ++t) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) cnt[w][tid] = 0;
+        __syncthreads();
+        const int i = base + t * MSORT_THREADS + tid;
+        const bool live = i < count;
+        const unsigned k = live ? kin[i] : 0u;
+        const int d = live ? (int)((k >> shift) & (MSORT_R - 1)) : MSORT_R + lane;        // dead lanes match nobody
+        const unsigned same = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        if (live && rank == 0) cnt[wid][d] = __popc(same);
+        __syncthreads();
+        if (live) {
+            int before = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) before += (w < wid) ? cnt[w][d] : 0;
+            const int p = slot[d] + before + rank;
+            kout[p] = k;
+            vout[p] = vin[i];
+        }
+        __syncthreads();
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) total += cnt[w][tid];
+        slot[tid] += total;
+        __syncthreads();
+    }
+}
+
+// ---- exclusive scan over many CTAs: tiles of SCAN_TILE entries scanned in place, the tile totals scanned by one CTA
+//      (k2_exclusive_scan below), then added back ----------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_PER_THREAD = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k2_scan_tiles(int* data, int n, int* __restrict__ tile_sum) {
+    __shared__ int warp_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int base = blockIdx.x * SCAN_TILE + tid * SCAN_PER_THREAD;
+    int v[SCAN_PER_THREAD], mine = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        v[k] = (base + k < n) ? data[base + k] : 0;
+        mine += v[k];
+    }
+    int x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int w = warp_sum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        warp_sum[lane] = w;
+    }
+    __syncthreads();
+    int run = (wid ? warp_sum[wid - 1] : 0) + x - mine;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        if (base + k < n) data[base + k] = run;
+        run += v[k];
+    }
+    if (tid == SCAN_THREADS - 1) tile_sum[blockIdx.x] = run;
+}
+
+__global__ void k2_scan_add(int* data, int n, const int* __restrict__ tile_prefix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] += tile_prefix[i / SCAN_TILE];
 }
 
 // cell_start[c] = first position in the sorted key array whose key is >= c  (c in [0, ncell])

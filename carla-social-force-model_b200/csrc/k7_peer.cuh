@@ -10,8 +10,9 @@
 //     (k1_sym_finish reads all staged rows) never sees tick k+1's rows arrive.
 // What remains between the kernels is a flag barrier (k7_barrier): every rank stores its epoch into every peer's flag
 // array (release, system scope) and waits until all peers' epochs have arrived (acquire, system scope).  The wait is
-// bounded: after ~10 s of spinning the kernel raises the error word instead of hanging the GPU, and later barriers
-// return at once (sfm_peer_status reports it; the engine and bench.py turn it into an exception).
+// bounded: after ~10 s of spinning (SFM_BARRIER_TIMEOUT_MS) the kernel records WHICH rank it gave up on instead of hanging
+// the GPU, and later barriers return at once (sfm_peer_status reports the stalled ranks; the engine and bench.py turn it
+// into an exception).  The exchange cannot be resumed after that: destroy the contexts and build new ones.
 #pragma once
 
 #include "sfm_common.cuh"
@@ -33,8 +34,10 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* addr) {
     return v;
 }
 
-// flags[r] on every rank = the last epoch rank r has signalled.  One thread per peer.
-__global__ void k7_barrier(PeerPtrs flags, unsigned* own_flags, int world, int rank, unsigned epoch, unsigned* error) {
+// flags[r] on every rank = the last epoch rank r has signalled.  One thread per peer.  error[0] collects the ranks a
+// barrier gave up on (bit r), error[1] the epoch of the first such barrier; once set, later barriers return at once.
+__global__ void k7_barrier(PeerPtrs flags, unsigned* own_flags, int world, int rank, unsigned epoch, unsigned* error,
+                           long long timeout_cycles) {
     const int r = threadIdx.x;
     if (r >= world) return;
     if (*reinterpret_cast<volatile unsigned*>(error)) return;  // a peer was lost earlier: do not wait again
@@ -42,8 +45,8 @@ __global__ void k7_barrier(PeerPtrs flags, unsigned* own_flags, int world, int r
     st_release_sys(reinterpret_cast<unsigned*>(flags.p[r]) + rank, epoch);
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(own_flags + r) - epoch) < 0) {
-        if (clock64() - t0 > 20000000000LL) {                // ~10 s at 1.9 GHz: a peer is gone
-            atomicExch(error, 1u);
+        if (clock64() - t0 > timeout_cycles) {                // default ~10 s at 1.9 GHz: peer r is gone
+            if (atomicOr(error, 1u << r) == 0u) atomicCAS(error + 1, 0u, epoch);
             break;
         }
         __nanosleep(200);

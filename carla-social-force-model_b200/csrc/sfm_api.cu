@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "k1_ped_pairs.cuh"
 #include "k1_sym.cuh"
 #include "k2_cells.cuh"
@@ -90,13 +92,14 @@ struct SetStorage {
     DevBuf<double> cutoff;
     DevBuf<int> offset, cell_start, cell_item, val_tmp;
     DevBuf<unsigned> key, key_tmp;
+    DevBuf<int> sort_hist, sort_scan;      // many-CTA sort: [256][CTAs] digit histogram, tile totals of its scan
     DevBuf<float> tol;
     DevBuf<int> chunk_first;
     DevBuf<float4> chunk, chord0;
     double threshold = 0.0;        // perception_threshold the cutoffs / bracket widths / grid of this set were built from
     bool stale = false;            // sfm_set_params changed that threshold afterwards: the set must be uploaded again
     void release() {
-        tol.release(); chunk_first.release(); chunk.release(); chord0.release();
+        tol.release(); chunk_first.release(); chunk.release(); chord0.release(); sort_hist.release(); sort_scan.release();
         center.release(); velocity.release(); point.release(); cutoff.release(); offset.release();
         cell_start.release(); cell_item.release(); val_tmp.release(); key.release(); key_tmp.release();
     }
@@ -136,7 +139,8 @@ struct sfm_ctx {
     // pedestrian binning
     CellGrid ped_grid{};
     int ped_cells = 0;
-    DevBuf<int> perm, ped_start, ped_cursor;
+    DevBuf<int> perm, ped_start, ped_cursor, ped_scan_tmp;
+    int sort_single_max = 8192;     // SFM_SORT_SINGLE_MAX: sets up to this many items are sorted by one CTA (one launch)
     DevBuf<unsigned> ped_cell;
     bool perm_valid = false;
     // point sets
@@ -201,6 +205,7 @@ struct sfm_ctx {
     DevBuf<unsigned> flags;                          // [MAX_PEERS] epochs signalled by the peers + [MAX_PEERS] error word
     unsigned epoch = 0;
     int64_t barriers = 0;
+    long long barrier_timeout_cycles = 20000000000LL;   // ~10 s at 1.9 GHz; SFM_BARRIER_TIMEOUT_MS overrides
     // ---- CUDA graph of one single-rank tick (sfm_step), opt-in (SFM_GRAPH=1): the ~12 launches of a tick replayed as one
     //      graph launch; re-captured whenever a pointer, a size or a parameter a kernel argument was built from may have
     //      changed.  Measured (profiles/small_n_steps_r1.log): 58 -> 55 us per tick at N = 64, 158 -> 145 us at N = 4,096,
@@ -223,6 +228,10 @@ struct SpanGuard {
     int idx = -1;
     cudaStream_t st;
     SpanGuard(sfm_ctx* ctx, int cls, cudaStream_t stream = nullptr) : c(ctx), st(stream ? stream : ctx->stream) {
+        // NVTX range per tick phase (host side of the launches; a no-op unless a tool is attached)
+        static const char* const names[ST_COUNT] = {"sfm:pairs (K1)", "sfm:cells (K2a)", "sfm:segments (K2b/c)",
+                                                    "sfm:integrate (K3)", "sfm:lifecycle (K4-K6)"};
+        nvtxRangePushA(names[cls]);
         if (!c->profiling) return;
         TimedSpan sp;
         auto get = [&]() {
@@ -240,6 +249,7 @@ struct SpanGuard {
     }
     ~SpanGuard() {
         if (idx >= 0) cudaEventRecord(c->spans[idx].stop, st);
+        nvtxRangePop();
     }
 };
 
@@ -424,7 +434,8 @@ int launch_barrier(sfm_ctx* c) {
     PeerPtrs fl{};
     for (int r = 0; r < c->world; ++r) fl.p[r] = c->peer_flags[r];
     c->epoch += 1;
-    k7_barrier<<<1, 32, 0, c->stream>>>(fl, c->flags.p, c->world, c->rank, c->epoch, c->flags.p + MAX_PEERS);
+    k7_barrier<<<1, 32, 0, c->stream>>>(fl, c->flags.p, c->world, c->rank, c->epoch, c->flags.p + MAX_PEERS,
+                                        c->barrier_timeout_cycles);
     c->launches += 1;
     c->barriers += 1;
     SFM_CUDA(cudaGetLastError());
@@ -522,6 +533,54 @@ int launch_pairs(sfm_ctx* c) {
     return launch_pairs_finish(c);
 }
 
+// In-place exclusive scan: one CTA for short arrays, tiles + scanned tile totals + add-back beyond that.
+int launch_exclusive_scan(sfm_ctx* c, int* data, int n, DevBuf<int>& tmp, cudaStream_t st) {
+    if (n <= 4 * SCAN_TILE) {
+        k2_exclusive_scan<<<1, 1024, 0, st>>>(data, n);
+        c->launches += 1;
+    } else {
+        const int tiles = cdiv(n, SCAN_TILE);
+        SFM_TRY(tmp.ensure(tiles));
+        k2_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(data, n, tmp.p);
+        k2_exclusive_scan<<<1, 1024, 0, st>>>(tmp.p, tiles);
+        k2_scan_add<<<cdiv(n, 256), 256, 0, st>>>(data, n, tmp.p);
+        c->launches += 3;
+    }
+    SFM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// (key, cell_item) of a set into (cell, index) order: one CTA up to sort_single_max items, the many-CTA sort beyond.
+int sort_items(sfm_ctx* c, SetStorage& st, int count, int key_bits) {
+    if (count <= c->sort_single_max) {
+        k2_radix_sort<<<1, SORT_THREADS, 0, c->stream>>>(st.key.p, st.cell_item.p, st.key_tmp.p, st.val_tmp.p, count, key_bits);
+        c->launches += 1;
+        SFM_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const int nblk = cdiv(count, MSORT_TILE);
+    SFM_TRY(st.sort_hist.ensure((size_t)MSORT_R * nblk));
+    unsigned* kin = st.key.p;
+    int* vin = st.cell_item.p;
+    unsigned* kout = st.key_tmp.p;
+    int* vout = st.val_tmp.p;
+    for (int shift = 0; shift < key_bits; shift += MSORT_BITS) {
+        k2_msort_hist<<<nblk, MSORT_THREADS, 0, c->stream>>>(kin, count, shift, st.sort_hist.p, nblk);
+        c->launches += 1;
+        SFM_TRY(launch_exclusive_scan(c, st.sort_hist.p, MSORT_R * nblk, st.sort_scan, c->stream));
+        k2_msort_scatter<<<nblk, MSORT_THREADS, 0, c->stream>>>(kin, vin, kout, vout, count, shift, st.sort_hist.p, nblk);
+        c->launches += 1;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    SFM_CUDA(cudaGetLastError());
+    if (kin != st.key.p) {
+        SFM_CUDA(cudaMemcpyAsync(st.key.p, kin, sizeof(unsigned) * count, cudaMemcpyDeviceToDevice, c->stream));
+        SFM_CUDA(cudaMemcpyAsync(st.cell_item.p, vin, sizeof(int) * count, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return 0;
+}
+
 int rebin_peds(sfm_ctx* c, cudaStream_t st = nullptr) {
     if (!st) st = c->stream;
     const int n = (int)c->n;
@@ -533,9 +592,9 @@ int rebin_peds(sfm_ctx* c, cudaStream_t st = nullptr) {
     SFM_CUDA(cudaMemsetAsync(c->ped_start.p, 0, sizeof(int) * (c->ped_cells + 1), st));
     SFM_CUDA(cudaMemsetAsync(c->ped_cursor.p, 0, sizeof(int) * (c->ped_cells + 1), st));
     k2_ped_count<<<cdiv(n, 256), 256, 0, st>>>(c->locr.p, n, c->ped_grid, c->ped_cell.p, c->ped_start.p);
-    k2_exclusive_scan<<<1, 1024, 0, st>>>(c->ped_start.p, c->ped_cells + 1);
+    SFM_TRY(launch_exclusive_scan(c, c->ped_start.p, c->ped_cells + 1, c->ped_scan_tmp, st));
     k2_ped_fill<<<cdiv(n, 256), 256, 0, st>>>(c->ped_cell.p, n, c->ped_start.p, c->ped_cursor.p, c->perm.p);
-    c->launches += 3;
+    c->launches += 2;
     SFM_CUDA(cudaGetLastError());
     c->perm_valid = true;
     return 0;
@@ -597,10 +656,10 @@ int build_set_grid(sfm_ctx* c, SetStorage& st, int64_t count, const double* cent
     while ((1 << key_bits) < ncell) ++key_bits;
     SpanGuard g(c, ST_CELLS);
     k2_item_keys<<<cdiv(count, 256), 256, 0, c->stream>>>(st.center.p, (int)count, s.grid, st.key.p, st.cell_item.p);
-    k2_radix_sort<<<1, SORT_THREADS, 0, c->stream>>>(st.key.p, st.cell_item.p, st.key_tmp.p, st.val_tmp.p, (int)count,
-                                                     key_bits);
+    c->launches += 1;
+    SFM_TRY(sort_items(c, st, (int)count, key_bits));
     k2_cell_bounds<<<cdiv(ncell + 1, 256), 256, 0, c->stream>>>(st.key.p, (int)count, ncell, st.cell_start.p);
-    c->launches += 3;
+    c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     s.cell_start = st.cell_start.p;
     s.cell_item = st.cell_item.p;
@@ -975,6 +1034,9 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_K1_FIRST")) c->k1_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PRUNE")) c->k2_prune = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_DIRECT")) c->k2_direct = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SFM_SORT_SINGLE_MAX")) c->sort_single_max = std::max(0, std::atoi(env));
+    if (const char* env = std::getenv("SFM_BARRIER_TIMEOUT_MS"))
+        c->barrier_timeout_cycles = std::max(1LL, (long long)(std::atof(env) * 1.0e-3 * (double)prop.clockRate * 1.0e3));
     if (const char* env = std::getenv("SFM_GRAPH")) c->use_graph = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PERSIST")) c->k2_persist = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("SFM_K2_PERSIST_MULTI")) c->k2_persist_multi = std::atoi(env) != 0;
@@ -1004,6 +1066,7 @@ int sfm_destroy(sfm_ctx* c) {
     c->raw_a.release(); c->raw_b.release(); c->raw_c.release(); c->raw_d.release(); c->raw_e.release();
     c->rec_bytes.release(); c->rec_out.release();
     if (c->rec_pinned) cudaFreeHost(c->rec_pinned);
+    c->ped_scan_tmp.release();
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
     c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release(); c->facc.release();
     if (c->p2p)
@@ -1709,8 +1772,8 @@ int sfm_despawn_finished(sfm_ctx* c, int64_t* n_after, int64_t* n_removed) {
     {
         SpanGuard g(c, ST_LIFECYCLE);
         k4_keep_flags<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->finished.p, idx.p);
-        k2_exclusive_scan<<<1, 1024, 0, c->stream>>>(idx.p, (int)n + 1);     // idx[n] = survivors
-        c->launches += 2;
+        c->launches += 1;
+        SFM_TRY(launch_exclusive_scan(c, idx.p, (int)n + 1, c->ped_scan_tmp, c->stream));      // idx[n] = survivors
         SFM_CUDA(cudaGetLastError());
     }
     int survivors = 0;
@@ -1792,9 +1855,10 @@ int rebin_dynamic(sfm_ctx* c) {
     while ((1 << key_bits) < ncell) ++key_bits;
     SpanGuard g(c, ST_CELLS);
     k2_item_keys<<<cdiv(count, 256), 256, 0, c->stream>>>(st.center.p, count, st.s.grid, st.key.p, st.cell_item.p);
-    k2_radix_sort<<<1, SORT_THREADS, 0, c->stream>>>(st.key.p, st.cell_item.p, st.key_tmp.p, st.val_tmp.p, count, key_bits);
+    c->launches += 1;
+    SFM_TRY(sort_items(c, st, count, key_bits));
     k2_cell_bounds<<<cdiv(ncell + 1, 256), 256, 0, c->stream>>>(st.key.p, count, ncell, st.cell_start.p);
-    c->launches += 3;
+    c->launches += 1;
     SFM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -2004,7 +2068,7 @@ int sfm_peer_status(sfm_ctx* c, int64_t* barriers, int* timed_out) {
     if (timed_out) {
         *timed_out = 0;
         if (c->flags.p) {
-            unsigned e = 0;
+            unsigned e = 0;                  // bit r: a barrier of this rank gave up waiting for rank r
             SFM_CUDA(cudaMemcpyAsync(&e, c->flags.p + MAX_PEERS, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
             SFM_CUDA(cudaStreamSynchronize(c->stream));
             *timed_out = (int)e;

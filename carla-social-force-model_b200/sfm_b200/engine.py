@@ -23,8 +23,18 @@ ROW_ALIGN = 256
 
 
 def partition_rows(n, world):
-    """Contiguous row blocks, sizes differing by at most one: returns int64 [world + 1] boundaries."""
-    base, extra = divmod(int(n), int(world))
+    """Contiguous row blocks made of whole 256-row tiles of the pair kernel (block sizes differ by at most one tile; the
+    last block takes the ragged tail): returns int64 [world + 1] boundaries.  With whole tiles per rank the tile pairs of
+    the multi-rank run are those of the single-GPU run, so -- when the tile count divides by the rank count -- the two
+    are bit-identical for ANY crowd size (integer accumulation is order-free).  Crowds smaller than one tile per rank are
+    split evenly by rows."""
+    n, world = int(n), int(world)
+    tiles = (n + ROW_ALIGN - 1) // ROW_ALIGN
+    if tiles >= world:
+        bounds = np.minimum(n, ROW_ALIGN * ((tiles * np.arange(world + 1, dtype=np.int64)) // world))
+        bounds[-1] = n
+        return bounds.astype(np.int64)
+    base, extra = divmod(n, world)
     sizes = np.full(world, base, dtype=np.int64)
     sizes[:extra] += 1
     bounds = np.zeros(world + 1, dtype=np.int64)
@@ -253,5 +263,14 @@ class Engine:
 
     def check_peers(self):
         """Raise if a flag barrier of the peer-memory exchange gave up waiting for another rank."""
-        if self.peer and self.ctx.peer_status()['timed_out']:
-            raise native.SfmError('peer-memory exchange: a barrier timed out waiting for another rank; results are invalid')
+        if not self.peer:
+            return
+        status = self.ctx.peer_status()
+        if status['timed_out']:
+            raise native.SfmError(f"peer-memory exchange: rank {self.rank} gave up waiting for rank(s) "
+                                  f"{status['stalled_ranks']} at a flag barrier; results are invalid -- close every rank's "
+                                  'engine and build new ones')
+
+    def close(self):
+        """Release the device context (and its mappings of the peers' buffers)."""
+        self.ctx.close()

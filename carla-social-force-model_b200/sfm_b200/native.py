@@ -424,7 +424,8 @@ class Context:
     def peer_status(self):
         n, bad = C.c_int64(), C.c_int()
         _check(self._lib.sfm_peer_status(self._h, C.byref(n), C.byref(bad)))
-        return dict(barriers=n.value, timed_out=bool(bad.value))
+        stalled = [r for r in range(32) if bad.value >> r & 1]
+        return dict(barriers=n.value, timed_out=bool(bad.value), stalled_ranks=stalled)
 
     # -- lifecycle on the device
     def set_mode_machines(self, initial_target_speed, crossing_speed, crossing_safety_margin, mode_target_speed=None,

@@ -182,7 +182,9 @@ int sfm_peer_import(sfm_ctx* ctx, const void* all_handles);
  * all-gather); flag barrier.  No NCCL call on the path. */
 int sfm_step_peer(sfm_ctx* ctx, int n_steps, int integrate_positions);
 int sfm_peer_barrier(sfm_ctx* ctx);
-/* barriers executed so far; timed_out != 0 when a barrier gave up waiting for a peer (~10 s). */
+/* barriers executed so far; timed_out != 0 when a barrier gave up waiting (~10 s, SFM_BARRIER_TIMEOUT_MS): bit r is set
+ * for every rank r that did not arrive.  A timed-out exchange is not resumable -- results after it are invalid and later
+ * barriers return immediately; destroy the contexts of all ranks (sfm_destroy) and create new ones. */
 int sfm_peer_status(sfm_ctx* ctx, int64_t* barriers, int* timed_out);
 
 /* ---- lifecycle on the device: what PedestrianSimulation.tick and SimulationRunner.tick do in

@@ -148,3 +148,46 @@ def test_pair_force_is_reproducible(sfm_config):
     a = make_context(w, sfm_config).force(native.PEDESTRIAN)
     b = make_context(w, sfm_config).force(native.PEDESTRIAN)
     np.testing.assert_array_equal(a, b)
+
+
+def test_large_dynamic_set_enumeration_bit_exact(sfm_config):
+    """A dynamic set of 100,000 obstacles re-binned on the device by the many-CTA radix sort / scan: the neighbour
+    enumeration equals the reference's triplet for triplet, the forces agree to 1e-10 (forces.py:208-283)."""
+    rng = np.random.default_rng(77)
+    n, n_obs, side = 2048, 100_000, 1000.0
+    w = synth.make_config(2, n=n)
+    loc = w.loc.copy()
+    loc[:, :2] = rng.uniform(0.0, side, size=(n, 2))
+    centres = rng.uniform(0.0, side, size=(n_obs, 2))
+    t = 2.0 * np.pi * np.arange(6) / 6
+    ring0 = 0.3 * np.column_stack((np.cos(t), np.sin(t)))
+    rings = [c + ring0 for c in centres]
+    vels = rng.normal(0.0, 3.0, size=(n_obs, 2))
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+    ctx.upload_state(loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+    offsets = 6 * np.arange(n_obs + 1, dtype=np.int64)
+    ctx.set_obstacles_csr(native.DYNAMIC_OBSTACLE, centres, vels, offsets, np.concatenate(rings))
+    scene = G.scene_for(w, sfm_config)
+    want_f, want = O.obstacle_force(loc, w.vel, w.radius, centres, rings, vels, scene.dynamic, False, return_pairs=True)
+    got = ctx.enumerate_pairs(native.DYNAMIC_OBSTACLE, capacity=1 << 20)
+    assert len(want) > 100_000
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_allclose(ctx.force(native.DYNAMIC_OBSTACLE), want_f, rtol=1e-10, atol=1e-10)
+    # same answer when the set is uploaded again (re-sorted) and when a mid-sized set takes the many-CTA path
+    ctx.set_obstacles_csr(native.DYNAMIC_OBSTACLE, centres, vels, offsets, np.concatenate(rings))
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.DYNAMIC_OBSTACLE, capacity=1 << 20), want)
+
+
+def test_many_cta_sort_and_scan_on_small_sets(sfm_config, monkeypatch):
+    """SFM_SORT_SINGLE_MAX=0 sends every set through the many-CTA sort: the cfg2 enumerations stay bit-exact."""
+    monkeypatch.setenv('SFM_SORT_SINGLE_MAX', '0')
+    w = synth.make_config(2)
+    ctx = make_context(w, sfm_config)
+    scene = G.scene_for(w, sfm_config)
+    _, want = O.border_force(w.loc, w.radius, w.mode, scene.borders, scene.section_center, scene.section_length,
+                             scene.border, False, return_pairs=True)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.BORDER), want)
+    _, want = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in w.static_obstacles],
+                               [r for _, r in w.static_obstacles], None, scene.static, False, return_pairs=True)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.STATIC_OBSTACLE), want)
