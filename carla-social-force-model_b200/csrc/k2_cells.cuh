@@ -362,7 +362,7 @@ struct SegArgs {
     const int* cell_item;
     // parameters
     MoussaidD mp;
-    double border_a, border_b;
+    double border_a, border_b, neg_inv_border_b;   // -1 / b, so that exp(-dist / b) costs no division
     int use_radius;
     double2* f_out;                 // [n]
     int n_groups;                   // ceil(n / 32) pedestrian groups
@@ -373,32 +373,35 @@ struct SegArgs {
     long long emit_capacity;
 };
 
+// `nrm` = np.linalg.norm(loc - point) as the nearest-point search already evaluated it (numpy's arithmetic), or < 0 to have
+// it computed here.  Unit vectors are formed with one reciprocal and two products instead of two divisions (a few ulp from
+// numpy's quotient; the enumeration, which is what must be bit-exact, does not depend on them).
 template <int KIND>   // 0: border (exponential repulsion), 1: obstacle (Moussaid)
 __device__ __forceinline__ double2 segment_force(const SegArgs& a, double px, double py, double vx, double vy,
-                                                 double radius, double2 P, double2 ovel) {
+                                                 double radius, double2 P, double2 ovel, double nrm) {
     if (KIND == 0) {
         // forces.py:158-165: direction from the border point to the pedestrian
         const double dx = __dsub_rn(px, P.x), dy = __dsub_rn(py, P.y);
-        const double nrm = norm2_np(dx, dy);
-        const double dv = (nrm == 0.0) ? 1.0 : nrm;
-        const double ex = __ddiv_rn(dx, dv), ey = __ddiv_rn(dy, dv);
+        if (nrm < 0.0) nrm = norm2_np(dx, dy);
+        const double rinv = __ddiv_rn(1.0, (nrm == 0.0) ? 1.0 : nrm);
+        const double ex = __dmul_rn(dx, rinv), ey = __dmul_rn(dy, rinv);
         double dist = nrm;
         if (a.use_radius) dist = __dsub_rn(dist, radius);
-        const double mag = exp(__ddiv_rn(__dmul_rn(-1.0, dist), a.border_b));
+        const double mag = exp(__dmul_rn(dist, a.neg_inv_border_b));
         return make_double2(__dmul_rn(__dmul_rn(ex, a.border_a), mag), __dmul_rn(__dmul_rn(ey, a.border_a), mag));
     } else {
         // forces.py:233-270
         const double dx = __dsub_rn(P.x, px), dy = __dsub_rn(P.y, py);
-        const double nrm = norm2_np(dx, dy);
-        const double dv = (nrm == 0.0) ? 1.0 : nrm;
-        const double ex = __ddiv_rn(dx, dv), ey = __ddiv_rn(dy, dv);
+        if (nrm < 0.0) nrm = norm2_np(dx, dy);
+        const double rinv = __ddiv_rn(1.0, (nrm == 0.0) ? 1.0 : nrm);
+        const double ex = __dmul_rn(dx, rinv), ey = __dmul_rn(dy, rinv);
         double dl = nrm;
         if (a.use_radius) dl = __dsub_rn(dl, radius);
         const double wx = __dsub_rn(vx, ovel.x), wy = __dsub_rn(vy, ovel.y);
         const double Dx = __dadd_rn(__dmul_rn(a.mp.lambda, wx), ex), Dy = __dadd_rn(__dmul_rn(a.mp.lambda, wy), ey);
         const double Dn = norm2_np(Dx, Dy);
-        const double Dv = (Dn == 0.0) ? 1.0 : Dn;
-        const double tx = __ddiv_rn(Dx, Dv), ty = __ddiv_rn(Dy, Dv);
+        const double Dinv = __ddiv_rn(1.0, (Dn == 0.0) ? 1.0 : Dn);
+        const double tx = __dmul_rn(Dx, Dinv), ty = __dmul_rn(Dy, Dinv);
         const double nx = __dmul_rn(ty, -1.0), ny = tx;
         // stateutils.py:104-112: angle(e) - angle(t) wrapped once into [-pi, pi] == atan2(t x e, t . e): one atan2 instead
         // of two (equal to the reference's difference to a few ulp; exactly 0 when e == t, e.g. a standing pedestrian
@@ -561,14 +564,13 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                 const double gy = fmax(fmax(y0 - cen_l.y, cen_l.y - y1), 0.0);
                 accept_l = !(gx * gx + gy * gy > cut_l * cut_l * 1.000000001);
             }
-            unsigned todo = __ballot_sync(0xffffffffu, accept_l);
+            // item -> warp by the item's own index, so a pedestrian's summation order does not depend on which other
+            // pedestrians share its group (results are reproducible under any pedestrian ordering)
+            unsigned todo = __ballot_sync(0xffffffffu, accept_l && (s_l % K2_WARPS) == wid);
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                // item -> warp by the item's own index, so a pedestrian's summation order does not depend on which
-                // other pedestrians share its group (results are reproducible under any pedestrian ordering)
                 const int s = __shfl_sync(0xffffffffu, s_l, src);
-                if ((s % K2_WARPS) != wid) continue;
                 const double cxs = __shfl_sync(0xffffffffu, cen_l.x, src), cys = __shfl_sync(0xffffffffu, cen_l.y, src);
                 const double cut = __shfl_sync(0xffffffffu, cut_l, src);
                 const int o0 = __shfl_sync(0xffffffffu, o0_l, src), o1 = __shfl_sync(0xffffffffu, o1_l, src);
@@ -597,8 +599,13 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                 // ---- direct path: index window around the projection on the item's chord (header), float64 inside it
                 bool direct = false;
                 int k_lo = 0, k_cnt = 0;
+                double best = -1.0;                 // distance to the nearest point where the search already has it
+                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
                 if (a.chord0) {
-                    const float4 c0 = __ldg(&a.chord0[2 * s]), c1 = __ldg(&a.chord0[2 * s + 1]);
+                    c0 = __ldg(&a.chord0[2 * s]);
+                    c1 = __ldg(&a.chord0[2 * s + 1]);
+                }
+                if (c1.x > 0.0f || (a.chord0 && c1.z == 0.0f)) {        // (uniform: the item has a usable chord record)
                     const float wx = pxf - c0.x, wy = pyf - c0.y, nm1 = c1.z;
                     const float kap = fmaf(wx, c0.z, wy * c0.w) * c1.x * nm1;
                     const float ks = fminf(fmaxf(rintf(kap), 0.0f), nm1);
@@ -609,7 +616,7 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                     const float Q = 4.0f * c1.y * (Ds + c1.y) * (nm1 * nm1) * c1.x;
                     const float rho = fmaf(sqrtf(fmaf(del, del, Q)), 1.001f, 0.004f);
                     const float lo_f = fminf(fmaxf(ceilf(kap - rho), 0.0f), ks), hi_f = fmaxf(fminf(floorf(kap + rho), nm1), ks);
-                    const bool ok = (c1.x > 0.0f || nm1 == 0.0f) && (hi_f - lo_f) < 8.0f;          // NaN / inf -> false
+                    const bool ok = (hi_f - lo_f) < 8.0f;                                          // NaN / inf -> false
                     direct = __all_sync(0xffffffffu, !pass || ok);
                     if (direct && pass) {
                         k_lo = (int)lo_f;
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                     }
                 }
                 if (direct) {
-                    double best = __longlong_as_double(0x7ff0000000000000LL);
+                    best = __longlong_as_double(0x7ff0000000000000LL);
                     for (int j = 0; __any_sync(0xffffffffu, j < k_cnt); ++j) {
                         if (j < k_cnt) {
                             const int q = o0 + k_lo + j;
@@ -629,8 +636,10 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                             }
                         }
                     }
-                    if (pass && !(best < __longlong_as_double(0x7ff0000000000000LL)))
+                    if (pass && !(best < __longlong_as_double(0x7ff0000000000000LL))) {
                         best_q = exact_argmin(a.point, o0, o1, px, py);            // non-finite coordinates: full scan
+                        best = -1.0;
+                    }
                 } else {
                 // Nearest point, stage 1 (float32, all lanes in lock step over the staged points): the smallest squared
                 // distance m1 and the index window [lo, hi] of every point within tol of it, in one pass.
@@ -707,7 +716,7 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                 }
                 if (pass) {
                     const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
-                                                          KIND ? a.velocity[s] : make_double2(0.0, 0.0));
+                                                          KIND ? a.velocity[s] : make_double2(0.0, 0.0), best);
                     fx = __dadd_rn(fx, f.x);
                     fy = __dadd_rn(fy, f.y);
                     if (a.emit) {

@@ -759,6 +759,9 @@ int upload_set(sfm_ctx* c, SetStorage& st, int64_t count, const double* centers,
         float inv = (uu > 0.0 && P > 1) ? (float)(1.0 / uu) : 0.0f;
         float Ef = std::nextafter((float)Em, INFINITY);
         if (!std::isfinite(Em) || !std::isfinite((double)inv) || !std::isfinite(cut[i]) || P > (1 << 22)) { inv = 0.0f; Ef = 0.0f; }
+        // the window half-width is at least 2 E (P-1) / |u| index units: beyond 4 the 8-point limit can never be met
+        // (closed rings, strongly curved sections) and the kernel does not even try
+        if (inv > 0.0f && 2.0 * Em * (double)(P - 1) * std::sqrt((double)inv) > 4.0) inv = 0.0f;
         const float nm1 = (inv > 0.0f) ? (float)(P - 1) : (P == 1 && std::isfinite(Em) ? 0.0f : 1.0f);   // 1 with inv = 0: direct path off
         chord0[2 * i] = make_float4(ax, ay, ux, uy);
         chord0[2 * i + 1] = make_float4(inv, Ef, nm1, nm1 > 0.0f ? 1.0f / nm1 : 0.0f);
@@ -816,7 +819,7 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
     a.chord0 = c->k2_direct ? st.s.chord0 : nullptr;
     a.grid = st.s.grid; a.cell_start = st.s.cell_start; a.cell_item = st.s.cell_item;
     a.mp = make_moussaid_d(cls == SFM_FORCE_DYNAMIC_OBSTACLE ? c->params.dynamic_obs : c->params.static_obs);
-    a.border_a = c->params.border_a; a.border_b = c->params.border_b;
+    a.border_a = c->params.border_a; a.border_b = c->params.border_b; a.neg_inv_border_b = -1.0 / c->params.border_b;
     a.use_radius = c->params.use_ped_radius;
     a.f_out = out.p;
     a.eval_count = eval_count;
