@@ -177,4 +177,21 @@ __global__ void __launch_bounds__(256) k3_integrate(StepArgs a) {
     if (a.advance_routes) advance_waypoint(a.routes, a.mm, i, L.x, L.y, a.wp_rw, a.mode_rw, a.sim_time);
 }
 
+// calculate_new_velocities for a force array the caller composed itself (pedestrian_simulation.py:117-124 with
+// stateutils.cap_velocity, stateutils.py:18-23): v' = v + dt F, clamped to target_speed * max_speed_factor -- numpy's
+// operation order, unfused, so the result equals the reference's bit for bit.  Writes the new velocity into `vels`.
+__global__ void __launch_bounds__(256) k3_apply_force(int64_t n, double4* vels, const double* __restrict__ force, double dt,
+                                                      double max_speed_factor) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 V = vels[i];
+    double vx = __dadd_rn(V.x, __dmul_rn(dt, force[3 * i + 0]));
+    double vy = __dadd_rn(V.y, __dmul_rn(dt, force[3 * i + 1]));
+    double vz = __dadd_rn(V.z, __dmul_rn(dt, force[3 * i + 2]));
+    double sp = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+    if (sp == 0.0) sp = 1.0;
+    const double factor = fmin(1.0, __ddiv_rn(__dmul_rn(V.w, max_speed_factor), sp));
+    vels[i] = make_double4(__dmul_rn(vx, factor), __dmul_rn(vy, factor), __dmul_rn(vz, factor), V.w);
+}
+
 }  // namespace sfm

@@ -1475,6 +1475,18 @@ int sfm_tick_records(sfm_ctx* c, int64_t n, void* records, int64_t stride, const
     return 0;
 }
 
+int sfm_host_register(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail("bad host range");
+    SFM_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int sfm_host_unregister(void* ptr) {
+    if (!ptr) return fail("null pointer");
+    SFM_CUDA(cudaHostUnregister(ptr));
+    return 0;
+}
+
 int sfm_host_column_gather(const void* records, int64_t stride, int64_t offset, int64_t width, int64_t n, void* packed) {
     if (n < 0 || width <= 0 || (n > 0 && (!records || !packed))) return fail("bad column description");
     const uint8_t* base = static_cast<const uint8_t*>(records) + offset;
@@ -1491,6 +1503,27 @@ int sfm_host_column_equal(const void* records, int64_t stride, int64_t offset, i
     *equal = 1;
     for (int64_t i = 0; i < n; ++i)
         if (std::memcmp(base + i * stride, want + i * width, (size_t)width) != 0) { *equal = 0; break; }
+    return 0;
+}
+
+int sfm_apply_force(sfm_ctx* c, int64_t n, const double* force, double* new_vel) {
+    SFM_TRY(check_ctx(c));
+    if (!c->have_params) return fail("sfm_set_params must be called first");
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (n == 0) return 0;
+    if (!force || !new_vel) return fail("null array");
+    SFM_CUDA(cudaMemcpyAsync(c->raw_a.p, force, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    {
+        SpanGuard g(c, ST_INTEGRATE);
+        k3_apply_force<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->vels.p, c->raw_a.p, c->params.step_length,
+                                                             c->params.max_speed_factor);
+        unpack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->locr.p, c->vels.p, nullptr, c->raw_b.p);
+        c->launches += 2;
+        SFM_CUDA(cudaGetLastError());
+    }
+    c->staged = false;
+    SFM_CUDA(cudaMemcpyAsync(new_vel, c->raw_b.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -25,7 +25,6 @@ from ped_mode_manager import PedMode
 from pedestrian_state import PedState
 from sfm_b200 import native
 from sfm_b200.session import get_session
-from stateutils import cap_velocity
 
 _NATIVE_ORDER = {name: k for k, name in enumerate(native.FORCE_CLASSES)}
 
@@ -139,6 +138,7 @@ class PedestrianSimulation:
         ctx = session.ctx
         self._bind_device(session)
         cols = table.columns
+        session.pin(state)
         on_device = not self.record_states                  # the mode bookkeeping of :63-73 runs in K4a
         if session.resident_table is not table or ctx.n != len(state):
             ctx.upload_state(*self.peds.device_columns(cols['current_mode']))
@@ -204,8 +204,13 @@ class PedestrianSimulation:
             session.owner[which], session.set_version[which] = None, 'empty'
 
     def calculate_new_velocities(self, force):
-        """New desired velocities from a force array (pedestrian_simulation.py:117-124)."""
-        desired_velocity = cap_velocity(self.peds.vel() + self.step_length * force, self.peds.max_speed())
+        """New desired velocities from a force array (pedestrian_simulation.py:117-124) -- on the device too
+        (``sfm_apply_force``: v + dt F, then the speed clamp of stateutils.py:18-23, in numpy's operation order)."""
+        session = get_session()
+        session.set_params(native.params_from_config(self.sfm_config, self.step_length,
+                                                     enable={name: name in self.forces for name in native.FORCE_CLASSES}))
+        session.upload_peds(self.peds, getattr(self, '_mode_codes', None))
+        desired_velocity = session.ctx.apply_force(np.ascontiguousarray(force, dtype=np.float64))
         self.new_velocities = self.peds.state[['id', 'vel']]
         self.new_velocities['vel'] = desired_velocity
 

@@ -24,8 +24,8 @@ ABI_VERSION = 3
 SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create', 'sfm_destroy', 'sfm_set_stream',
            'sfm_synchronize', 'sfm_set_params', 'sfm_set_origin', 'sfm_set_partition', 'sfm_upload_state',
            'sfm_update_kinematics', 'sfm_update_targets', 'sfm_download_state', 'sfm_set_borders', 'sfm_set_obstacles',
-           'sfm_force', 'sfm_enumerate_pairs', 'sfm_count_point_evaluations', 'sfm_step', 'sfm_tick_host', 'sfm_tick_records',
-           'sfm_host_column_gather', 'sfm_host_column_equal', 'sfm_download_force',
+           'sfm_force', 'sfm_enumerate_pairs', 'sfm_count_point_evaluations', 'sfm_step', 'sfm_tick_host', 'sfm_tick_records', 'sfm_apply_force',
+           'sfm_host_column_gather', 'sfm_host_column_equal', 'sfm_host_register', 'sfm_host_unregister', 'sfm_download_force',
            'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_stage', 'sfm_step_begin', 'sfm_step_end',
            'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats',
            # lifecycle
@@ -117,7 +117,10 @@ def lib():
         'sfm_count_point_evaluations': (C.c_int, [p_ctx, C.c_int, p_i64, p_i64]),
         'sfm_step': (C.c_int, [p_ctx, C.c_int, C.c_int]),
         'sfm_tick_host': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d]),
+        'sfm_apply_force': (C.c_int, [p_ctx, i64, p_d, p_d]),
         'sfm_tick_records': (C.c_int, [p_ctx, i64, C.c_void_p, i64, p_i64, C.c_double, C.c_int, p_i64]),
+        'sfm_host_register': (C.c_int, [C.c_void_p, C.c_size_t]),
+        'sfm_host_unregister': (C.c_int, [C.c_void_p]),
         'sfm_host_column_gather': (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p]),
         'sfm_host_column_equal': (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p, C.POINTER(C.c_int)]),
         'sfm_download_force': (C.c_int, [p_ctx, i64, p_d]),
@@ -176,6 +179,22 @@ def _f64(a, shape=None):
 
 def _ptr(a, ctype=C.c_double):
     return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+class PinnedArray:
+    """Keeps a numpy array page-locked (``sfm_host_register``) and alive until ``release`` -- DMA straight out of it."""
+
+    def __init__(self, array):
+        self.array = array                       # the reference keeps the memory from being freed while it is registered
+        self.ptr = array.ctypes.data
+        span = (len(array) - 1) * array.strides[0] + array.dtype.itemsize if len(array) else 0
+        self.ok = span > 0 and lib().sfm_host_register(C.c_void_p(self.ptr), span) == 0
+
+    def release(self):
+        if self.ok:
+            lib().sfm_host_unregister(C.c_void_p(self.ptr))
+            self.ok = False
+        self.array = None
 
 
 def column_gather(state, field, width):
@@ -377,6 +396,13 @@ class Context:
                                           _ptr(offsets, C.c_int64), float(sim_time), int(bool(tick_modes)),
                                           _ptr(counters, C.c_int64)))
         return counters
+
+    def apply_force(self, force, out=None):
+        """calculate_new_velocities on the device for a caller-composed force [n, 3]; returns the new velocities."""
+        force = _f64(force, (self.n, 3))
+        out = np.empty((self.n, 3)) if out is None else out
+        _check(self._lib.sfm_apply_force(self._h, self.n, _ptr(force), _ptr(out)))
+        return out
 
     def download_force(self, out=None):
         out = np.empty((self.n, 3)) if out is None else out

@@ -24,6 +24,16 @@ class Session:
         self.resident_table = None          # ModeTable whose pedestrian rows (and machines) are on the device
         self.machines_version = None        # ... and the table version its device mirror reflects
         self.traffic_version = None
+        self.pinned = None                  # native.PinnedArray of the PedState table the resident tick copies from
+
+    def pin(self, state):
+        """Page-lock the pedestrian table the resident tick hands to ``sfm_tick_records`` (re-done when the table is
+        replaced by a spawn / despawn); a failed registration just leaves the copy on the driver's staging path."""
+        if self.pinned is not None and self.pinned.array is state:
+            return
+        if self.pinned is not None:
+            self.pinned.release()
+        self.pinned = native.PinnedArray(state)
 
     def set_params(self, params):
         """Make ``params`` the context's parameters unless they already are.  Point sets stay resident across parameter
@@ -67,5 +77,7 @@ def get_session():
 def reset_session():
     global _session
     if _session is not None:
+        if _session.pinned is not None:
+            _session.pinned.release()
         _session.ctx.close()
     _session = None

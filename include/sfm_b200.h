@@ -144,11 +144,19 @@ int sfm_tick_host(sfm_ctx* ctx, int64_t n, const double* loc, const double* vel,
  * mode codes are those of the last sfm_upload_state / sfm_update_targets. */
 int sfm_tick_records(sfm_ctx* ctx, int64_t n, void* records, int64_t stride, const int64_t* field_offsets,
                      double sim_time, int tick_modes, int64_t* counters4);
+/* Page-lock a host range the caller owns (e.g. the PedState table) so that sfm_tick_records / sfm_tick_host copy from it
+ * by DMA instead of through the driver's staging buffer; the caller keeps the memory alive until sfm_host_unregister. */
+int sfm_host_register(void* ptr, size_t bytes);
+int sfm_host_unregister(void* ptr);
 /* Host-side helpers for AoS tables (no device work): copy one column out of / compare it with a packed array.  The
  * drop-in uses them on the `mode` column (object pointers) to notice that the table holds other objects than before. */
 int sfm_host_column_gather(const void* records, int64_t stride, int64_t offset, int64_t width, int64_t n, void* packed);
 int sfm_host_column_equal(const void* records, int64_t stride, int64_t offset, int64_t width, int64_t n,
                           const void* packed, int* equal);
+/* calculate_new_velocities for a caller-composed force array force[n][3] (pedestrian_simulation.py:117-124 with
+ * stateutils.cap_velocity, stateutils.py:18-23): v' = v + dt F clamped to target_speed * max_speed_factor, on the state
+ * last uploaded; the new velocities replace the device's and are copied to new_vel[n][3]. */
+int sfm_apply_force(sfm_ctx* ctx, int64_t n, const double* force, double* new_vel);
 /* Total force / one class's force of the most recent step, [n][3]. */
 int sfm_download_force(sfm_ctx* ctx, int64_t n, double* out);
 int sfm_download_class_force(sfm_ctx* ctx, int force_class, int64_t n, double* out);

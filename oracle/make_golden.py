@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the imported, unmodified reference (build container only).
 
-TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden [--only cfg1|cfg2|lifecycle|csv]
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden [--only cfg1|cfg2|cfg2traj|lifecycle|csv]
 The inputs are regenerated from ``sfm_b200.synth`` by seed; each file stores a SHA-256 of the input bytes so that a
 drift of the generator is detected instead of silently comparing against stale outputs.
 """
@@ -64,6 +64,21 @@ def golden_cfg2(ref, cfg):
             tag = f"r{int(use_radius)}_z{int(z_spread > 0)}"
             np.savez_compressed(os.path.join(GOLDEN, f'cfg2_forces_{tag}.npz'), digest=workload_digest(w),
                                 **{f'F_{k}': v for k, v in forces.items()})
+
+
+CFG2_TRAJECTORY_STEPS = (1, 5, 10)
+
+
+def golden_cfg2_trajectory(ref, cfg):
+    """Ten ticks of the reference's own loop at N = 4,096 (dense all-pairs regime, all five forces, vehicles moving):
+    positions and velocities of every second pedestrian after ticks 1, 5 and 10 (about 3 minutes, 4.4 GB)."""
+    w = synth.make_config(2)
+    t0 = time.time()
+    out = ref_loader.run_ticks(ref, w, cfg, max(CFG2_TRAJECTORY_STEPS), record_forces=False)
+    print(f'cfg2 trajectory: {time.time() - t0:.1f}s', flush=True)
+    keep = list(CFG2_TRAJECTORY_STEPS)
+    np.savez_compressed(os.path.join(GOLDEN, 'cfg2_trajectory.npz'), digest=workload_digest(w), steps=np.array(keep),
+                        rows=np.arange(0, w.n, 2), loc=out['loc'][keep][:, ::2], vel=out['vel'][keep][:, ::2])
 
 
 def lifecycle_digest(w, life):
@@ -149,6 +164,8 @@ def main():
         golden_cfg1(ref, cfg)
     if args.only in (None, 'cfg2'):
         golden_cfg2(ref, cfg)
+    if args.only in (None, 'cfg2traj'):
+        golden_cfg2_trajectory(ref, cfg)
     if args.only in (None, 'lifecycle'):
         golden_lifecycle(ref, cfg)
         golden_lifecycle_despawn(ref, cfg)

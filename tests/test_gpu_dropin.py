@@ -166,3 +166,20 @@ def test_resident_tick_keeps_sets_and_rows_on_device(sfm_config):
     sim.peds.state['vel'] = state['vel']
     sim.tick(1.0)
     assert np.abs(sim.peds.state['vel'] - want).max() < 1e-6
+
+
+def test_calculate_new_velocities_on_device_equals_numpy(sfm_config):
+    """calculate_new_velocities(force) for a caller-composed force array runs on the device (sfm_apply_force) in numpy's
+    operation order: bit-identical to pedestrian_simulation.py:117-124 / stateutils.py:18-23 evaluated by the oracle."""
+    from oracle import sfm_oracle as O
+    w = synth.make_config(1)
+    sim = build_sim(w, sfm_config, record_states=False)
+    rng = np.random.default_rng(3)
+    force = rng.normal(0.0, 30.0, size=(w.n, 3))
+    force[5] = 0.0
+    sim.peds.state['vel'][5] = 0.0                                   # zero speed: the divide-by-one branch
+    want = O.new_velocities(sim.peds.state['vel'].copy(), force, sim.peds.state['target_speed'].copy(), w.step_length)
+    sim.calculate_new_velocities(force)
+    got = sim.get_new_velocities()
+    assert np.shares_memory(got, sim.peds.state)
+    np.testing.assert_array_equal(got['vel'], want)

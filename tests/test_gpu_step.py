@@ -31,6 +31,28 @@ def test_cfg1_100_step_trajectory(sfm_config):
             assert (speed <= w.target_speed * 1.3 * (1 + 1e-12)).all()
 
 
+def test_cfg2_10_step_trajectory_against_reference_golden(sfm_config):
+    """BASELINE.json configs[1] as a run: ten ticks of N = 4,096 with all five forces and moving vehicles against the
+    trajectory the imported reference produced.  Stated tolerance: position deviation <= 2e-6 m after one tick, median
+    <= 1e-5 m and max <= 1e-3 m after ten (float32 pair forces feeding a dense, chaotic crowd)."""
+    w = synth.make_config(2)
+    g = G.load('cfg2_trajectory.npz', w)
+    ctx = make_context(w, sfm_config)
+    steps, rows = list(g['steps']), g['rows']
+    for step in range(max(steps)):
+        set_vehicles(ctx, w, step)
+        ctx.step(1, integrate_positions=True)
+        if step + 1 in steps:
+            k = steps.index(step + 1)
+            loc, vel = ctx.download_state()
+            dev = np.linalg.norm(loc[rows] - g['loc'][k], axis=1)
+            dv = np.linalg.norm(vel[rows] - g['vel'][k], axis=1)
+            limit = {1: 2e-6, 5: 1e-4, 10: 1e-3}[step + 1]
+            assert dev.max() <= limit, (step + 1, dev.max())
+            if step + 1 == 10:
+                assert np.median(dev) <= 1e-5 and np.median(dv) <= 1e-4, (np.median(dev), np.median(dv))
+
+
 def test_one_step_matches_oracle_velocity_update(sfm_config):
     """With the pedestrian force off every remaining kernel is float64 in numpy's operation order: the whole step
     (forces, clamp, Euler) must then agree with the oracle to rounding."""

@@ -37,3 +37,20 @@ def test_cfg2_force_classes(sfm_config, use_radius, z):
     sel = slice(None) if rows is None else rows
     for name, f in per_class.items():
         np.testing.assert_allclose(f, g[f'F_{name}'][sel], rtol=1e-12, atol=1e-12, err_msg=name)
+
+
+def test_cfg2_trajectory_first_ticks(sfm_config):
+    """The reference's own 10-tick loop at N = 4,096 (tests/golden/cfg2_trajectory.npz): the oracle reproduces the state
+    after ticks 1 and 5 (the GPU test covers all ten)."""
+    w = synth.make_config(2)
+    g = G.load('cfg2_trajectory.npz', w)
+    scene = G.scene_for(w, sfm_config)
+    loc, vel = w.loc.copy(), w.vel.copy()
+    steps, rows = list(g['steps']), g['rows']
+    for step in range(5):
+        dyn, dyn_vel = G.dyn_for(w, step)
+        loc, vel, _ = O.step(scene, loc, vel, w.next_waypoint, w.radius, w.target_speed, w.mode, dyn, dyn_vel)
+        if step + 1 in steps:
+            k = steps.index(step + 1)
+            np.testing.assert_allclose(loc[rows], g['loc'][k], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(vel[rows], g['vel'][k], rtol=1e-9, atol=1e-9)
