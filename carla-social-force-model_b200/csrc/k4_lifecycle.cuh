@@ -69,10 +69,12 @@ __device__ __forceinline__ double norm2d(double x, double y) {
     return __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
 }
 
-// Intersection of segment p0-p1 with q0-q1 (host mirror: check_traffic._segment_intersection).  Returns false when the
-// segments do not meet; for collinear overlap the overlap's midpoint.
+// Intersection of segment p0-p1 with q0-q1 as shapely's LineString.intersection gives it (host mirror:
+// check_traffic._segment_intersection).  Returns false when empty; otherwise the hit as the segment h0-h1 -- a point has
+// h0 == h1, collinear overlapping segments yield both ends of the overlap, and a zero-length p (the pedestrian stands on
+// its waypoint) hits iff that point lies on q.
 __device__ __forceinline__ bool segment_hit(double p0x, double p0y, double p1x, double p1y, double q0x, double q0y,
-                                            double q1x, double q1y, double& hx, double& hy) {
+                                            double q1x, double q1y, double& h0x, double& h0y, double& h1x, double& h1y) {
     const double rx = __dsub_rn(p1x, p0x), ry = __dsub_rn(p1y, p0y);
     const double sx = __dsub_rn(q1x, q0x), sy = __dsub_rn(q1y, q0y);
     const double denom = __dsub_rn(__dmul_rn(rx, sy), __dmul_rn(ry, sx));
@@ -81,21 +83,39 @@ __device__ __forceinline__ bool segment_hit(double p0x, double p0y, double p1x, 
         const double t = __ddiv_rn(__dsub_rn(__dmul_rn(qpx, sy), __dmul_rn(qpy, sx)), denom);
         const double u = __ddiv_rn(__dsub_rn(__dmul_rn(qpx, ry), __dmul_rn(qpy, rx)), denom);
         if (!(t >= 0.0 && t <= 1.0 && u >= 0.0 && u <= 1.0)) return false;
-        hx = __dadd_rn(p0x, __dmul_rn(t, rx));
-        hy = __dadd_rn(p0y, __dmul_rn(t, ry));
+        h0x = h1x = __dadd_rn(p0x, __dmul_rn(t, rx));
+        h0y = h1y = __dadd_rn(p0y, __dmul_rn(t, ry));
         return true;
     }
     if (__dsub_rn(__dmul_rn(qpx, ry), __dmul_rn(qpy, rx)) != 0.0) return false;      // parallel, not collinear
     const double rr = __dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry));
-    if (rr == 0.0) return false;
+    if (rr == 0.0) {
+        const double ss = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+        h0x = h1x = p0x;
+        h0y = h1y = p0y;
+        if (ss == 0.0) return qpx == 0.0 && qpy == 0.0;
+        if (__dsub_rn(__dmul_rn(qpx, sy), __dmul_rn(qpy, sx)) != 0.0) return false;
+        const double t = __ddiv_rn(-__dadd_rn(__dmul_rn(qpx, sx), __dmul_rn(qpy, sy)), ss);
+        return t >= 0.0 && t <= 1.0;
+    }
     const double a = __ddiv_rn(__dadd_rn(__dmul_rn(qpx, rx), __dmul_rn(qpy, ry)), rr);
     const double b = __ddiv_rn(__dadd_rn(__dmul_rn(__dsub_rn(q1x, p0x), rx), __dmul_rn(__dsub_rn(q1y, p0y), ry)), rr);
     const double lo = fmax(fmin(a, b), 0.0), hi = fmin(fmax(a, b), 1.0);
     if (!(lo <= hi)) return false;
-    const double m = __dmul_rn(0.5, __dadd_rn(lo, hi));
-    hx = __dadd_rn(p0x, __dmul_rn(m, rx));
-    hy = __dadd_rn(p0y, __dmul_rn(m, ry));
+    h0x = __dadd_rn(p0x, __dmul_rn(lo, rx));
+    h0y = __dadd_rn(p0y, __dmul_rn(lo, ry));
+    h1x = __dadd_rn(p0x, __dmul_rn(hi, rx));
+    h1y = __dadd_rn(p0y, __dmul_rn(hi, ry));
     return true;
+}
+
+// intersection.distance(Point(x)) (check_traffic.py:52-54): to the point, or to the nearest point of the overlap segment
+__device__ __forceinline__ double hit_distance(double h0x, double h0y, double h1x, double h1y, double x, double y) {
+    const double vx = __dsub_rn(h1x, h0x), vy = __dsub_rn(h1y, h0y);
+    const double vv = __dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy));
+    if (vv == 0.0) return norm2d(__dsub_rn(h0x, x), __dsub_rn(h0y, y));
+    const double t = fmin(1.0, fmax(0.0, __ddiv_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, h0x), vx), __dmul_rn(__dsub_rn(y, h0y), vy)), vv)));
+    return norm2d(__dsub_rn(__dadd_rn(h0x, __dmul_rn(t, vx)), x), __dsub_rn(__dadd_rn(h0y, __dmul_rn(t, vy)), y));
 }
 
 struct ModeTickArgs {
@@ -206,13 +226,13 @@ __global__ void __launch_bounds__(K4_THREADS) k4_gap_acceptance(const ModeTickAr
             const double bx = __dsub_rn(c.x, h.x), by = __dsub_rn(c.y, h.y);                 // back  (:36)
             const double tx = __dadd_rn(fx, __dmul_rn(u.x, horizon)), ty = __dadd_rn(fy, __dmul_rn(u.y, horizon));
             if (fmax(bx, tx) < x0 || fmin(bx, tx) > x1 || fmax(by, ty) < y0 || fmin(by, ty) > y1) continue;
-            double ix, iy;
-            if (!segment_hit(px, py, gx, gy, bx, by, tx, ty, ix, iy)) continue;
+            double ix, iy, jx, jy;
+            if (!segment_hit(px, py, gx, gy, bx, by, tx, ty, ix, iy, jx, jy)) continue;
             const double vs = s_speed[v];
             if (vs == 0.0) continue;                                                          // :48-49
-            const double tti_ped = __ddiv_rn(norm2d(__dsub_rn(ix, px), __dsub_rn(iy, py)), speed);
-            const double tti_front = __ddiv_rn(norm2d(__dsub_rn(ix, fx), __dsub_rn(iy, fy)), vs);
-            const double tti_back = __ddiv_rn(norm2d(__dsub_rn(ix, bx), __dsub_rn(iy, by)), vs);
+            const double tti_ped = __ddiv_rn(hit_distance(ix, iy, jx, jy, px, py), speed);
+            const double tti_front = __ddiv_rn(hit_distance(ix, iy, jx, jy, fx, fy), vs);
+            const double tti_back = __ddiv_rn(hit_distance(ix, iy, jx, jy, bx, by), vs);
             if (__dsub_rn(tti_front, margin) < tti_ped && tti_ped < __dadd_rn(tti_back, margin)) {   // :57
                 a.blocked[k] = 1;
                 break;

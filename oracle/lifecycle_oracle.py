@@ -88,23 +88,46 @@ class Machines:
 
 
 def segment_intersection(p0, p1, q0, q1):
-    """Intersection point of segments p0-p1 and q0-q1, or None (collinear overlap: the overlap's midpoint)."""
+    """Intersection of segments p0-p1 and q0-q1 as shapely's ``LineString.intersection`` yields it (check_traffic.py:46):
+    None when empty, else the pair (h0, h1) -- a Point has h0 == h1, a collinear overlap is the LineString h0-h1.  A
+    zero-length pedestrian path (the pedestrian stands on its waypoint) meets the other segment iff that point lies on it."""
     r, s = p1 - p0, q1 - q0
     denom = r[0] * s[1] - r[1] * s[0]
     qp = q0 - p0
     if denom != 0.0:
         t = (qp[0] * s[1] - qp[1] * s[0]) / denom
         u = (qp[0] * r[1] - qp[1] * r[0]) / denom
-        return p0 + t * r if (0.0 <= t <= 1.0 and 0.0 <= u <= 1.0) else None
+        if 0.0 <= t <= 1.0 and 0.0 <= u <= 1.0:
+            h = p0 + t * r
+            return h, h
+        return None
     if qp[0] * r[1] - qp[1] * r[0] != 0.0:
         return None
     rr = r[0] * r[0] + r[1] * r[1]
     if rr == 0.0:
-        return None
+        ss = s[0] * s[0] + s[1] * s[1]
+        if ss == 0.0:
+            return (p0, p0) if (qp[0] == 0.0 and qp[1] == 0.0) else None
+        if qp[0] * s[1] - qp[1] * s[0] != 0.0:
+            return None
+        t = -(qp[0] * s[0] + qp[1] * s[1]) / ss
+        return (p0, p0) if 0.0 <= t <= 1.0 else None
     a = (qp[0] * r[0] + qp[1] * r[1]) / rr
     b = ((q1[0] - p0[0]) * r[0] + (q1[1] - p0[1]) * r[1]) / rr
     lo, hi = max(min(a, b), 0.0), min(max(a, b), 1.0)
-    return p0 + 0.5 * (lo + hi) * r if lo <= hi else None
+    return (p0 + lo * r, p0 + hi * r) if lo <= hi else None
+
+
+def hit_distance(hit, x):
+    """``intersection.distance(Point(x))`` (check_traffic.py:52-54): distance from x to the point, or to the nearest point
+    of the overlap segment."""
+    h0, h1 = hit
+    v = h1 - h0
+    vv = v[0] * v[0] + v[1] * v[1]
+    if vv == 0.0:
+        return np.linalg.norm(h0 - x)
+    t = min(1.0, max(0.0, ((x[0] - h0[0]) * v[0] + (x[1] - h0[1]) * v[1]) / vv))
+    return np.linalg.norm(h0 + t * v - x)
 
 
 def check_traffic(ped_loc, ped_goal, crossing_speed, safety_margin, veh_centres, veh_velocities, veh_extents):
@@ -127,9 +150,9 @@ def check_traffic(ped_loc, ped_goal, crossing_speed, safety_margin, veh_centres,
         speed = np.linalg.norm(vel)
         if speed == 0:                                                        # :48-49
             continue
-        tti_ped = np.linalg.norm(hit - ped_loc) / crossing_speed
-        tti_front = np.linalg.norm(hit - front) / speed
-        tti_back = np.linalg.norm(hit - back) / speed
+        tti_ped = hit_distance(hit, ped_loc) / crossing_speed
+        tti_front = hit_distance(hit, front) / speed
+        tti_back = hit_distance(hit, back) / speed
         if tti_front - safety_margin < tti_ped < tti_back + safety_margin:    # :57
             return False
     return True

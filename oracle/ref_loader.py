@@ -38,6 +38,19 @@ class _Empty:
     is_empty = True
 
 
+class _Overlap:
+    """What shapely returns for two collinear overlapping segments: the LineString of the overlap; ``distance`` to a
+    point is the distance to its nearest point."""
+    is_empty = False
+
+    def __init__(self, h0, h1):
+        self.hit = (h0, h1)
+
+    def distance(self, other):
+        from oracle.lifecycle_oracle import hit_distance
+        return float(hit_distance(self.hit, other.xy))
+
+
 class _LineString:
     """Stand-in for shapely.geometry.LineString restricted to one segment."""
 
@@ -47,7 +60,9 @@ class _LineString:
     def intersection(self, other):
         from oracle.lifecycle_oracle import segment_intersection
         hit = segment_intersection(self.a, self.b, other.a, other.b)
-        return _Empty() if hit is None else _Point(hit)
+        if hit is None:
+            return _Empty()
+        return _Point(hit[0]) if hit[0] is hit[1] or np.array_equal(hit[0], hit[1]) else _Overlap(*hit)
 
 
 def available():

@@ -191,3 +191,42 @@ def test_many_cta_sort_and_scan_on_small_sets(sfm_config, monkeypatch):
     _, want = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in w.static_obstacles],
                                [r for _, r in w.static_obstacles], None, scene.static, False, return_pairs=True)
     np.testing.assert_array_equal(ctx.enumerate_pairs(native.STATIC_OBSTACLE), want)
+
+
+def test_perception_threshold_change_needs_a_new_upload(sfm_config):
+    """The obstacle sets bake perception_threshold into their cutoffs and cell grid: after sfm_set_params changed it the
+    resident set is refused (no silent use of the old cutoff) until it is uploaded again -- then it follows the new one."""
+    w = synth.make_config(2, n=1024)
+    ctx = make_context(w, sfm_config)
+    before = ctx.force(native.STATIC_OBSTACLE)
+    cfg = dict(sfm_config, static_obstacle_force=dict(sfm_config['static_obstacle_force'], perception_threshold=6.0))
+    ctx.set_params(native.params_from_config(cfg, w.step_length))
+    with pytest.raises(native.SfmError, match='perception_threshold changed'):
+        ctx.force(native.STATIC_OBSTACLE)
+    ctx.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles], [r for _, r in w.static_obstacles])
+    scene = G.scene_for(w, cfg)
+    want, pairs = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in w.static_obstacles],
+                                   [r for _, r in w.static_obstacles], None, scene.static, False, return_pairs=True)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.STATIC_OBSTACLE), pairs)
+    after = ctx.force(native.STATIC_OBSTACLE)
+    np.testing.assert_allclose(after, want, rtol=1e-11, atol=1e-11)
+    assert np.abs(after - before).max() > 1e-3                      # the smaller threshold really dropped neighbours
+    ctx.set_params(native.params_from_config(sfm_config, w.step_length))        # back to the old threshold: stale again
+    with pytest.raises(native.SfmError):
+        ctx.step(1, True)
+
+
+def test_infinite_section_length_reaches_every_pedestrian(sfm_config):
+    """A section whose length (= cutoff, forces.py:149-150) is infinite is 'close' to every pedestrian of the crowd, not
+    only to those in the neighbouring grid cells."""
+    w = synth.make_config(2, n=2048)
+    length = w.section_length.copy()
+    length[3] = np.inf
+    ctx = make_context(w, sfm_config)
+    ctx.set_borders(w.borders, w.section_center, length)
+    scene = G.scene_for(w, sfm_config)
+    want, pairs = O.border_force(w.loc, w.radius, w.mode, w.borders, w.section_center, length, scene.border, False,
+                                 return_pairs=True)
+    assert (pairs[:, 1] == 3).sum() == w.n
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.BORDER), pairs)
+    np.testing.assert_allclose(ctx.force(native.BORDER), want, rtol=1e-11, atol=1e-11)

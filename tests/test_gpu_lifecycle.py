@@ -320,3 +320,25 @@ def test_recording_across_spawn_and_despawn(sfm_config, tmp_path):
     assert len(ped) == 1 + sum(len(ids) for ids, _ in frames)
     last = ped[-1].split(',')
     assert int(last[1]) == ticks - 1 and int(last[0]) == frames[-1][0][-1]
+
+
+def test_degenerate_gap_acceptance_on_device(sfm_config):
+    """K4a on the collinear / zero-length scenes of tests/degenerate_traffic.py: the decisions of the oracle (shapely's
+    overlap-segment semantics, check_traffic.py:46-58)."""
+    from tests.degenerate_traffic import scenes
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(sfm_config, 0.05))
+    for k, (loc, goal, speed, margin, centres, vels, extents, want) in enumerate(scenes()):
+        expect = LO.check_traffic(loc, goal, speed, margin, centres, vels, extents)
+        assert want is None or expect == want
+        n = 3                                                  # the scene's pedestrian between two bystanders
+        loc3, wp3 = np.zeros((n, 3)), np.zeros((n, 3))
+        loc3[:, :2], wp3[:, :2] = [[-50.0, 40.0], loc, [60.0, -40.0]], [[-50.0, 45.0], goal, [60.0, -45.0]]
+        mode = np.array([1, 4, 1], dtype=np.uint8)
+        ctx.upload_state(loc3, np.zeros((n, 3)), wp3, np.full(n, 0.3), np.full(n, speed / 1.5), mode)
+        ctx.set_mode_machines(np.full(n, speed / 1.5), np.full(n, speed), np.full(n, margin))
+        ctx.set_traffic(centres, vels, np.tile(extents[0], (len(centres), 1)))
+        ctx.tick_modes(0.0)
+        got = ctx.download_mode_codes()
+        assert (got[1] == 2) == expect, f'scene {k + 1}: device {got[1]}, oracle says cross={expect}'
+        assert got[0] == 1 and got[2] == 1

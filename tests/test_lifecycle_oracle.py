@@ -199,3 +199,48 @@ def test_oracle_spawn_and_despawn_reproduce_reference_golden(sfm_config):
     assert np.array_equal(g['alive'], got['alive']) and np.array_equal(g['mode'], got['mode'])
     assert g['alive'][0].sum() == 34 and g['alive'][46].sum() > g['alive'][44].sum()        # the second wave arrives
     assert np.array_equal(g['ids_final'], got['ids_final']) and np.abs(g['loc_final'] - got['loc_final']).max() <= 1e-9
+
+
+def test_degenerate_gap_acceptance_scenes():
+    ref = ref_loader.load() if ref_loader.available() else None
+    _degenerate_scenes(ref)
+
+
+def _degenerate_scenes(ref):
+    """Collinear and zero-length paths (tests/degenerate_traffic.py): the oracle, the drop-in's host function and -- where
+    the reference tree is present -- the reference's own check_traffic (over the LineString stand-in, which returns the
+    overlap segment like shapely) take the hand-derived decisions."""
+    import check_traffic as host
+    from ped_mode_manager import PedMode, PedModeManager
+    from tests.degenerate_traffic import scenes
+    dtype = [('loc', 'f8', (3,)), ('next_waypoint', 'f8', (3,)), ('mode', 'O')]
+    for k, (loc, goal, speed, margin, centres, vels, extents, want) in enumerate(scenes()):
+        got = LO.check_traffic(loc, goal, speed, margin, centres, vels, extents)
+        if want is not None:
+            assert got == want, f'scene {k + 1}'
+        ped = np.zeros(1, dtype=dtype)[0]
+        ped['loc'][:2], ped['next_waypoint'][:2] = loc, goal
+        ped['mode'] = PedModeManager('p_0', speed / 1.5, PedMode.CHECKING_TRAFFIC, 1.5, margin)
+        vehicles = [(c, None) for c in centres]
+        assert host.check_traffic(ped, vehicles, list(vels), list(extents)) == got, f'host, scene {k + 1}'
+        if ref is not None:
+            import importlib.util
+            import os
+            spec = importlib.util.spec_from_file_location('_ref_check_traffic',
+                                                          os.path.join(ref_loader.REFERENCE_DIR, 'check_traffic.py'))
+            mod = importlib.util.module_from_spec(spec)
+            import sys
+            saved = sys.modules.get('stateutils')
+            sys.modules['stateutils'] = ref.stateutils
+            try:
+                spec.loader.exec_module(mod)
+            finally:
+                if saved is not None:
+                    sys.modules['stateutils'] = saved
+                else:
+                    sys.modules.pop('stateutils', None)
+            rped = np.zeros(1, dtype=dtype)[0]
+            rped['loc'][:2], rped['next_waypoint'][:2] = loc, goal
+            rped['mode'] = ref.ped_mode_manager.PedModeManager('p_0', speed / 1.5, ref.ped_mode_manager.PedMode.CHECKING_TRAFFIC,
+                                                               1.5, margin)
+            assert mod.check_traffic(rped, vehicles, vels, extents) == got, f'reference, scene {k + 1}'
