@@ -118,6 +118,7 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
     const f32x2 dx = add2(sub2(xj, I.x), sub2(xlj, I.xl)), dy = add2(sub2(yj, I.y), sub2(ylj, I.yl));
     f32x2 dz = 0ull, wz = 0ull, Dz = 0ull;
     f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
+    const f32x2 dxy2 = d2;
     if (!PLANAR) {
         dz = add2(sub2(zj, I.z), sub2(zlj, I.zl));
         d2 = fma2(dz, dz, d2);
@@ -126,6 +127,7 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
     const f32x2 wx = sub2(I.vx, vxj), wy = sub2(I.vy, vyj);
     const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy);
     f32x2 D2 = fma2(Dy, Dy, mul2(Dx, Dx));
+    const f32x2 Dxy2 = D2;
     if (!PLANAR) {
         wz = sub2(I.vz, vzj);
         Dz = fma2(dz, rinv, wz);
@@ -143,13 +145,17 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
     unpack2(cross, cl, ch);
     unpack2(dot, tl, th);
     constexpr bool ASIN = PLANAR && (SFM_KS_ASIN != 0);
+    constexpr bool DIFF = (SFM_KS_ASIN != 0) && (SFM_KS_ANGLE != 0) && !SIGN0;
     f32x2 R = 0ull, theta;
     // (SIGN0 keeps the octant form: it returns theta = +-0 exactly for w parallel to d, which the difference form cannot)
-    if (ASIN && SFM_KS_ANGLE != 0 && !SIGN0) {
+    if (DIFF) {
         // first-quadrant angle phi = atan2(|sin|, |cos|) from sqrt2 sin(phi - pi/4) = |sin| - |cos|; then
-        // theta = sign(cross) (pi/2 + sign(dot) (phi - pi/2)) = copysign(pi/2, cross) + sign(cross dot) (phi - pi/2)
+        // theta = sign(cross) (pi/2 + sign(dot) (phi - pi/2)) = copysign(pi/2, cross) + sign(cross dot) (phi - pi/2).
+        // sin, cos = cross, dot / (|d_xy| |D_xy|): planar tiles have |d_xy| = |d|, |D_xy| = |D| (no extra MUFU); general
+        // tiles take one rsqrt of the product of the xy parts -- where the reciprocal of the octant form used to be
         R = mul2(rinv, Dinv);
-        const f32x2 q = mul2(pack2(fabsf(cl) - fabsf(tl), fabsf(ch) - fabsf(th)), R);
+        const f32x2 Rxy = PLANAR ? R : rsqrt2(mul2(dxy2, Dxy2));
+        const f32x2 q = mul2(pack2(fabsf(cl) - fabsf(tl), fabsf(ch) - fabsf(th)), Rxy);
         const f32x2 s = mul2(q, q);
         f32x2 p;
 #if SFM_KS_ASIN_TERMS == 6
@@ -213,7 +219,7 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
     if (RADIUS) {
         const f32x2 dl = sub2(sub2(mul2(d2, rinv), I.r), rj);
         y = fma2(mul2(dl, Dinv), c.k_exp, c.log2A);
-    } else if (ASIN) {
+    } else if (ASIN || DIFF) {
         y = fma2(mul2(d2, R), c.k_exp, c.log2A);                          // |d| / |D| = d2 (1/|d|)(1/|D|)
     } else {
         y = fma2(mul2(mul2(d2, rinv), Dinv), c.k_exp, c.log2A);
