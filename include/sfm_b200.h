@@ -161,8 +161,11 @@ int sfm_apply_force(sfm_ctx* ctx, int64_t n, const double* force, double* new_ve
 int sfm_download_force(sfm_ctx* ctx, int64_t n, double* out);
 int sfm_download_class_force(sfm_ctx* ctx, int force_class, int64_t n, double* out);
 
-/* ---- multi-GPU plumbing: the staged (pos, lambda*vel, radius) planes every rank all-gathers once per step -------- */
-/* Device pointer of the gather buffer [world][8][rows_pad] float32, and the size of one rank's block in bytes.
+/* ---- multi-GPU plumbing: the staged (pos hi/lo, lambda*vel, radius) planes every rank all-gathers once per step ---
+ * (SURVEY.md 8b sketched `sfm_comm_init(ctx, nccl_unique_id, rank, world)`: the library does not own a communicator --
+ *  NCCL is driven by the caller (torch.distributed) over tensor views of the two buffers below, or bypassed altogether by
+ *  the peer-memory exchange further down, where both collectives are fused into the library's own kernels.) */
+/* Device pointer of the gather buffer [world][11][rows_pad] float32, and the size of one rank's block in bytes.
  * After each sfm_step the caller all-gathers block `rank` into every rank's buffer (NCCL, in place). */
 int sfm_gather_buffer(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_rank);
 /* Multi-GPU tick in two halves.  sfm_step_begin enqueues the pair accumulation (each unordered pedestrian pair is
