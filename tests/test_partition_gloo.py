@@ -42,18 +42,24 @@ def _rank_main(rank, world, port, n, out_dir):
     bounds = engine.partition_rows(w.n, world)
     rows_pad = engine.padded_rows(bounds)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    # this rank's staged block: 8 float32 planes x rows_pad (x, y, z, r, lambda*vx, lambda*vy, lambda*vz, spare)
-    block = torch.zeros(8, rows_pad, dtype=torch.float32)
-    block[0:3, :hi - lo] = torch.from_numpy(w.loc[lo:hi].T.astype(np.float32))
-    block[3, :hi - lo] = torch.from_numpy(w.radius[lo:hi].astype(np.float32))
-    block[4:7, :hi - lo] = torch.from_numpy((2.0 * w.vel[lo:hi]).T.astype(np.float32))
-    block[0:2, hi - lo:] = 1.0e15                                   # pad rows sit far away
-    gathered = torch.zeros(world, 8, rows_pad, dtype=torch.float32)
+    # this rank's staged block: 11 float32 planes x rows_pad -- position hi parts (2^-6 m lattice), lo parts, radius,
+    # lambda * velocity, non-planar flag (csrc/sfm_common.cuh) -- restated on the host
+    PX, PXL, PR, PVX, PFLAG, NPLANES = 0, 3, 6, 7, 10, 11
+    block = torch.zeros(NPLANES, rows_pad, dtype=torch.float32)
+    hi_part = np.rint(w.loc[lo:hi] * 64.0) / 64.0
+    block[PX:PX + 3, :hi - lo] = torch.from_numpy(hi_part.T.astype(np.float32))
+    block[PXL:PXL + 3, :hi - lo] = torch.from_numpy((w.loc[lo:hi] - hi_part.astype(np.float32)).T.astype(np.float32))
+    block[PR, :hi - lo] = torch.from_numpy(w.radius[lo:hi].astype(np.float32))
+    block[PVX:PVX + 3, :hi - lo] = torch.from_numpy((2.0 * w.vel[lo:hi]).T.astype(np.float32))
+    block[PX:PX + 2, hi - lo:] = 1.0e15                             # pad rows sit far away
+    gathered = torch.zeros(world, NPLANES, rows_pad, dtype=torch.float32)
     dist.all_gather_into_tensor(gathered.view(-1), block.view(-1))
-    # rebuild the global crowd from the gathered layout and compute this rank's rows
-    loc = np.concatenate([gathered[q, 0:3, :bounds[q + 1] - bounds[q]].numpy().T for q in range(world)]).astype(np.float64)
-    vel = np.concatenate([gathered[q, 4:7, :bounds[q + 1] - bounds[q]].numpy().T for q in range(world)]).astype(np.float64) / 2.0
-    rad = np.concatenate([gathered[q, 3, :bounds[q + 1] - bounds[q]].numpy() for q in range(world)]).astype(np.float64)
+    # rebuild the global crowd from the gathered layout (hi + lo is exact) and compute this rank's rows
+    rows_of = lambda q: int(bounds[q + 1] - bounds[q])                                        # noqa: E731
+    loc = np.concatenate([(gathered[q, PX:PX + 3, :rows_of(q)].numpy().astype(np.float64)
+                           + gathered[q, PXL:PXL + 3, :rows_of(q)].numpy().astype(np.float64)).T for q in range(world)])
+    vel = np.concatenate([gathered[q, PVX:PVX + 3, :rows_of(q)].numpy().T for q in range(world)]).astype(np.float64) / 2.0
+    rad = np.concatenate([gathered[q, PR, :rows_of(q)].numpy() for q in range(world)]).astype(np.float64)
     assert np.array_equal(loc, w.loc) and np.array_equal(vel, w.vel) and np.array_equal(rad, w.radius)
     f = O.pedestrian_force(loc, vel, rad, rows=np.arange(lo, hi))
     np.save(os.path.join(out_dir, f'f{rank}.npy'), f)
