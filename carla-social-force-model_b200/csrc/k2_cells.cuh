@@ -421,8 +421,10 @@ __device__ __forceinline__ double2 segment_force(const SegArgs& a, double px, do
     }
 }
 
-// np.argmin(np.linalg.norm(loc - points, axis=-1)) with numpy's arithmetic (rare tie path of the scan below).
-__device__ __forceinline__ int exact_argmin(const double2* __restrict__ point, int o0, int o1, double px, double py) {
+// np.argmin(np.linalg.norm(loc - points, axis=-1)) with numpy's arithmetic over the bracket [o0, o1); `best` receives the
+// winning distance (what the force needs next) or -1 when no point compared finite.
+__device__ __forceinline__ int exact_argmin(const double2* __restrict__ point, int o0, int o1, double px, double py,
+                                            double& best_out) {
     double best = __longlong_as_double(0x7ff0000000000000LL);
     int best_q = o0;
     for (int q = o0; q < o1; ++q) {
@@ -433,6 +435,7 @@ __device__ __forceinline__ int exact_argmin(const double2* __restrict__ point, i
             best_q = q;
         }
     }
+    best_out = (best < __longlong_as_double(0x7ff0000000000000LL)) ? best : -1.0;
     return best_q;
 }
 
@@ -637,8 +640,7 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                         }
                     }
                     if (pass && !(best < __longlong_as_double(0x7ff0000000000000LL))) {
-                        best_q = exact_argmin(a.point, o0, o1, px, py);            // non-finite coordinates: full scan
-                        best = -1.0;
+                        best_q = exact_argmin(a.point, o0, o1, px, py, best);      // non-finite coordinates: full scan
                     }
                 } else {
                 // Nearest point, stage 1 (float32, all lanes in lock step over the staged points): the smallest squared
@@ -711,8 +713,8 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                 }
                 if (pass)
                     // stage 2: numpy's exact arithmetic over the bracket (first index on exact ties, forces.py:154, :228)
-                    best_q = (hi < lo) ? exact_argmin(a.point, o0, o1, px, py)        // non-finite coordinates: full scan
-                                       : exact_argmin(a.point, lo, min(hi + 1, o1), px, py);
+                    best_q = (hi < lo) ? exact_argmin(a.point, o0, o1, px, py, best)      // non-finite coordinates: full scan
+                                       : exact_argmin(a.point, lo, min(hi + 1, o1), px, py, best);
                 }
                 if (pass) {
                     const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],

@@ -144,3 +144,28 @@ def test_sign_of_zero_angle(sfm_config):
     standing = np.ones(w.n, dtype=bool)
     standing[::7] = False
     assert np.abs(want[standing]).max() > 1e-2 and ctx.stats()['fixup_rows'] == 0
+
+
+def test_pair_force_translation_invariance_is_exact(sfm_config):
+    """The staged hi parts live on a 2^-6 m lattice and the kernel only ever forms differences: moving the whole crowd by a
+    lattice vector (here 4,096 m and -8,192 m, far beyond where a single float32 could hold 1e-5 m) leaves every bit of the
+    pair force unchanged -- and so does moving the staging origin."""
+    w = synth.make_config(2)
+    rng = np.random.default_rng(5)
+    loc = w.loc.copy()
+    loc[:, :2] += rng.uniform(-0.03, 0.03, size=(w.n, 2))              # off the float32 lattice ...
+    loc[:, :2] = np.rint(loc[:, :2] * 2.0 ** 30) / 2.0 ** 30            # ... but on 2^-30 m, so that float64 can shift it exactly
+    assert (loc[:, :2].astype(np.float32).astype(np.float64) != loc[:, :2]).mean() > 0.9
+    shift = np.array([4096.0, -8192.0, 0.0])
+    assert np.array_equal((loc + shift) - shift, loc)                   # the shift itself is exact in float64
+    out = []
+    for offset, origin in ((0.0 * shift, None), (shift, None), (shift, (4000.0, -8000.0, 0.0)), (0.0 * shift, (-77.0, 13.0, 0.0))):
+        ctx = native.Context(0)
+        ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+        if origin is not None:
+            ctx.set_origin(*origin)
+        ctx.upload_state(loc + offset, w.vel, w.next_waypoint + offset, w.radius, w.target_speed, w.mode)
+        out.append(ctx.force(native.PEDESTRIAN))
+        ctx.close()
+    for other in out[1:]:
+        np.testing.assert_array_equal(other, out[0])
