@@ -22,7 +22,7 @@
 namespace sfm {
 
 #ifndef SFM_KS_IR
-#define SFM_KS_IR 2
+#define SFM_KS_IR 4
 #endif
 #ifndef SFM_KS_ASIN
 #define SFM_KS_ASIN 1           // planar tiles: interaction angle from sin/cos (no MUFU.RCP) with an asin polynomial
@@ -44,6 +44,15 @@ namespace sfm {
 #define SFM_KS_MINB 4           // min CTAs per SM handed to __launch_bounds__ (register cap 128: no spills; 5 -> 96 registers
                                 // spills the fixed-point accumulators and is 1.5-4 % slower, profiles/tune_k1s_r2*.log)
 #endif
+#ifndef SFM_KS_POLY
+#define SFM_KS_POLY 0           // asin polynomial: 0 Horner, 1 Estrin, 2 even / odd split
+#endif
+#ifndef SFM_KS_SIGNS
+#define SFM_KS_SIGNS 0          // 1: theta' = |theta| - copysign(eps gamma, cross) |D| (transfer off the polynomial's chain),
+#endif                          //    sign(theta') = sign(cross) sign(that) by one product
+#ifndef SFM_KS_ABLATE
+#define SFM_KS_ABLATE 0         // timing-only experiments (WRONG results): bit 0 no sign transfers, 1 no ex2, 2 short polynomial,
+#endif                          //   3 no lo parts, 4 no J-side read-modify-write, 5 no __syncwarp, 6 no rsqrt
 constexpr int KS_UNROLL = SFM_KS_UNROLL;                 // unroll depth of the j-quad loop
 constexpr int KS_IR = SFM_KS_IR;                         // rows per thread
 constexpr int KS_THREADS = K1_TJ / KS_IR;                // one 256-row tile per CTA
@@ -115,7 +124,11 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
                                             const AsinConst& sc, f32x2& gx, f32x2& gy, f32x2& gz) {
     // d = (hi_j - hi_i) + (lo_j - lo_i): exact lattice difference + remainder (sfm_common.cuh)
     // PLANAR: every pedestrian of both tiles has the same z and no vertical velocity, so d_z = w_z = D_z = 0 exactly
+#if SFM_KS_ABLATE & 8
+    const f32x2 dx = sub2(xj, I.x), dy = sub2(yj, I.y);
+#else
     const f32x2 dx = add2(sub2(xj, I.x), sub2(xlj, I.xl)), dy = add2(sub2(yj, I.y), sub2(ylj, I.yl));
+#endif
     f32x2 dz = 0ull, wz = 0ull, Dz = 0ull;
     f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
     const f32x2 dxy2 = d2;
@@ -123,7 +136,11 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
         dz = add2(sub2(zj, I.z), sub2(zlj, I.zl));
         d2 = fma2(dz, dz, d2);
     }
+#if SFM_KS_ABLATE & 64
+    const f32x2 rinv = fma2(d2, splat2(1e-3f), splat2(0.5f));
+#else
     const f32x2 rinv = rsqrt2(d2);
+#endif
     const f32x2 wx = sub2(I.vx, vxj), wy = sub2(I.vy, vyj);
     const f32x2 Dx = fma2(dx, rinv, wx), Dy = fma2(dy, rinv, wy);
     f32x2 D2 = fma2(Dy, Dy, mul2(Dx, Dx));
@@ -133,7 +150,11 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
         Dz = fma2(dz, rinv, wz);
         D2 = fma2(Dz, Dz, D2);
     }
+#if SFM_KS_ABLATE & 64
+    const f32x2 Dinv = fma2(D2, splat2(1e-3f), splat2(0.5f));
+#else
     const f32x2 Dinv = rsqrt2(D2);
+#endif
     const f32x2 Dn = mul2(D2, Dinv);
 #if SFM_KS_NEGSUB
     const f32x2 cross = sub2(mul2(wx, dy), mul2(wy, dx));
@@ -158,21 +179,49 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
         const f32x2 q = mul2(pack2(fabsf(cl) - fabsf(tl), fabsf(ch) - fabsf(th)), Rxy);
         const f32x2 s = mul2(q, q);
         f32x2 p;
+#if SFM_KS_POLY == 1
+        // Estrin: 8 operations, depth 3 (Horner: 6 operations, depth 6)
+        {
+            const f32x2 s2 = mul2(s, s);
+            const f32x2 pa = fma2(sc.s1, s, sc.s0), pb = fma2(sc.s3, s, sc.s2), pcc = fma2(sc.s5, s, sc.s4);
+            const f32x2 s4 = mul2(s2, s2);
+            const f32x2 pe = fma2(sc.s6, s2, pcc), pf = fma2(pb, s2, pa);
+            p = fma2(pe, s4, pf);
+        }
+#elif SFM_KS_POLY == 2
+        // even / odd split: 7 operations, depth 5
+        {
+            const f32x2 s2 = mul2(s, s);
+            f32x2 pe = fma2(sc.s6, s2, sc.s4);
+            f32x2 po = fma2(sc.s5, s2, sc.s3);
+            pe = fma2(pe, s2, sc.s2);
+            po = fma2(po, s2, sc.s1);
+            pe = fma2(pe, s2, sc.s0);
+            p = fma2(po, s, pe);
+        }
+#else
 #if SFM_KS_ASIN_TERMS == 6
         p = fma2(sc.s5, s, sc.s4);
 #else
         p = fma2(sc.s6, s, sc.s5);
         p = fma2(p, s, sc.s4);
 #endif
+#if !(SFM_KS_ABLATE & 4)
         p = fma2(p, s, sc.s3);
         p = fma2(p, s, sc.s2);
         p = fma2(p, s, sc.s1);
+#endif
         p = fma2(p, s, sc.s0);
+#endif
         const f32x2 g = fma2(p, q, splat2(-0.78539816339744831f));                 // phi - pi/2 in [-pi/2, 0]
 #if SFM_KS_ANGLE == 1
         const f32x2 mg = g ^ (mul2(cross, dot) & 0x8000000080000000ULL);
         const f32x2 h = (cross & 0x8000000080000000ULL) | splat2(1.57079632679489662f);
         theta = add2(h, mg);
+#elif SFM_KS_ABLATE & 1
+        theta = add2(g, splat2(1.57079632679489662f));
+#elif SFM_KS_SIGNS == 1
+        theta = add2(g ^ (dot & 0x8000000080000000ULL), splat2(1.57079632679489662f));   // |theta| in [0, pi]
 #else
         const f32x2 tabs = add2(g ^ (dot & 0x8000000080000000ULL), splat2(1.57079632679489662f));   // |theta| in [0, pi]
         theta = tabs ^ (cross & 0x8000000080000000ULL);
@@ -212,8 +261,15 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
         unpack2(p, pl, ph);
         theta = pack2(octant_fix(pl, axl, ayl, tl, cl), octant_fix(ph, axh, ayh, th, ch));
     }
+#if SFM_KS_SIGNS == 1
+    // theta = sigma |theta| (sigma = sign(cross)): theta' = sigma (|theta| - sigma eps gamma |D|); its square is sign-free
+    const f32x2 thq = (DIFF) ? fma2(c.eps_gamma_neg ^ (cross & 0x8000000080000000ULL), Dn, theta) : 0ull;
+    const f32x2 thp = (DIFF) ? mul2(thq, cross) : fma2(c.eps_gamma_neg, Dn, theta);      // DIFF: only its sign is used below
+    const f32x2 u = mul2(Dn, (DIFF) ? thq : thp);
+#else
     const f32x2 thp = fma2(c.eps_gamma_neg, Dn, theta);
     const f32x2 u = mul2(Dn, thp);
+#endif
     const f32x2 u2 = mul2(u, u);
     f32x2 y;
     if (RADIUS) {
@@ -224,10 +280,19 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
     } else {
         y = fma2(mul2(mul2(d2, rinv), Dinv), c.k_exp, c.log2A);
     }
+#if SFM_KS_ABLATE & 2
+    const f32x2 e1 = fma2(c.c_nprime_neg, u2, y);
+    const f32x2 e2 = fma2(c.c_n_neg, u2, y);
+#else
     const f32x2 e1 = ex2_2(fma2(c.c_nprime_neg, u2, y));
     const f32x2 e2 = ex2_2(fma2(c.c_n_neg, u2, y));
+#endif
     const f32x2 a = mul2(e1, Dinv);
+#if SFM_KS_ABLATE & 1
+    f32x2 b = mul2(e2, Dinv);
+#else
     f32x2 b = mul2(e2, Dinv) | (thp & 0x8000000080000000ULL);            // copysign(e2 / |D|, theta')
+#endif
     if (SIGN0) {
         float bl, bh, hl, hh;
         unpack2(b, bl, bh);
@@ -280,19 +345,25 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
             if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz1 = r ? add2(jz1, gz) : gz; }
         }
         // J side: F_j += g, into this warp's private slice (lanes hold distinct j, so plain read-modify-write)
+#if SFM_KS_ABLATE & 16
+        Gx[0] = add2(Gx[0], add2(jx0, jx1)); Gy[0] = add2(Gy[0], add2(jy0, jy1));
+#else
         ulonglong2* ax = reinterpret_cast<ulonglong2*>(&accw[0][j]);
         ulonglong2* ay = reinterpret_cast<ulonglong2*>(&accw[1][j]);
         ulonglong2 vx = *ax, vy = *ay;
         vx.x = add2(vx.x, jx0); vx.y = add2(vx.y, jx1);
         vy.x = add2(vy.x, jy0); vy.y = add2(vy.y, jy1);
         *ax = vx; *ay = vy;
+#endif
         if (!PLANAR) {
             ulonglong2* az = reinterpret_cast<ulonglong2*>(&accw[2][j]);
             ulonglong2 vz = *az;
             vz.x = add2(vz.x, jz0); vz.y = add2(vz.y, jz1);
             *az = vz;
         }
+#if !(SFM_KS_ABLATE & 32)
         __syncwarp();                                   // next step another lane owns this quad
+#endif
     }
 #pragma unroll
     for (int r = 0; r < KS_IR; ++r) {

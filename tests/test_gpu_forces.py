@@ -230,3 +230,65 @@ def test_infinite_section_length_reaches_every_pedestrian(sfm_config):
     assert (pairs[:, 1] == 3).sum() == w.n
     np.testing.assert_array_equal(ctx.enumerate_pairs(native.BORDER), pairs)
     np.testing.assert_allclose(ctx.force(native.BORDER), want, rtol=1e-11, atol=1e-11)
+
+
+def test_cutoffs_are_strict_to_the_last_bit(sfm_config):
+    """forces.py:149-150, :222-223 test `norm < cutoff` in float64: pedestrians at exactly the cutoff distance (also where
+    sqrt rounds onto it), one ulp inside / outside, and just inside the float32 pre-filter's margin must be classified like
+    numpy classifies them -- for a section, a static obstacle and a vehicle."""
+    w = synth.make_config(2, n=256)
+    centre = np.array([100.0, 200.0])
+    cut_static = sfm_config['static_obstacle_force']['perception_threshold']            # 20
+    cut_dynamic = sfm_config['dynamic_obstacle_force']['perception_threshold']          # 50
+    ring = centre + 0.4 * np.column_stack((np.cos(np.arange(8) * np.pi / 4), np.sin(np.arange(8) * np.pi / 4)))
+    line = centre + np.column_stack((np.linspace(-5, 5, 101), np.zeros(101)))
+    dists = []
+    for cut in (cut_static, 17.5, cut_dynamic):
+        steps = [0.0, np.spacing(cut), -np.spacing(cut), 4 * np.spacing(cut), -4 * np.spacing(cut), 1e-9, -1e-9, 1e-7, -1e-7,
+                 5e-5, -5e-5, 3e-4, -3e-4]
+        dists += [cut + s for s in steps]
+    loc = np.zeros((256, 3))
+    vel, wp = w.vel[:256] * 0.0, w.next_waypoint[:256]
+    k = 0
+    for d in dists:                                       # along x, along y, and on the 3-4-5 direction (sqrt is exact)
+        for direction in ((1.0, 0.0), (0.0, -1.0), (0.6, 0.8), (-0.8, 0.6)):
+            loc[k, :2] = centre + d * np.array(direction)
+            k += 1
+    loc[k:, :2] = centre + np.random.default_rng(3).uniform(-60, 60, size=(256 - k, 2))
+    ctx = native.Context(0)
+    ctx.set_params(native.params_from_config(sfm_config, w.step_length))
+    ctx.upload_state(loc, vel, wp, w.radius[:256], w.target_speed[:256], np.ones(256, dtype=np.uint8))
+    ctx.set_borders([line], centre[None, :], np.array([17.5]))
+    ctx.set_obstacles(native.STATIC_OBSTACLE, [centre], [ring])
+    ctx.set_obstacles(native.DYNAMIC_OBSTACLE, [centre], [ring], [np.array([3.0, -1.0])])
+    scene = G.scene_for(w, sfm_config)
+    _, want_b = O.border_force(loc, w.radius[:256], np.ones(256, dtype=np.uint8), [line], centre[None, :], np.array([17.5]),
+                               scene.border, False, return_pairs=True)
+    _, want_s = O.obstacle_force(loc, vel, w.radius[:256], [centre], [ring], None, scene.static, False, return_pairs=True)
+    _, want_d = O.obstacle_force(loc, vel, w.radius[:256], [centre], [ring], [np.array([3.0, -1.0])], scene.dynamic, False,
+                                 return_pairs=True)
+    inside = np.linalg.norm(loc[:k, :2] - centre, axis=1) < 17.5
+    assert inside.any() and (~inside).any() and 0 < len(want_b) < 256          # both sides of every cutoff are populated
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.BORDER), want_b)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.STATIC_OBSTACLE), want_s)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.DYNAMIC_OBSTACLE), want_d)
+
+
+def test_cell_list_forces_do_not_depend_on_pedestrian_order(sfm_config):
+    """A pedestrian's border / obstacle force is summed in (cell, item index) order whatever its neighbours in the table
+    are: permuting the pedestrians permutes the forces bit for bit; the pair force (tile partial sums regroup) follows to
+    the float32 tolerance."""
+    w = synth.make_config(2)
+    perm = np.random.default_rng(9).permutation(w.n)
+    a = make_context(w, sfm_config)
+    b = native.Context(0)
+    b.set_params(native.params_from_config(sfm_config, w.step_length))
+    b.upload_state(w.loc[perm], w.vel[perm], w.next_waypoint[perm], w.radius[perm], w.target_speed[perm], w.mode[perm])
+    b.set_borders(w.borders, w.section_center, w.section_length)
+    b.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles], [r for _, r in w.static_obstacles])
+    veh = w.vehicles_at(0)
+    b.set_obstacles(native.DYNAMIC_OBSTACLE, veh[1], veh[5], veh[3])
+    for cls in (native.ACCELERATION, native.BORDER, native.STATIC_OBSTACLE, native.DYNAMIC_OBSTACLE):
+        np.testing.assert_array_equal(b.force(cls), a.force(cls)[perm])
+    fa, fb = a.force(native.PEDESTRIAN)[perm], b.force(native.PEDESTRIAN)
+    assert np.abs(fb - fa).max() <= 1e-5 + 1e-4 * np.abs(fa).max()
