@@ -292,3 +292,43 @@ def test_cell_list_forces_do_not_depend_on_pedestrian_order(sfm_config):
         np.testing.assert_array_equal(b.force(cls), a.force(cls)[perm])
     fa, fb = a.force(native.PEDESTRIAN)[perm], b.force(native.PEDESTRIAN)
     assert np.abs(fb - fa).max() <= 1e-5 + 1e-4 * np.abs(fa).max()
+
+
+@pytest.mark.parametrize('use_radius', [False, True])
+def test_appendix_b_edge_cases(sfm_config, use_radius):
+    """SURVEY.md appendix B side by side (tests/appendix_b.py -- the oracle is pinned to the imported reference on the same
+    scene in tests/test_oracle_vs_reference.py): argmin ties, pedestrians exactly at a cutoff, theta = -pi / +pi, zero
+    distance to a border / ring point, masked modes, waypoint reached, zero target speed, |v'| = 0, a pedestrian 3 km away."""
+    from tests import appendix_b
+    cfg = dict(sfm_config, use_ped_radius=use_radius)
+    w = appendix_b.scene()
+    ctx = make_context(w, cfg)
+    scene = G.scene_for(w, cfg)
+    dyn, dyn_vel = G.dyn_for(w, 0)
+    with np.errstate(all='ignore'):
+        want = _oracle_classes(w, cfg)
+        _, risk = O.pedestrian_force(w.loc, w.vel, w.radius, scene.ped, use_radius, return_risk=True)
+        _, pairs_b = O.border_force(w.loc, w.radius, w.mode, w.borders, w.section_center, w.section_length, scene.border,
+                                    use_radius, return_pairs=True)
+        _, pairs_s = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in w.static_obstacles],
+                                      [r for _, r in w.static_obstacles], None, scene.static, use_radius, return_pairs=True)
+        _, pairs_d = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in dyn], [r for _, r in dyn], dyn_vel,
+                                      scene.dynamic, use_radius, return_pairs=True)
+        want_loc, want_vel, want_f = O.step(scene, w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode, dyn,
+                                            dyn_vel)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.BORDER), pairs_b)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.STATIC_OBSTACLE), pairs_s)
+    np.testing.assert_array_equal(ctx.enumerate_pairs(native.DYNAMIC_OBSTACLE), pairs_d)
+    for cls, name in ((native.ACCELERATION, 'acceleration_force'), (native.BORDER, 'border_force'),
+                      (native.STATIC_OBSTACLE, 'static_obstacle_force'), (native.DYNAMIC_OBSTACLE, 'dynamic_obstacle_force')):
+        np.testing.assert_allclose(ctx.force(cls), want[name], rtol=1e-11, atol=1e-11, err_msg=name)
+    got = ctx.force(native.PEDESTRIAN)
+    assert_forces_close(got, want['pedestrian_force'], risk=risk, name='appendix-b pairs')
+    assert not ctx.force(native.BORDER)[[5, 8, 9]].any() and not ctx.force(native.STATIC_OBSTACLE)[5].any()
+    assert not got[2].any()                                        # 3 km from everybody: underflows to exactly zero
+    ctx.step(1, integrate_positions=True)
+    loc, vel = ctx.download_state()
+    tol = 0.05 * (1e-5 + 1e-4 * np.abs(want_f) + risk[:, None])   # dv = dt * dF
+    assert (np.abs(vel - want_vel) <= tol + 1e-12).all()
+    assert not vel[1].any() and not vel[2].any()                   # target speed 0; |v'| = 0
+    np.testing.assert_array_equal(loc[2], w.loc[2])

@@ -59,3 +59,37 @@ def test_force_switches(ref, sfm_config):
     sim = ref_loader.build_simulation(ref, w, cfg)
     _, mine = _oracle_forces(w, cfg)
     assert list(mine) == list(sim.forces) == ['acceleration_force', 'border_force']
+
+
+@pytest.mark.parametrize('use_radius', [False, True])
+def test_appendix_b_edge_cases_match_reference(ref, sfm_config, use_radius):
+    """SURVEY.md appendix B side by side (tests/appendix_b.py): argmin ties, strict cutoffs at exactly the cutoff distance,
+    theta = -pi / +pi without a wrap, zero distances to a border / ring point, masked modes, waypoint reached, zero target
+    speed, |v'| = 0 -- every class and one tick of new velocities, oracle == imported reference."""
+    from tests import appendix_b
+    cfg = dict(sfm_config, use_ped_radius=use_radius)
+    w = appendix_b.scene()
+    sim = ref_loader.build_simulation(ref, w, cfg)
+    sim.update_dynamic_obstacles(w.vehicles_at(0))
+    scene, mine = _oracle_forces(w, cfg)
+    with np.errstate(all='ignore'):
+        for name, force in sim.forces.items():
+            want = force.get_force(sim.peds)
+            np.testing.assert_allclose(mine[name], want, rtol=1e-12, atol=1e-12, err_msg=name)
+        sim.tick(0.0)
+    veh = w.vehicles_at(0)
+    _, vel, _ = O.step(scene, w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode, list(zip(veh[1], veh[5])),
+                       veh[3])
+    np.testing.assert_allclose(vel, sim.get_new_velocities()['vel'], rtol=1e-12, atol=1e-12)
+    # the cases are what the scene's docstring says they are
+    b, s = mine['border_force'], mine['static_obstacle_force']
+    assert not b[[5, 8, 9]].any() and not s[5].any() and not vel[1].any() and not vel[2].any()
+    _, pairs_b = O.border_force(w.loc, w.radius, w.mode, w.borders, w.section_center, w.section_length, scene.border,
+                                use_radius, return_pairs=True)
+    _, pairs_s = O.obstacle_force(w.loc, w.vel, w.radius, [c for c, _ in w.static_obstacles],
+                                  [r for _, r in w.static_obstacles], None, scene.static, use_radius, return_pairs=True)
+    pb = {(int(p), int(k)): int(q) for p, k, q in pairs_b}
+    ps = {(int(p), int(k)): int(q) for p, k, q in pairs_s}
+    assert pb[(3, 0)] == 4 and ps[(4, 0)] == 0                     # first index on exact ties
+    assert (10, 1) not in pb and (11, 1) not in ps                 # exactly at the cutoff: excluded
+    assert pb[(12, 0)] == 7 and ps[(13, 0)] == 2                   # zero distance
