@@ -75,10 +75,20 @@ class PedestrianSimulation:
         """Do one step in the simulation."""
         if self.peds.state is None or self.peds.size() == 0:
             return
-        table = self.peds.mode_table()
+        # resident path with the device holding this table's identity column: the object pointers are compared there
+        # (sfm_tick_records, identity 'check') instead of by a strided pass over the table on the host
+        session = get_session() if not self.record_states else None
+        table = self.peds.cached_mode_table() if session is not None and session.identity_table is not None else None
+        deferred = table is not None and session.identity_table is table and session.resident_table is table
+        if not deferred:
+            table = self.peds.mode_table()
         if table is not None and self._fusable() and self._uniform_waiting_time(table):
-            self._tick_table(table, sim_time)
-            return
+            if self._tick_table(table, sim_time, check_identity=deferred):
+                return
+            table = self.peds.mode_table()          # the device saw other objects: full look at the column, then again
+            if table is not None and self._fusable() and self._uniform_waiting_time(table):
+                self._tick_table(table, sim_time)
+                return
         # generic path: apply_current_mode, then every machine's tick (pedestrian_simulation.py:63-65) -- one pass over the
         # mode objects, which also yields the uint8 codes the device needs
         state = self.peds.state
@@ -131,8 +141,10 @@ class PedestrianSimulation:
             else:
                 f._bind(session)
 
-    def _tick_table(self, table, sim_time):
-        """The resident / columnar paths (module docstring): no interpreter loop over pedestrians."""
+    def _tick_table(self, table, sim_time, check_identity=False):
+        """The resident / columnar paths (module docstring): no interpreter loop over pedestrians.  Returns False when
+        ``check_identity`` was asked for and the device found other objects in the ``mode`` column than ``table`` was
+        built from (nothing has been done then)."""
         state = self.peds.state
         session = get_session()
         ctx = session.ctx
@@ -143,7 +155,9 @@ class PedestrianSimulation:
         if session.resident_table is not table or ctx.n != len(state):
             ctx.upload_state(*self.peds.device_columns(cols['current_mode']))
             session.resident_table, session.machines_version, session.traffic_version = table, None, None
+            session.identity_table = None
             self._life_counters = None
+            check_identity = False
         if not on_device:
             # columnar host path: apply_current_mode, tick, gap acceptance for the pedestrians at the kerb, snapshot
             state['target_speed'] = cols['target_speed']                                      # :63
@@ -170,7 +184,14 @@ class PedestrianSimulation:
                 ctx.set_traffic(centres, self.dyn_obs_vel if len(centres) else [], self.dyn_obs_extent if len(centres) else [])
                 session.traffic_version = self._dyn_version
             before = self._life_counters
-            counters = ctx.tick_records(state, sim_time, tick_modes=True)
+            if check_identity and session.identity_table is table:
+                counters, changed = ctx.tick_records(state, sim_time, tick_modes=True, identity=('check', 'mode'))
+                if changed:
+                    session.identity_table = None
+                    return False
+            else:
+                counters = ctx.tick_records(state, sim_time, tick_modes=True, identity=('adopt', 'mode'))
+                session.identity_table = table
             cols['sim_time'][:] = sim_time
             if before is None or counters[0] != before[0] or counters[1] != before[1]:
                 m = ctx.download_modes()                    # somebody started crossing or woke up: refresh the host objects
@@ -179,6 +200,7 @@ class PedestrianSimulation:
                 cols['next_mode_time'][:] = m['next_mode_time']
             self._life_counters = counters
         self.new_velocities = state[['id', 'vel']]          # a view: the device call wrote state['vel']
+        return True
 
     def _fusable(self):
         names = list(self.forces)

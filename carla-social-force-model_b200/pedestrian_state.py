@@ -21,6 +21,7 @@ class PedState:
         self.state = None
         self.all_states = {}            # sim_time -> snapshot, filled by record_current_state
         self._table, self._table_ptrs = None, None      # ModeTable of the current rows + the objects it was built from
+        self._table_state = None                        # ... and the state array that comparison was made on
 
     # ---- rows in / out (pedestrian_state.py:26-43) ------------------------------------------------------------------
     def add_pedestrian(self, initial_ped_state):
@@ -132,13 +133,22 @@ class PedState:
         if self.state is None or len(self.state) == 0 or self.state.strides[0] <= 0:
             return None
         if self._table_ptrs is not None and len(self.state) == len(self._table_ptrs) and self._same_objects():
+            self._table_state = self.state
             return self._table
         if self._table is not None:
             self._table.release()
         modes = list(self.state['mode'])
         self._table = ModeTable(modes) if ModeTable.adoptable(modes) else None
         self._table_ptrs = self._mode_pointers().copy()
+        self._table_state = self.state
         return self._table
+
+    def cached_mode_table(self):
+        """The last ``mode_table()`` result if ``state`` is still the very array it was validated for, else ``None`` -- no
+        look at the column: the caller (the resident tick) has the device compare the object pointers instead."""
+        if self._table is not None and self.state is not None and self._table_state is self.state:
+            return self._table
+        return None
 
     def _same_objects(self):
         try:                                    # strided memcmp in the native library (host code, ~0.05 ms at N = 65,536)

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get('SFM_LIB') or os.path.join(HERE, 'libsfm_b200.so')    
 FORCE_CLASSES = ('acceleration_force', 'pedestrian_force', 'border_force', 'static_obstacle_force',
                  'dynamic_obstacle_force')                      # pedestrian_simulation.py:37-48 dict order
 ACCELERATION, PEDESTRIAN, BORDER, STATIC_OBSTACLE, DYNAMIC_OBSTACLE = range(5)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/sfm_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create', 'sfm_destroy', 'sfm_set_stream',
@@ -118,7 +118,8 @@ def lib():
         'sfm_step': (C.c_int, [p_ctx, C.c_int, C.c_int]),
         'sfm_tick_host': (C.c_int, [p_ctx, i64, p_d, p_d, p_d, p_d]),
         'sfm_apply_force': (C.c_int, [p_ctx, i64, p_d, p_d]),
-        'sfm_tick_records': (C.c_int, [p_ctx, i64, C.c_void_p, i64, p_i64, C.c_double, C.c_int, p_i64]),
+        'sfm_tick_records': (C.c_int, [p_ctx, i64, C.c_void_p, i64, p_i64, C.c_double, C.c_int, p_i64, i64, C.c_int,
+                                      C.POINTER(C.c_int)]),
         'sfm_host_register': (C.c_int, [C.c_void_p, C.c_size_t]),
         'sfm_host_unregister': (C.c_int, [C.c_void_p]),
         'sfm_host_column_gather': (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p]),
@@ -386,15 +387,25 @@ class Context:
         """Host-buffer tick; arrays must be C-contiguous float64 [n, 3] (pinned memory makes the copies asynchronous)."""
         _check(self._lib.sfm_tick_host(self._h, self.n, _ptr(loc), _ptr(vel), _ptr(new_vel), _ptr(new_loc)))
 
-    def tick_records(self, state, sim_time, tick_modes):
+    def tick_records(self, state, sim_time, tick_modes, identity=None):
         """One drop-in tick on the structured pedestrian table ``state`` (in place: new velocities land in ``state['vel']``,
-        and with ``tick_modes`` the applied target speeds in ``state['target_speed']``).  Returns the lifecycle counters."""
+        and with ``tick_modes`` the applied target speeds in ``state['target_speed']``).  Returns the lifecycle counters.
+
+        ``identity``: ``None``, or ``('adopt' | 'check', field)`` -- the 8-byte column ``field`` (the ``mode`` object
+        pointers) is adopted as the table's identity, or checked against the adopted one on the device; with ``'check'``
+        the return value is ``(counters, changed)`` and a changed table is handed back untouched."""
         fields = state.dtype.fields
         offsets = np.array([fields[k][1] for k in ('loc', 'vel', 'next_waypoint', 'radius', 'target_speed')], dtype=np.int64)
         counters = np.zeros(4, dtype=np.int64)
+        changed = C.c_int(0)
+        id_mode, id_off = 0, 0
+        if identity is not None:
+            id_mode, id_off = {'adopt': 1, 'check': 2}[identity[0]], fields[identity[1]][1]
         _check(self._lib.sfm_tick_records(self._h, len(state), C.c_void_p(state.ctypes.data), state.strides[0],
                                           _ptr(offsets, C.c_int64), float(sim_time), int(bool(tick_modes)),
-                                          _ptr(counters, C.c_int64)))
+                                          _ptr(counters, C.c_int64), int(id_off), id_mode, C.byref(changed)))
+        if identity is not None and identity[0] == 'check':
+            return counters, bool(changed.value)
         return counters
 
     def apply_force(self, force, out=None):

@@ -24,6 +24,7 @@ class Session:
         self.resident_table = None          # ModeTable whose pedestrian rows (and machines) are on the device
         self.machines_version = None        # ... and the table version its device mirror reflects
         self.traffic_version = None
+        self.identity_table = None          # ModeTable whose `mode` object pointers the device holds (sfm_tick_records)
         self.pinned = None                  # native.PinnedArray of the PedState table the resident tick copies from
 
     def pin(self, state):
@@ -57,6 +58,7 @@ class Session:
     def upload_peds(self, peds, mode_codes=None):
         self.ctx.upload_state(*peds.device_columns(mode_codes))
         self.resident_table = None          # a full upload drops the device-side mode machines
+        self.identity_table = None
 
     def bind_set(self, which, owner, version, loader):
         """Make ``owner``'s point set resident for class ``which`` unless it already is (same object, same version)."""

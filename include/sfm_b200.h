@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SFM_ABI_VERSION 3
+#define SFM_ABI_VERSION 4
 
 typedef struct sfm_ctx sfm_ctx;
 
@@ -141,9 +141,16 @@ int sfm_tick_host(sfm_ctx* ctx, int64_t n, const double* loc, const double* vel,
  * The new velocities are written into the records' vel field (what `state[['id','vel']]` aliases, :123-124) and, with
  * `tick_modes`, the target speed the clamp used into target_speed (pedestrian_state.py:94-95).  counters4 (may be NULL)
  * receives sfm_lifecycle_counters after the tick, so the caller knows whether any machine changed mode.  Row count and
- * mode codes are those of the last sfm_upload_state / sfm_update_targets. */
+ * mode codes are those of the last sfm_upload_state / sfm_update_targets.
+ * Identity column (ABI v4): the 8 bytes at `identity_offset` of every record -- the drop-in passes the `mode` column, whose
+ * entries are the PedModeManager object pointers (pedestrian_state.py:17-19) -- tell whether the table still holds the
+ * pedestrians the resident mode machines describe.  identity_mode 0: ignored; 1: adopted as the table's identity; 2:
+ * compared with the adopted column on the device right after the upload -- on any difference (a spawn, a despawn, a
+ * replaced object) *identity_changed = 1 and the call returns 0 with nothing else done: no mode step, no forces, the
+ * records untouched; the caller rebuilds its mode table and calls again with identity_mode 1. */
 int sfm_tick_records(sfm_ctx* ctx, int64_t n, void* records, int64_t stride, const int64_t* field_offsets,
-                     double sim_time, int tick_modes, int64_t* counters4);
+                     double sim_time, int tick_modes, int64_t* counters4, int64_t identity_offset, int identity_mode,
+                     int* identity_changed);
 /* Page-lock a host range the caller owns (e.g. the PedState table) so that sfm_tick_records / sfm_tick_host copy from it
  * by DMA instead of through the driver's staging buffer; the caller keeps the memory alive until sfm_host_unregister. */
 int sfm_host_register(void* ptr, size_t bytes);

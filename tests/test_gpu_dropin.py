@@ -183,3 +183,40 @@ def test_calculate_new_velocities_on_device_equals_numpy(sfm_config):
     got = sim.get_new_velocities()
     assert np.shares_memory(got, sim.peds.state)
     np.testing.assert_array_equal(got['vel'], want)
+
+
+def test_device_identity_check_notices_replaced_objects(sfm_config, monkeypatch):
+    """After its first tick the resident path no longer walks the `mode` column on the host: the device compares the
+    object pointers (sfm_tick_records, identity 'check').  An object replaced IN PLACE -- same array, same length -- must
+    still be noticed: the tick then hands the table back untouched and the full path rebuilds the machines, so the run
+    equals one whose table held that object from the start; steady ticks never call the host-side comparison."""
+    from sfm_b200 import native
+    w = synth.make_config(2, n=4096)                       # >= 4096 rows: the 2-D DMA write-back path
+    calls = []
+    real = native.column_equal
+    monkeypatch.setattr(native, 'column_equal', lambda *a, **k: calls.append(1) or real(*a, **k))
+
+    def run(replace_at):
+        sim = build_sim(w, sfm_config, record_states=False)
+        out = []
+        for k in range(6):
+            if k == replace_at:
+                old = sim.peds.state['mode'][7]
+                new = PedModeManager(old.ped_name, 0.5 * old.initial_target_speed, PedMode.WALKING_SIDEWALK, 1.0, -1.0)
+                sim.peds.state['mode'][7] = new                # in place: the array object and its length stay the same
+            sim.tick(0.05 * k)
+            out.append((sim.peds.state['vel'].copy(), sim.peds.state['target_speed'].copy()))
+            sim.peds.state['loc'] += sim.get_new_velocities()['vel'] * w.step_length
+        return out
+
+    calls.clear()
+    plain = run(None)
+    assert len(calls) <= 1, calls                           # steady ticks: no host pass over the column
+    swapped = run(3)
+    for k in range(3):
+        assert np.array_equal(plain[k][0], swapped[k][0])
+    assert swapped[3][1][7] == 0.5 * plain[3][1][7]          # the new object's speed governs from its first tick on
+    assert not np.array_equal(plain[3][0][7], swapped[3][0][7])
+    others = np.arange(w.n) != 7
+    assert np.array_equal(plain[3][0][others], swapped[3][0][others])      # same positions, only row 7's clamp differs
+    assert np.array_equal(swapped[5][1][others], plain[5][1][others])
