@@ -374,8 +374,13 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
     }
 }
 
+#ifdef SFM_KS_MAXNREG
+#define SFM_KS_BOUNDS __maxnreg__(SFM_KS_MAXNREG)
+#else
+#define SFM_KS_BOUNDS __launch_bounds__(KS_THREADS, SFM_KS_MINB)
+#endif
 template <bool RADIUS, bool SIGN0>
-__global__ void __launch_bounds__(KS_THREADS, SFM_KS_MINB) k1_sym_pairs(const SymArgs a) {
+__global__ void SFM_KS_BOUNDS k1_sym_pairs(const SymArgs a) {
     __shared__ __align__(128) float tile[K1_STAGES][KS_PLANES][K1_TJ];
     __shared__ __align__(16) float accj[KS_WARPS][3][K1_TJ];
     __shared__ __align__(8) uint64_t bar[K1_STAGES];

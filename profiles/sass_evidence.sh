@@ -10,9 +10,9 @@ for k in k1_sym_pairsILb0ELb0 k2_segmentsILi0 k2_segmentsILi1 k2_msort_scatter k
   echo
 done
 
-# instruction mix of the planar inner loop of the pair kernel (one step = 4 packed calls = 8 pair terms per lane) and of the
+# instruction mix of the planar inner loop of the pair kernel (one step = 2 x 4 rows = 8 packed calls = 16 pair terms per lane) and of the
 # general (3-D) loop: the bodies of the two backward branches with > 150 instructions that hold no scalar FFMA
-echo "## k1_sym_pairs<false,false> inner loops (per step of 4 packed calls)"
+echo "## k1_sym_pairs<false,false> inner loops (per step of 8 packed calls: 4 rows per thread x 2 j-pairs)"
 cuobjdump -sass $LIB | awk '/Function : .*k1_sym_pairsILb0ELb0E/{p=1} p{print} /Function : /{if(p&&!/k1_sym_pairsILb0ELb0E/)exit}' | grep -v '^\s*/\* 0x' > /tmp/_k1.sass
 python3 - <<'PY'
 import re
