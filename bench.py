@@ -45,9 +45,10 @@ import numpy as np                     # noqa: E402
 K1_INSTR_PER_PAIR = 58                 # FP32-pipe instructions per ordered pair (81 FLOP, 5 MUFU)
 K1_INSTR_PER_PAIR_2D = 48              # same table: the 2-D / radius-off specialisation (what a flat crowd needs)
 K1_INSTR_DOUBLE_SINGLE = 4             # + (hi_j - hi_i) + (lo_j - lo_i) instead of one subtraction, x and y
+PLANE_BYTES = 60                       # staged float32 planes per pedestrian (csrc/sfm_common.cuh: 15 planes)
 # K3 algorithmic bytes per agent-step: read loc+r 32, vel+speed 32, waypoint 16, pair force 24, three
-# cell-list forces 3 x 16; write loc 32, vel 32, float32 staging planes 44, total force 24
-K3_BYTES_PER_AGENT = 32 + 32 + 16 + 24 + 48 + 32 + 32 + 44 + 24
+# cell-list forces 3 x 16; write loc 32, vel 32, float32 staging planes 60, total force 24
+K3_BYTES_PER_AGENT = 32 + 32 + 16 + 24 + 48 + 32 + 32 + PLANE_BYTES + 24
 SMS, LANES = 148, 128
 CFG5_N1 = 370688                       # N_8 / sqrt(8) rounded to 256: the 1-GPU point of the 1M constant-pair-work ladder
 
@@ -96,6 +97,8 @@ def bench_config(name, w, world, workload):
             'forces': 'all five on',
             'l2': 'GPU arm: L2 flushed between timed steps (256 MiB fill, outside the timed spans); CPU arm: n/a',
             'partition': f'row blocks over {world} rank(s)',
+            'staged_order': 'GPU arm: each rank stages its rows along a Hilbert curve, rebuilt on the device every 32 ticks '
+                            '(speed only; row order and results per row unchanged); CPU arm: n/a',
             'vehicles': ('device-resident: centres advanced and ellipse rings regenerated on the device every tick'
                          if workload == 'cfg4' else 'none' if w.veh_center is None else 'host rings')}
 
@@ -246,15 +249,16 @@ def parity_check(job, e, w, cfg, n_uniform=24, n_far=8, chunk=8):
     from sfm_b200 import native
     from sfm_b200.engine import crowd_origin
     loc_l, vel_l = e.local_state()
+    order_l = e.ctx.slot_order()                   # the staged order this tick's pair kernel reads its rows in
     e.step(1, True)
     f_l = e.ctx.download_force()
     loc2_l, vel2_l = e.local_state()
     e.synchronize()
-    parts = job.gather((loc_l, vel_l, f_l, loc2_l, vel2_l))
+    parts = job.gather((loc_l, vel_l, f_l, loc2_l, vel2_l, order_l + int(e.lo)))
     if job.rank != 0:
         job.barrier()                              # wait on the host while rank 0 checks (no device-side spinning)
         return None
-    loc, vel, force, loc2, vel2 = (np.concatenate([p[k] for p in parts]) for k in range(5))
+    loc, vel, force, loc2, vel2, order = (np.concatenate([p[k] for p in parts]) for k in range(6))
     report = {'tick': 'the tick after the timed and host-buffer ticks (evolved, non-float32-exact state)'}
     # (1) float64 oracle on a row sample: forces.py on the float64 state (1e-4 rel + 1e-5 abs per component, plus the
     #     magnitude carried by pairs within 1e-5 rad of the model's sign / wrap discontinuities)
@@ -281,6 +285,9 @@ def parity_check(job, e, w, cfg, n_uniform=24, n_far=8, chunk=8):
         ctx.set_params(native.params_from_config(cfg, w.step_length))
         ctx.set_origin(*crowd_origin(w.loc))
         ctx.upload_state(loc, vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
+        # same staged order as the ranks (each rank's own order, shifted to its row block): the float32 tile partials of
+        # the pair force follow the tile composition, everything above them is integer or float64
+        ctx.set_slot_order(order)
         if len(w.borders):
             ctx.set_borders(w.borders, w.section_center, w.section_length)
         if len(w.static_obstacles):
@@ -451,6 +458,9 @@ def run_ours(args, world, rank, local_rank):
     ctx.set_params(native.params_from_config(cfg, w.step_length))
     k1_ms, k2_ms = job.max_over_ranks([iso['ms_pairs'] / max(iso['pair_launches'], 1), k2['ms']])
     k1_evals = iso['pair_evaluations'] / max(iso['pair_launches'], 1)
+    tile_pairs = lambda st: st['pair_evaluations'] / 65536.0                                           # noqa: E731
+    local_frac_alone = iso['local_tile_pairs'] / max(tile_pairs(iso), 1.0)
+    local_frac_timed = stats['local_tile_pairs'] / max(tile_pairs(stats), 1.0)
     k2_pairs, k2_evals = (int(sum(v)) for v in zip(*job.gather((k2['pairs'], k2['evals']))))
     e.check_peers()
     e.ctx.close()
@@ -501,7 +511,7 @@ def run_ours(args, world, rank, local_rank):
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 pair forces on double-single positions / f64 state, cell-list forces and integration',
             'data': 'synthetic', 'config': bench_config(name, w, world, args.workload), 'transport': transport,
-            'exchange_bytes_per_pedestrian': {'all_gather': 44, 'reduce_scatter': 32},
+            'exchange_bytes_per_pedestrian': {'all_gather': PLANE_BYTES, 'reduce_scatter': 32},
             'e2e': {'value': e2e_value, 'unit': 'pair-interactions/s', 'ms_per_step': e2e_ms_per_step,
                     'h2d_bytes_per_step': int(rows * 48), 'd2h_bytes_per_step': int(rows * 48), 'steps': e2e_steps,
                     'api': 'sfm_tick_host (pinned host loc/vel in, new loc/vel out)'},
@@ -515,13 +525,19 @@ def run_ours(args, world, rank, local_rank):
                          'ms_per_launch': k1_ms,
                          'pair_terms_evaluated_per_s': k1_rate, 'ordered_pairs_covered_per_s': k1_ordered_rate,
                          'frac_ordered_equivalent': k1_ordered_rate * instr / 1e12 / fp32_peak,
-                         'frac_with_double_single_differences': k1_rate * (instr + K1_INSTR_DOUBLE_SINGLE) / 1e12 / fp32_peak,
+                         'frac_with_double_single_differences':
+                             k1_rate * (instr + K1_INSTR_DOUBLE_SINGLE * (1.0 - local_frac_alone)) / 1e12 / fp32_peak,
                          'ms_per_launch_inside_step': k1_ms_in_step, 'instr_per_pair': instr,
+                         'local_tile_pair_fraction': {'timed_ticks': local_frac_timed, 'alone': local_frac_alone,
+                                                      'meaning': 'share of the 256 x 256 tile pairs (rank 0) read through '
+                                                                 'run-local origins: one subtraction per coordinate; the '
+                                                                 'rest -- neighbouring tiles -- take the double-single form'},
                          'note': 'f_ji = -f_ij exactly, so each unordered pair is evaluated once: achieved/frac count '
                                  'the evaluated pair terms (hardware utilisation); the ordered-pair figures are the '
-                                 'useful work the metric counts.  frac uses SURVEY 8d\'s per-pair figure; the kernel '
-                                 'additionally forms d = (hi_j - hi_i) + (lo_j - lo_i) (+4 instr per pair), which the '
-                                 '1e-4 / 1e-5 parity bar needs on evolved states',
+                                 'useful work the metric counts.  frac uses SURVEY 8d\'s per-pair figure; on neighbouring '
+                                 'tiles the kernel additionally forms d = (hi_j - hi_i) + (lo_j - lo_i) (+4 instr per pair), '
+                                 'which the 1e-4 / 1e-5 parity bar needs on evolved states -- frac_with_double_single_'
+                                 'differences weighs that by the share of tile pairs that took it',
                          'algorithmic': (f'{instr} FP32-pipe instr per pair term (SURVEY 8d: 58 = 3-D radius-on, 81 FLOP, '
                                          '5 MUFU; 48 = the 2-D radius-off specialisation a flat crowd takes)'),
                          'peak_source': f'148 SM x 128 lanes x sm_max_mhz ({peak_kind} MEASURED_PEAKS.json clock); '

@@ -69,6 +69,8 @@ struct SymArgs {
     int own_first_tile;        // first tile of this rank's rows
     long long* facc;           // [total_slots][4]: fixed-point force x, y, z and the poison counter
     PairParams pp;
+    int use_local;             // 0: every tile takes the double-single path (SFM_K1_LOCAL=0)
+    unsigned long long* local_pairs;   // [1] tile pairs that took the local path (sfm_stats.local_tile_pairs)
 };
 
 // asin(x) = x P(x^2) on [0, sin(pi/4)]: minimax fits, max abs error 6.2e-7 (6 terms) / 1.0e-7 (7 terms)
@@ -117,7 +119,10 @@ __device__ __forceinline__ RowP splat_row(const RowF& f) {
 
 // SIGN0: reproduce np.sign(0) = 0 (forces.py:108) in the fast path -- only instantiated for epsilon == 0, where theta' = 0
 // is reached by every pair with w parallel to d (e.g. a standing crowd); with epsilon != 0 the event has measure zero.
-template <bool RADIUS, bool PLANAR, bool SIGN0>
+// LOCAL: the partner tile is read through the origins of its 64-row runs (sfm_common.cuh) -- xj, yj, zj are the XR / YR /
+// ZR planes and I.x, I.y, I.z hold m = (hi_i - c) + lo_i for the run the lane is working on: d = xr_j - m_i, one
+// subtraction per coordinate where the double-single form takes three.
+template <bool RADIUS, bool PLANAR, bool SIGN0, bool LOCAL>
 __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const f32x2 yj, const f32x2 zj,
                                             const f32x2 xlj, const f32x2 ylj, const f32x2 zlj, const f32x2 rj,
                                             const f32x2 vxj, const f32x2 vyj, const f32x2 vzj, const PackedConst& c,
@@ -127,13 +132,14 @@ __device__ __forceinline__ void pair_terms2(const RowP& I, const f32x2 xj, const
 #if SFM_KS_ABLATE & 8
     const f32x2 dx = sub2(xj, I.x), dy = sub2(yj, I.y);
 #else
-    const f32x2 dx = add2(sub2(xj, I.x), sub2(xlj, I.xl)), dy = add2(sub2(yj, I.y), sub2(ylj, I.yl));
+    const f32x2 dx = LOCAL ? sub2(xj, I.x) : add2(sub2(xj, I.x), sub2(xlj, I.xl));
+    const f32x2 dy = LOCAL ? sub2(yj, I.y) : add2(sub2(yj, I.y), sub2(ylj, I.yl));
 #endif
     f32x2 dz = 0ull, wz = 0ull, Dz = 0ull;
     f32x2 d2 = fma2(dy, dy, mul2(dx, dx));
     const f32x2 dxy2 = d2;
     if (!PLANAR) {
-        dz = add2(sub2(zj, I.z), sub2(zlj, I.zl));
+        dz = LOCAL ? sub2(zj, I.z) : add2(sub2(zj, I.z), sub2(zlj, I.zl));
         d2 = fma2(dz, dz, d2);
     }
 #if SFM_KS_ABLATE & 64
@@ -312,58 +318,81 @@ __device__ __forceinline__ bool fixed_ok(float v) { return fabsf(v) < KS_FIXED_L
 __device__ __forceinline__ long long to_fixed(float v) { return __float2ll_rn(v * KS_FIXED_SCALE); }
 
 // One partner tile against this thread's rows: accumulates -F_i partials in registers (returned in gi) and +g into the
-// warp's private J-side slice.  Lanes are staggered over the j-quads so no two lanes of a warp touch the same j.
-template <bool RADIUS, bool PLANAR, bool SIGN0>
+// warp's private J-side slice.  Lanes are staggered over the j-quads so no two lanes of a warp touch the same j: the tile
+// is walked in four phases, and in a phase the lower half-warp works on the 16 quads of run `ph` of the tile while the
+// upper half-warp works on run `ph + 2` (lane l on quad (k + l) mod 16 of its run at step k).  A lane therefore stays on
+// one 64-row run for 16 steps, which is what lets the LOCAL path keep m_i = (hi_i - c_run) + lo_i in registers.
+template <bool RADIUS, bool PLANAR, bool SIGN0, bool LOCAL>
 __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], float (*__restrict__ accw)[K1_TJ],
-                                         const int lane, const RowP (&I)[KS_IR], const PackedConst& pc,
-                                         const AsinConst& sc, float (&gi)[KS_IR][3]) {
+                                         const int lane, const RowF (&If)[KS_IR], const RowP (&I)[KS_IR],
+                                         const PackedConst& pc, const AsinConst& sc, float (&gi)[KS_IR][3]) {
     f32x2 Gx[KS_IR], Gy[KS_IR], Gz[KS_IR];
 #pragma unroll
     for (int r = 0; r < KS_IR; ++r) Gx[r] = Gy[r] = Gz[r] = 0ull;
     const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
-#pragma unroll KS_UNROLL
-    for (int step = 0; step < KS_QUADS; ++step) {
-        const int j = ((step + lane) & (KS_QUADS - 1)) * 4;          // staggered: distinct j per lane
-        auto ld = [&](int plane) { return *reinterpret_cast<const ulonglong2*>(&tl[plane][j]); };
-        const ulonglong2 X = ld(PX), Y = ld(PY), XL = ld(PXL), YL = ld(PYL);
-        const ulonglong2 Z = PLANAR ? zero : ld(PZ), ZL = PLANAR ? zero : ld(PZL), VZ = PLANAR ? zero : ld(PVZ);
-        const ulonglong2 R = RADIUS ? ld(PR) : zero;
-        const ulonglong2 VX = ld(PVX), VY = ld(PVY);
-        f32x2 jx0 = 0ull, jy0 = 0ull, jz0 = 0ull, jx1 = 0ull, jy1 = 0ull, jz1 = 0ull;   // sum over my rows
+    constexpr int RUN_QUADS = SUB_ROWS / 4;                          // 16 quads per run
+    const int half = lane >> 4, l16 = lane & (RUN_QUADS - 1);
+#pragma unroll 1
+    for (int ph = 0; ph < SUBS_PER_TILE; ++ph) {
+        const int run = (ph + 2 * half) & (SUBS_PER_TILE - 1);
+        RowP Iw[KS_IR];
 #pragma unroll
-        for (int r = 0; r < KS_IR; ++r) {
-            f32x2 gx, gy, gz;
-            pair_terms2<RADIUS, PLANAR, SIGN0>(I[r], X.x, Y.x, Z.x, XL.x, YL.x, ZL.x, R.x, VX.x, VY.x, VZ.x, pc, sc, gx, gy,
-                                               gz);
-            Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
-            jx0 = r ? add2(jx0, gx) : gx; jy0 = r ? add2(jy0, gy) : gy;
-            if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz0 = r ? add2(jz0, gz) : gz; }
-            pair_terms2<RADIUS, PLANAR, SIGN0>(I[r], X.y, Y.y, Z.y, XL.y, YL.y, ZL.y, R.y, VX.y, VY.y, VZ.y, pc, sc, gx, gy,
-                                               gz);
-            Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
-            jx1 = r ? add2(jx1, gx) : gx; jy1 = r ? add2(jy1, gy) : gy;
-            if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz1 = r ? add2(jz1, gz) : gz; }
+        for (int r = 0; r < KS_IR; ++r) Iw[r] = I[r];
+        if (LOCAL) {
+            const float4 meta = *reinterpret_cast<const float4*>(&tl[PMETA][4 * run]);     // (c_x, c_y, c_z, compact)
+#pragma unroll
+            for (int r = 0; r < KS_IR; ++r) {
+                Iw[r].x = splat2((If[r].x - meta.x) + If[r].xl);     // hi_i - c: exact (lattice points)
+                Iw[r].y = splat2((If[r].y - meta.y) + If[r].yl);
+                if (!PLANAR) Iw[r].z = splat2((If[r].z - meta.z) + If[r].zl);
+            }
         }
-        // J side: F_j += g, into this warp's private slice (lanes hold distinct j, so plain read-modify-write)
+#pragma unroll KS_UNROLL
+        for (int step = 0; step < RUN_QUADS; ++step) {
+            const int j = (run * RUN_QUADS + ((step + l16) & (RUN_QUADS - 1))) * 4;   // staggered: distinct j per lane
+            auto ld = [&](int plane) { return *reinterpret_cast<const ulonglong2*>(&tl[plane][j]); };
+            const ulonglong2 X = ld(LOCAL ? PXR : PX), Y = ld(LOCAL ? PYR : PY);
+            const ulonglong2 XL = LOCAL ? zero : ld(PXL), YL = LOCAL ? zero : ld(PYL);
+            const ulonglong2 Z = PLANAR ? zero : ld(LOCAL ? PZR : PZ), ZL = (PLANAR || LOCAL) ? zero : ld(PZL);
+            const ulonglong2 VZ = PLANAR ? zero : ld(PVZ);
+            const ulonglong2 R = RADIUS ? ld(PR) : zero;
+            const ulonglong2 VX = ld(PVX), VY = ld(PVY);
+            f32x2 jx0 = 0ull, jy0 = 0ull, jz0 = 0ull, jx1 = 0ull, jy1 = 0ull, jz1 = 0ull;   // sum over my rows
+#pragma unroll
+            for (int r = 0; r < KS_IR; ++r) {
+                f32x2 gx, gy, gz;
+                pair_terms2<RADIUS, PLANAR, SIGN0, LOCAL>(Iw[r], X.x, Y.x, Z.x, XL.x, YL.x, ZL.x, R.x, VX.x, VY.x, VZ.x, pc,
+                                                          sc, gx, gy, gz);
+                Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
+                jx0 = r ? add2(jx0, gx) : gx; jy0 = r ? add2(jy0, gy) : gy;
+                if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz0 = r ? add2(jz0, gz) : gz; }
+                pair_terms2<RADIUS, PLANAR, SIGN0, LOCAL>(Iw[r], X.y, Y.y, Z.y, XL.y, YL.y, ZL.y, R.y, VX.y, VY.y, VZ.y, pc,
+                                                          sc, gx, gy, gz);
+                Gx[r] = add2(Gx[r], gx); Gy[r] = add2(Gy[r], gy);
+                jx1 = r ? add2(jx1, gx) : gx; jy1 = r ? add2(jy1, gy) : gy;
+                if (!PLANAR) { Gz[r] = add2(Gz[r], gz); jz1 = r ? add2(jz1, gz) : gz; }
+            }
+            // J side: F_j += g, into this warp's private slice (lanes hold distinct j, so plain read-modify-write)
 #if SFM_KS_ABLATE & 16
-        Gx[0] = add2(Gx[0], add2(jx0, jx1)); Gy[0] = add2(Gy[0], add2(jy0, jy1));
+            Gx[0] = add2(Gx[0], add2(jx0, jx1)); Gy[0] = add2(Gy[0], add2(jy0, jy1));
 #else
-        ulonglong2* ax = reinterpret_cast<ulonglong2*>(&accw[0][j]);
-        ulonglong2* ay = reinterpret_cast<ulonglong2*>(&accw[1][j]);
-        ulonglong2 vx = *ax, vy = *ay;
-        vx.x = add2(vx.x, jx0); vx.y = add2(vx.y, jx1);
-        vy.x = add2(vy.x, jy0); vy.y = add2(vy.y, jy1);
-        *ax = vx; *ay = vy;
+            ulonglong2* ax = reinterpret_cast<ulonglong2*>(&accw[0][j]);
+            ulonglong2* ay = reinterpret_cast<ulonglong2*>(&accw[1][j]);
+            ulonglong2 vx = *ax, vy = *ay;
+            vx.x = add2(vx.x, jx0); vx.y = add2(vx.y, jx1);
+            vy.x = add2(vy.x, jy0); vy.y = add2(vy.y, jy1);
+            *ax = vx; *ay = vy;
 #endif
-        if (!PLANAR) {
-            ulonglong2* az = reinterpret_cast<ulonglong2*>(&accw[2][j]);
-            ulonglong2 vz = *az;
-            vz.x = add2(vz.x, jz0); vz.y = add2(vz.y, jz1);
-            *az = vz;
-        }
+            if (!PLANAR) {
+                ulonglong2* az = reinterpret_cast<ulonglong2*>(&accw[2][j]);
+                ulonglong2 vz = *az;
+                vz.x = add2(vz.x, jz0); vz.y = add2(vz.y, jz1);
+                *az = vz;
+            }
 #if !(SFM_KS_ABLATE & 32)
-        __syncwarp();                                   // next step another lane owns this quad
+            __syncwarp();                               // next step another lane owns this quad
 #endif
+        }
     }
 #pragma unroll
     for (int r = 0; r < KS_IR; ++r) {
@@ -442,6 +471,10 @@ __global__ void SFM_KS_BOUNDS k1_sym_pairs(const SymArgs a) {
     for (int r = 0; r < KS_IR; ++r) own_flag |= (own[(size_t)PFLAG * a.rows_pad + r * KS_THREADS + tid] != 0.0f);
     const bool planar_own = __syncthreads_or(own_flag) == 0;
 
+    float own_box[4];                            // xy bounding box of tile I (PMETA, written by K3)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) own_box[k] = own[(size_t)PMETA * a.rows_pad + META_BOX + k];
+    int n_local = 0;
     for (int k = 0; k < n_items; ++k) {
         const int stage = k & 1;
         const int J = item_tile(k);
@@ -452,6 +485,13 @@ __global__ void SFM_KS_BOUNDS k1_sym_pairs(const SymArgs a) {
 #pragma unroll
         for (int r = 0; r < KS_IR; ++r) flag_j |= (tile[stage][PFLAG][tid + r * KS_THREADS] != 0.0f);
         const bool tile_nonplanar = __syncthreads_or(flag_j) != 0;
+        // local path: every 64-row run of the partner tile is compact around its own origin (K3 decides, per tick) and
+        // the two tiles' bounding boxes are at least LOCAL_SEP apart -- every pair closer than that stays double-single
+        const float* meta = tile[stage][PMETA];
+        const float sep = fmaxf(fmaxf(meta[META_BOX] - own_box[2], own_box[0] - meta[META_BOX + 2]),
+                                fmaxf(meta[META_BOX + 1] - own_box[3], own_box[1] - meta[META_BOX + 3]));
+        const bool tile_local = a.use_local && meta[3] != 0.0f && meta[7] != 0.0f && meta[11] != 0.0f && meta[15] != 0.0f &&
+                                sep >= LOCAL_SEP;
         if (J == I) {
             // diagonal tile: guarded asymmetric evaluation with self pairs removed, rows of I only
             PairAcc acc[KS_IR];
@@ -466,10 +506,12 @@ __global__ void SFM_KS_BOUNDS k1_sym_pairs(const SymArgs a) {
             for (int r = 0; r < KS_IR; ++r) { gi[r][0] = acc[r].gx; gi[r][1] = acc[r].gy; gi[r][2] = acc[r].gz; }
             __syncthreads();
         } else {
-            if (planar_own && !tile_nonplanar)
-                sym_tile<RADIUS, true, SIGN0>(tile[stage], accj[wid], lane, rowp, pc, sc, gi);
-            else
-                sym_tile<RADIUS, false, SIGN0>(tile[stage], accj[wid], lane, rowp, pc, sc, gi);
+            const bool planar = planar_own && !tile_nonplanar;
+            if (planar && tile_local) sym_tile<RADIUS, true, SIGN0, true>(tile[stage], accj[wid], lane, rowf, rowp, pc, sc, gi);
+            else if (planar) sym_tile<RADIUS, true, SIGN0, false>(tile[stage], accj[wid], lane, rowf, rowp, pc, sc, gi);
+            else if (tile_local) sym_tile<RADIUS, false, SIGN0, true>(tile[stage], accj[wid], lane, rowf, rowp, pc, sc, gi);
+            else sym_tile<RADIUS, false, SIGN0, false>(tile[stage], accj[wid], lane, rowf, rowp, pc, sc, gi);
+            n_local += tile_local ? 1 : 0;
             __syncthreads();                                    // every warp's J-side slice is complete
             // flush the J side: sum the warps' slices in fixed order, fixed-point atomics into the global accumulator
             for (int e = tid; e < K1_TJ; e += KS_THREADS) {
@@ -518,6 +560,7 @@ __global__ void SFM_KS_BOUNDS k1_sym_pairs(const SymArgs a) {
             if (fix[r][c] != 0) atomicAdd(dst + c, (unsigned long long)fix[r][c]);
         if (bad[r]) atomicAdd(dst + 3, (unsigned long long)bad[r]);
     }
+    if (tid == 0 && n_local) atomicAdd(a.local_pairs, (unsigned long long)n_local);
 }
 
 // Fixed-point accumulators -> float64 pair force of the local rows.  Rows whose poison counter is set (a degenerate or
@@ -534,15 +577,19 @@ struct FinishArgs {
     int* bad_list;                  // [n_local] rows to repair
     int* bad_count;                 // [1], zeroed before the launch
     PairParams pp;
+    const int* slot_of_row;         // row -> staged slot (k8_order.cuh); nullptr: row r is staged at slot r
 };
+
+__device__ __forceinline__ int slot_of(const FinishArgs& a, int row) { return a.slot_of_row ? a.slot_of_row[row] : row; }
 
 __global__ void __launch_bounds__(256) k1_sym_finish(const FinishArgs a) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= a.n_local) return;
-    const longlong4 own = *reinterpret_cast<const longlong4*>(a.facc_own + (size_t)row * 4);
+    const size_t slot = (size_t)slot_of(a, row);
+    const longlong4 own = *reinterpret_cast<const longlong4*>(a.facc_own + slot * 4);
     long long fx = own.x, fy = own.y, fz = own.z, poison = own.w;
     for (int r = 0; r < a.n_peer; ++r) {            // integer sums: associative, so any order gives the same bits
-        const longlong4 o = *reinterpret_cast<const longlong4*>(a.facc_peer[r] + (size_t)row * 4);
+        const longlong4 o = *reinterpret_cast<const longlong4*>(a.facc_peer[r] + slot * 4);
         fx += o.x; fy += o.y; fz += o.z; poison += o.w;
     }
     const double inv = 1.0 / 4294967296.0;
@@ -562,8 +609,9 @@ __global__ void __launch_bounds__(KS_REPAIR_THREADS) k1_sym_repair(const FinishA
     const int total = a.world * a.rows_pad;
     for (int b = blockIdx.x; b < count; b += gridDim.x) {
         const int r = a.bad_list[b];
-        const RowF I = load_row(a.planes + ((size_t)a.own_block * NPLANES) * a.rows_pad, (size_t)a.rows_pad, (size_t)r);
-        const int islot = a.own_block * a.rows_pad + r;
+        const int slot = slot_of(a, r);
+        const RowF I = load_row(a.planes + ((size_t)a.own_block * NPLANES) * a.rows_pad, (size_t)a.rows_pad, (size_t)slot);
+        const int islot = a.own_block * a.rows_pad + slot;
         double gx = 0.0, gy = 0.0, gz = 0.0;
         for (int j = tid; j < total; j += KS_REPAIR_THREADS) {
             const int q = j / a.rows_pad;

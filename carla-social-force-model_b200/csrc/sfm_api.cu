@@ -15,6 +15,7 @@
 #include "k3_integrate.cuh"
 #include "k4_lifecycle.cuh"
 #include "k7_peer.cuh"
+#include "k8_order.cuh"
 
 using namespace sfm;
 
@@ -153,6 +154,16 @@ struct sfm_ctx {
     DevBuf<unsigned long long> emit_count;
     DevBuf<unsigned long long> fixup_rows;
     bool fixup_zeroed = false;
+    bool k1_local = true;           // pair kernel: tiles whose 64-row runs are compact are read through the runs' origins
+    // staged slot order (k8_order.cuh): rows are staged along a Hilbert curve so that those runs ARE compact
+    DevBuf<int> slot_of_row, row_of_slot, order_box;
+    SetStorage order_sort;          // key / value / scratch buffers of the radix sort
+    int64_t order_n = -1, order_rows_pad = -1;     // the (n, rows_pad) the maps were built for; anything else = identity
+    int reorder_interval = 0;       // sfm_set_reorder_interval: rebuild the order every this many ticks (0: never)
+    int64_t ticks_total = 0;        // ticks stepped by this context (never reset)
+    int64_t order_tick = 0;         // ticks_total when the order was last rebuilt
+    bool order_due = false;         // new positions were uploaded / the interval was set: rebuild at the next (re)staging
+    int64_t reorders = 0;
     // accounting
     bool profiling = false;
     int64_t launches = 0, steps = 0, pair_launches = 0, pair_evals = 0;
@@ -397,6 +408,8 @@ int ensure_layout(sfm_ctx* c, int64_t n) {
     return 0;
 }
 
+bool order_valid(const sfm_ctx* c) { return c->n > 0 && c->order_n == c->n && c->order_rows_pad == c->rows_pad; }
+
 // The gather buffer the pair kernel reads this tick, and the one K3 stages the next tick's rows into (the same buffer
 // unless the peer-memory exchange alternates between the two halves).
 float* planes_cur(sfm_ctx* c) { return c->planes.p + (size_t)c->parity * c->world * NPLANES * c->rows_pad; }
@@ -408,6 +421,7 @@ StepArgs step_args(sfm_ctx* c, int target_parity = -1) {
     StepArgs a{};
     a.locr = c->locr.p; a.vels = c->vels.p; a.wp = c->wp.p; a.mode = c->mode.p;
     a.n = c->n; a.rows_pad = c->rows_pad;
+    a.row_of_slot = order_valid(c) ? c->row_of_slot.p : nullptr;
     a.ped_force = c->f_ped.p;
     a.f_total = c->f_total.p;
     const size_t own_off = (size_t)c->rank * NPLANES * c->rows_pad;
@@ -457,9 +471,12 @@ int launch_barrier(sfm_ctx* c) {
     return 0;
 }
 
+int maybe_reorder(sfm_ctx* c);
+
 // master state -> staged rows of the current tick.  With the peer-memory exchange the rows (pad rows included) go to
 // both halves of every rank's gather buffer, and a barrier makes sure everybody's rows have arrived: a collective call.
 int launch_stage(sfm_ctx* c) {
+    SFM_TRY(maybe_reorder(c));
     {
         SpanGuard g(c, ST_INTEGRATE);
         for (int half = 0; half < (c->p2p ? 2 : 1); ++half) {
@@ -471,6 +488,16 @@ int launch_stage(sfm_ctx* c) {
     }
     c->staged = true;
     if (c->p2p) SFM_TRY(launch_barrier(c));
+    return 0;
+}
+
+// Device counters of the pair kernels: [0] rows the repair path recomputed, [1] tile pairs that took the local path.
+int ensure_pair_counters(sfm_ctx* c) {
+    SFM_TRY(c->fixup_rows.ensure(2));
+    if (!c->fixup_zeroed) {
+        SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, 2 * sizeof(unsigned long long), c->stream));
+        c->fixup_zeroed = true;
+    }
     return 0;
 }
 
@@ -489,6 +516,8 @@ int launch_pairs_accumulate(sfm_ctx* c) {
     SymArgs a{};
     a.planes = planes_cur(c); a.rows_pad = (int)c->rows_pad; a.total_tiles = total_tiles;
     a.own_first_tile = c->rank * own_tiles; a.facc = c->facc.p; a.pp = make_pair_params(c->params.ped);
+    SFM_TRY(ensure_pair_counters(c));
+    a.use_local = c->k1_local ? 1 : 0; a.local_pairs = c->fixup_rows.p + 1;
     SpanGuard g(c, ST_PAIRS);
     SFM_CUDA(cudaMemsetAsync(c->facc.p, 0, slots * 4 * sizeof(long long), c->stream));
     dim3 grid(own_tiles, nsplit);
@@ -516,15 +545,12 @@ int launch_pairs_accumulate(sfm_ctx* c) {
 int launch_pairs_finish(sfm_ctx* c) {
     if (!c->pairs_pending) return 0;
     SFM_TRY(c->f_ped.ensure((size_t)3 * std::max<int64_t>(c->n, 1)));
-    SFM_TRY(c->fixup_rows.ensure(1));
-    if (!c->fixup_zeroed) {
-        SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, sizeof(unsigned long long), c->stream));
-        c->fixup_zeroed = true;
-    }
+    SFM_TRY(ensure_pair_counters(c));
     FinishArgs f{};
     f.planes = planes_cur(c); f.rows_pad = (int)c->rows_pad; f.world = c->world; f.own_block = c->rank;
     f.n_local = (int)c->n; f.facc_own = c->facc.p + (size_t)c->rank * c->rows_pad * 4; f.f_ped = c->f_ped.p;
     f.fixup_rows = c->fixup_rows.p; f.pp = make_pair_params(c->params.ped);
+    f.slot_of_row = order_valid(c) ? c->slot_of_row.p : nullptr;
     if (c->p2p)                                     // fused reduce-scatter: this rank's rows inside every peer's accumulator
         for (int r = 0; r < c->world; ++r)
             if (r != c->rank)
@@ -612,6 +638,41 @@ int rebin_peds(sfm_ctx* c, cudaStream_t st = nullptr) {
     c->launches += 2;
     SFM_CUDA(cudaGetLastError());
     c->perm_valid = true;
+    return 0;
+}
+
+// Staged slot order from the current positions (k8_order.cuh): bounding box, Hilbert keys, stable radix sort, the two maps.
+// Stream-ordered on the main stream; the caller restages (K3 or k3_stage) afterwards.
+int rebuild_order(sfm_ctx* c) {
+    const int n = (int)c->n;
+    if (n <= 0) return 0;
+    SetStorage& st = c->order_sort;
+    SFM_TRY(st.key.ensure(n)); SFM_TRY(st.key_tmp.ensure(n)); SFM_TRY(st.cell_item.ensure(n)); SFM_TRY(st.val_tmp.ensure(n));
+    SFM_TRY(c->slot_of_row.ensure(n)); SFM_TRY(c->row_of_slot.ensure(c->rows_pad)); SFM_TRY(c->order_box.ensure(4));
+    SpanGuard g(c, ST_CELLS);
+    k8_bbox_init<<<1, 32, 0, c->stream>>>(c->order_box.p);
+    k8_bbox<<<cdiv(n, 256), 256, 0, c->stream>>>(c->locr.p, n, c->order_box.p);
+    k8_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(c->locr.p, n, c->order_box.p, st.key.p, st.cell_item.p);
+    c->launches += 3;
+    SFM_CUDA(cudaGetLastError());
+    SFM_TRY(sort_items(c, st, n, 2 * ORDER_BITS));
+    k8_fill_order<<<cdiv(c->rows_pad, 256), 256, 0, c->stream>>>(st.cell_item.p, n, (int)c->rows_pad, c->slot_of_row.p,
+                                                                 c->row_of_slot.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    c->order_n = c->n; c->order_rows_pad = c->rows_pad;
+    c->order_tick = c->ticks_total;
+    c->order_due = false;
+    c->reorders += 1;
+    c->config_epoch += 1;                       // a captured tick graph holds the old maps' pointers (or none)
+    return 0;
+}
+
+// Called wherever rows are about to be (re)staged: rebuilds the order when it is due.  Crowds of fewer than 8 tiles stay
+// in row order -- nearly all of their tile pairs are neighbours, which take the double-single path anyway.
+int maybe_reorder(sfm_ctx* c) {
+    if (c->reorder_interval <= 0 || c->n <= 0 || c->rows_pad * (int64_t)c->world < 8 * ROW_ALIGN) return 0;
+    if (!order_valid(c) || c->order_due || c->ticks_total - c->order_tick >= c->reorder_interval) return rebuild_order(c);
     return 0;
 }
 
@@ -911,6 +972,9 @@ int step_end(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool ke
         SFM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         c->join_pending = false;
     }
+    // the order may be rebuilt here: the pair force of this tick has been read out under the old one (finish / repair
+    // above), K3 below stages the next tick's rows under the new one.  (Not while a tick is being captured as a graph.)
+    if (update_velocity && !c->use_graph) SFM_TRY(maybe_reorder(c));
     StepArgs a = step_args(c);
     if (P.enable[SFM_FORCE_BORDER] && c->borders.s.count) a.f_border = c->f_border.p;
     if (P.enable[SFM_FORCE_STATIC_OBSTACLE] && c->stat.s.count) a.f_static = c->f_static.p;
@@ -936,6 +1000,7 @@ int step_end(sfm_ctx* c, bool update_velocity, bool integrate_positions, bool ke
     }
     if (update_velocity) {
         c->steps += 1;
+        c->ticks_total += 1;
         c->perm_valid = false;      // positions moved; rebin before the next segment pass
     }
     c->step_open = false;
@@ -1066,6 +1131,7 @@ int sfm_create(int device, sfm_ctx** out) {
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     SFM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char* env = std::getenv("SFM_OVERLAP")) c->overlap = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SFM_K1_LOCAL")) c->k1_local = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K1_TARGET_CTAS")) c->k1_target_ctas = std::max(1, std::atoi(env));
     else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
     *out = c;
@@ -1086,6 +1152,7 @@ int sfm_destroy(sfm_ctx* c) {
     if (c->rec_pinned) cudaFreeHost(c->rec_pinned);
     c->ped_scan_tmp.release();
     c->raw_mode.release(); c->perm.release(); c->ped_start.release(); c->ped_cursor.release(); c->ped_cell.release();
+    c->order_sort.release(); c->slot_of_row.release(); c->row_of_slot.release(); c->order_box.release();
     c->borders.release(); c->stat.release(); c->dyn.release(); c->emit.release(); c->emit_count.release(); c->fixup_rows.release(); c->facc.release();
     if (c->p2p)
         for (int r = 0; r < c->world; ++r)
@@ -1176,6 +1243,7 @@ int sfm_upload_state(sfm_ctx* c, int64_t n, const double* loc, const double* vel
     c->rec_ident_n = -1;           // a new table: sfm_tick_records must adopt its identity column again
     c->staged = false;
     c->perm_valid = false;
+    c->order_due = true;                       // new positions: the staged order is due
     if (n == 0) return 0;
     SFM_TRY(c->locr.ensure(n)); SFM_TRY(c->vels.ensure(n)); SFM_TRY(c->wp.ensure(n)); SFM_TRY(c->mode.ensure(n));
     SFM_TRY(c->raw_a.ensure(3 * n)); SFM_TRY(c->raw_b.ensure(3 * n)); SFM_TRY(c->raw_c.ensure(3 * n));
@@ -1366,7 +1434,7 @@ int sfm_step(sfm_ctx* c, int n_steps, int integrate_positions) {
             SFM_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
             c->launches += c->graph_launches; c->pair_launches += c->graph_pair_launches;
             c->pair_evals += c->graph_pair_evals;
-            c->steps += 1; c->graph_replays += 1;
+            c->steps += 1; c->ticks_total += 1; c->graph_replays += 1;
             c->perm_valid = false;
             continue;
         }
@@ -1650,6 +1718,61 @@ int sfm_stage(sfm_ctx* c) {
 /* ================================================================================================================
  * lifecycle: mode machines, gap acceptance, routes, device-generated vehicle rings, recorder
  * ================================================================================================================ */
+
+int sfm_set_reorder_interval(sfm_ctx* c, int ticks) {
+    SFM_TRY(check_ctx(c));
+    if (ticks < 0) return fail("negative interval");
+    c->reorder_interval = ticks;
+    c->order_due = true;                        // due at the next (re)staging
+    return 0;
+}
+
+int sfm_reorder_slots(sfm_ctx* c) {
+    SFM_TRY(check_ctx(c));
+    if (c->n <= 0) return fail("no state uploaded yet");
+    if (c->step_open) return fail("a step is open: call sfm_step_end first");
+    SFM_TRY(rebuild_order(c));
+    c->staged = false;
+    return 0;
+}
+
+int sfm_get_slot_order(sfm_ctx* c, int64_t n, int32_t* slot_of_row) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n) return fail("row count differs from the uploaded state");
+    if (!slot_of_row) return fail("null array");
+    if (!order_valid(c)) {
+        for (int64_t i = 0; i < n; ++i) slot_of_row[i] = (int32_t)i;
+        return 0;
+    }
+    SFM_CUDA(cudaMemcpyAsync(slot_of_row, c->slot_of_row.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    SFM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_set_slot_order(sfm_ctx* c, int64_t n, const int32_t* slot_of_row) {
+    SFM_TRY(check_ctx(c));
+    if (n != c->n || n <= 0) return fail("row count differs from the uploaded state");
+    if (!slot_of_row) return fail("null array");
+    if (c->step_open) return fail("a step is open: call sfm_step_end first");
+    std::vector<uint8_t> seen((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t s = slot_of_row[i];
+        if (s < 0 || s >= n || seen[(size_t)s]) return fail("slot_of_row is not a permutation of [0, n)");
+        seen[(size_t)s] = 1;
+    }
+    SFM_TRY(c->slot_of_row.ensure(n)); SFM_TRY(c->row_of_slot.ensure(c->rows_pad));
+    SFM_CUDA(cudaMemcpyAsync(c->slot_of_row.p, slot_of_row, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    k8_invert_order<<<cdiv(c->rows_pad, 256), 256, 0, c->stream>>>(c->slot_of_row.p, (int)n, (int)c->rows_pad, c->row_of_slot.p);
+    c->launches += 1;
+    SFM_CUDA(cudaGetLastError());
+    SFM_CUDA(cudaStreamSynchronize(c->stream));          // the host array may go away
+    c->order_n = c->n; c->order_rows_pad = c->rows_pad;
+    c->order_tick = c->ticks_total;
+    c->order_due = false;
+    c->staged = false;
+    c->config_epoch += 1;
+    return 0;
+}
 
 int sfm_set_mode_machines(sfm_ctx* c, int64_t n, const double* initial_speed, const double* crossing_speed,
                           const double* safety_margin, const double* mode_speed, const double* next_mode_time,
@@ -2194,7 +2317,7 @@ int sfm_reset_stats(sfm_ctx* c) {
     c->launches = c->steps = c->pair_launches = c->pair_evals = 0;
     for (double& m : c->ms) m = 0.0;
     c->graph_replays = 0;
-    if (c->fixup_rows.p) SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, sizeof(unsigned long long), c->stream));
+    if (c->fixup_rows.p) SFM_CUDA(cudaMemsetAsync(c->fixup_rows.p, 0, 2 * sizeof(unsigned long long), c->stream));
     c->fixup_zeroed = c->fixup_rows.p != nullptr;
     return 0;
 }
@@ -2209,12 +2332,14 @@ int sfm_get_stats(sfm_ctx* c, sfm_stats* out) {
     out->ms_lifecycle = c->ms[ST_LIFECYCLE];
     out->graph_replays = c->graph_replays;
     out->fixup_rows = 0;
+    out->local_tile_pairs = 0;
     out->pair_evaluations = c->pair_evals;
     if (c->fixup_rows.p && c->fixup_zeroed) {
-        unsigned long long v = 0;
-        SFM_CUDA(cudaMemcpyAsync(&v, c->fixup_rows.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long v[2] = {0, 0};
+        SFM_CUDA(cudaMemcpyAsync(v, c->fixup_rows.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
         SFM_CUDA(cudaStreamSynchronize(c->stream));
-        out->fixup_rows = (int64_t)v;
+        out->fixup_rows = (int64_t)v[0];
+        out->local_tile_pairs = (int64_t)v[1];
     }
     return 0;
 }

@@ -10,18 +10,43 @@ namespace sfm {
 
 // ---- staged float32 planes read by the all-pairs kernel -------------------------------------------------------------
 // Gather buffer layout: [world][NPLANES][rows_pad] float32.  One rank block is what a rank contributes to the per-step
-// all-gather (44 B per pedestrian row).
+// all-gather (60 B per pedestrian row).
 //
 // Positions are staged as float32 PAIRS (double-single): x - origin = hi + lo with hi on the 2^-6 m lattice (exact in
 // float32 while |x - origin| < 2^18 m) and |lo| <= 2^-7 m.  The pair kernel forms d = (hi_j - hi_i) + (lo_j - lo_i): the
 // first difference is exact (both operands are lattice points), the second is exact to 2^-31 m, so d carries one float32
 // rounding RELATIVE TO |d| -- independent of how far the crowd is from the origin.  (A single float32 per coordinate
 // rounds to 1.5e-5 m at |x| >= 256 m, which alone breaks the 1e-4 / 1e-5 force tolerance on integrated states.)
-constexpr int NPLANES = 11;
-enum Plane { PX = 0, PY = 1, PZ = 2, PXL = 3, PYL = 4, PZL = 5, PR = 6, PVX = 7, PVY = 8, PVZ = 9, PFLAG = 10 };
+//
+// Sub-tile-local copies (the pair kernel's "local" path).  Every run of SUB_ROWS = 64 consecutive rows (a quarter of a
+// 256-row tile) also carries its positions as ONE float32 per coordinate relative to the run's own origin c -- the centre
+// of its bounding box, on the same lattice: xr = float32(x - origin - c).  When the run is spatially compact (every
+// |x - origin - c| <= LOCAL_LIMIT) the kernel forms d = xr_j - m_i with m_i = (hi_i - c_J) + lo_i computed once per
+// (row, sub-tile): ONE subtraction per coordinate and pair instead of three.  Rounding: xr_j to 2^-25 |xr_j|, m_i to
+// 2^-25 |x_i - c_J| (hi_i - c_J is exact: lattice points), the difference to 2^-25 |d| -- for the pairs that carry the
+// force (|d| of a metre or two, both magnitudes below ~8 m in a crowd ordered along a space-filling curve) about 5e-7 m,
+// against 1.5e-5 m for a single global origin.  Whether a run is compact is decided where it is staged (K3), per tick;
+// tiles with a run that is not take the double-single path, so the row order is a matter of speed, never of accuracy
+// (profiles/local_origin_emulation.py: staging error alone, both paths, against the force tolerance).
+// Which pairs may take it is decided per TILE pair, by geometry alone: only when the xy bounding boxes of the two 256-row
+// tiles are at least LOCAL_SEP apart.  Every pair closer than that -- the pairs that carry the force, and with it the
+// sensitivity to d -- is evaluated in double-single form (or by the guarded diagonal code), so the local path only ever
+// sees the far field, where a micrometre is nothing; what it saves is the work on the 95-99 % of the tile pairs that are
+// not neighbours.
+// The plane PMETA carries, in the first 16 slots of every tile, (c_x, c_y, c_z, compact ? 1 : 0) of its four runs, and in
+// slots META_BOX .. META_BOX + 3 the tile's xy bounding box (min x, min y, max x, max y, origin-relative).
+constexpr int NPLANES = 15;
+enum Plane { PX = 0, PY = 1, PZ = 2, PXL = 3, PYL = 4, PZL = 5, PR = 6, PVX = 7, PVY = 8, PVZ = 9, PFLAG = 10,
+             PXR = 11, PYR = 12, PZR = 13, PMETA = 14 };
 constexpr int ROW_ALIGN = 256;              // rows_pad granularity == j-tile length of the pair kernel
 constexpr float PAD_POS = 1.0e15f;          // padded rows sit this far away: exp(-dist/B) underflows to exactly 0
 constexpr double POS_LATTICE = 64.0;        // hi parts are multiples of 1 / POS_LATTICE metres
+constexpr int SUB_ROWS = 64;                // rows per sub-tile run (two warps of the staging CTA)
+constexpr int SUBS_PER_TILE = ROW_ALIGN / SUB_ROWS;
+constexpr double LOCAL_LIMIT = 16.0;        // largest |x - origin - c| of a compact run, metres
+constexpr float LOCAL_SEP = 1.0f;           // tile pairs whose bounding boxes are closer than this stay double-single
+constexpr int META_BOX = 16;                // first slot of the tile's bounding box in its PMETA plane
+constexpr double LOCAL_RANGE = 131072.0;    // run origins beyond 2^17 m from the staging origin: hi - c no longer exact
 
 // Parameters of the float32 Moussaid evaluation, pre-folded on the host (see k1_ped_pairs.cuh for the algebra).
 struct PairParams {

@@ -3,7 +3,7 @@
 Rows shard: each rank owns the state, the cell-list forces and the integration of a contiguous row block.  The pair
 force is evaluated once per unordered pair by exactly one rank (half-shell over 256-row tiles), so a step has two
 exchanges: an integer reduce-scatter of the fixed-point force accumulators (32 B per pedestrian) and an all-gather of
-each rank's staged block (44 B per pedestrian: 11 float32 planes).  Two transports:
+each rank's staged block (60 B per pedestrian: 15 float32 planes).  Two transports:
 
 * ``exchange='peer'`` (default on one box): the library maps every rank's buffers through CUDA IPC once, and the two
   collectives are folded into its own kernels -- ``k1_sym_finish`` pulls the partial accumulators over NVLink, K3 pushes
@@ -68,7 +68,11 @@ class _DeviceView:
 
 
 class Engine:
-    def __init__(self, sfm_config, step_length, device=None, group=None, use_torch_stream=True, exchange=None):
+    def __init__(self, sfm_config, step_length, device=None, group=None, use_torch_stream=True, exchange=None,
+                 reorder_every=32):
+        """``reorder_every``: ticks between rebuilds of the staged slot order (rows staged along a Hilbert curve so that the
+        pair kernel's one-subtraction local path applies, ``csrc/k8_order.cuh``); 0 keeps rows staged in row order -- then a
+        multi-rank run and a single-GPU run of the same crowd agree bit for bit without exchanging the order."""
         import os
         import torch                                   # plumbing only
         self.exchange_mode = exchange or os.environ.get('SFM_EXCHANGE', 'peer')
@@ -86,6 +90,8 @@ class Engine:
         self.ctx = native.Context(self.device)
         self.sfm_config, self.step_length = sfm_config, step_length
         self.ctx.set_params(native.params_from_config(sfm_config, step_length))
+        self.reorder_every = int(os.environ.get('SFM_REORDER_EVERY', reorder_every))
+        self.ctx.set_reorder_interval(self.reorder_every)
         # A dedicated (non-default) torch stream carries both the library's kernels and the NCCL all-gather, so the
         # two are ordered without host synchronisation; CUDA events recorded on it time the whole step.
         prio = -1 if os.environ.get('SFM_AUX_PRIORITY', 'high') == 'low' else 0      # experiment knob, see sfm_api.cu

@@ -23,13 +23,14 @@ IDLE = 0
 
 class HeadlessRunner:
     def __init__(self, sfm_config, workload, life, device=0, device_vehicles=False, record_every=0, record_capacity=0,
-                 ctx=None):
+                 ctx=None, reorder_every=32):
         w = workload
         self.w, self.life = w, life
         self.dt = w.step_length
         self.ctx = ctx or native.Context(device)
         c = self.ctx
         c.set_params(native.params_from_config(sfm_config, w.step_length))
+        c.set_reorder_interval(reorder_every)              # staged slot order (csrc/k8_order.cuh): speed only
         spawn_tick = getattr(life, 'spawn_tick', None)
         self.spawn_tick = np.zeros(w.n, dtype=np.int64) if spawn_tick is None else np.asarray(spawn_tick)
         first = np.nonzero(self.spawn_tick == 0)[0]

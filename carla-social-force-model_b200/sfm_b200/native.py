@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get('SFM_LIB') or os.path.join(HERE, 'libsfm_b200.so')    
 FORCE_CLASSES = ('acceleration_force', 'pedestrian_force', 'border_force', 'static_obstacle_force',
                  'dynamic_obstacle_force')                      # pedestrian_simulation.py:37-48 dict order
 ACCELERATION, PEDESTRIAN, BORDER, STATIC_OBSTACLE, DYNAMIC_OBSTACLE = range(5)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # every symbol include/sfm_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create', 'sfm_destroy', 'sfm_set_stream',
@@ -27,6 +27,7 @@ SYMBOLS = ('sfm_abi_version', 'sfm_last_error', 'sfm_device_count', 'sfm_create'
            'sfm_force', 'sfm_enumerate_pairs', 'sfm_count_point_evaluations', 'sfm_step', 'sfm_tick_host', 'sfm_tick_records', 'sfm_apply_force',
            'sfm_host_column_gather', 'sfm_host_column_equal', 'sfm_host_register', 'sfm_host_unregister', 'sfm_download_force',
            'sfm_download_class_force', 'sfm_gather_buffer', 'sfm_stage', 'sfm_step_begin', 'sfm_step_end',
+           'sfm_set_reorder_interval', 'sfm_reorder_slots', 'sfm_get_slot_order', 'sfm_set_slot_order',
            'sfm_force_accumulator', 'sfm_set_profiling', 'sfm_reset_stats', 'sfm_get_stats',
            # lifecycle
            'sfm_set_mode_machines', 'sfm_set_traffic', 'sfm_tick_modes', 'sfm_download_modes', 'sfm_set_routes',
@@ -56,7 +57,8 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [('launches', C.c_int64), ('steps', C.c_int64), ('ms_pairs', C.c_double), ('ms_cells', C.c_double),
                 ('ms_segments', C.c_double), ('ms_integrate', C.c_double), ('pair_launches', C.c_int64),
-                ('fixup_rows', C.c_int64), ('pair_evaluations', C.c_int64), ('ms_lifecycle', C.c_double), ('graph_replays', C.c_int64)]
+                ('fixup_rows', C.c_int64), ('pair_evaluations', C.c_int64), ('ms_lifecycle', C.c_double), ('graph_replays', C.c_int64),
+                ('local_tile_pairs', C.c_int64)]
 
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
@@ -128,6 +130,10 @@ def lib():
         'sfm_download_class_force': (C.c_int, [p_ctx, C.c_int, i64, p_d]),
         'sfm_gather_buffer': (C.c_int, [p_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         'sfm_stage': (C.c_int, [p_ctx]),
+        'sfm_set_reorder_interval': (C.c_int, [p_ctx, C.c_int]),
+        'sfm_reorder_slots': (C.c_int, [p_ctx]),
+        'sfm_get_slot_order': (C.c_int, [p_ctx, C.c_int64, C.c_void_p]),
+        'sfm_set_slot_order': (C.c_int, [p_ctx, C.c_int64, C.c_void_p]),
         'sfm_step_begin': (C.c_int, [p_ctx]),
         'sfm_step_end': (C.c_int, [p_ctx, C.c_int]),
         'sfm_force_accumulator': (C.c_int, [p_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
@@ -439,6 +445,25 @@ class Context:
 
     def stage(self):
         _check(self._lib.sfm_stage(self._h))
+
+    # -- staged slot order (csrc/k8_order.cuh): rows staged along a Hilbert curve, so the pair kernel's local path applies
+    def set_reorder_interval(self, ticks):
+        _check(self._lib.sfm_set_reorder_interval(self._h, int(ticks)))
+
+    def reorder_slots(self):
+        _check(self._lib.sfm_reorder_slots(self._h))
+
+    def slot_order(self):
+        """int32 [n]: the staged slot of every row (a permutation of range(n); the identity unless reordering is on)."""
+        out = np.empty(self.n, dtype=np.int32)
+        _check(self._lib.sfm_get_slot_order(self._h, self.n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_slot_order(self, slot_of_row):
+        a = np.ascontiguousarray(slot_of_row, dtype=np.int32)
+        if a.shape != (self.n,):
+            raise ValueError(f'expected shape {(self.n,)}, got {a.shape}')
+        _check(self._lib.sfm_set_slot_order(self._h, self.n, a.ctypes.data_as(C.c_void_p)))
 
     # -- peer-memory exchange (K7)
     PEER_HANDLE_BYTES = 3 * 64

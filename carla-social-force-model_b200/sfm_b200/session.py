@@ -17,6 +17,9 @@ _session = None
 class Session:
     def __init__(self, device):
         self.ctx = native.Context(device)
+        # rows stay in the caller's (spawn) order; below the API they are staged along a Hilbert curve, rebuilt every few
+        # ticks, so that the pair kernel's run-local path applies (csrc/k8_order.cuh) -- speed only
+        self.ctx.set_reorder_interval(int(os.environ.get('SFM_REORDER_EVERY', '32')))
         self.params_key = None
         self.thresholds = None
         self.owner = {native.BORDER: None, native.STATIC_OBSTACLE: None, native.DYNAMIC_OBSTACLE: None}

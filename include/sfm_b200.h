@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SFM_ABI_VERSION 4
+#define SFM_ABI_VERSION 5
 
 typedef struct sfm_ctx sfm_ctx;
 
@@ -72,6 +72,10 @@ typedef struct {
     int64_t pair_evaluations;             /* pair terms K1 evaluated (padded slots included; one per unordered pair) */
     double ms_lifecycle;                  /* K4/K5/K6: mode machines, waypoint hand-over, vehicle rings, recorder */
     int64_t graph_replays;                /* ticks of sfm_step that ran as one CUDA graph launch (SFM_GRAPH=1 enables) */
+    int64_t local_tile_pairs;             /* K1 tile pairs (256 x 256 rows) read through the origins of the partner tile's
+                                             64-row runs: the one-subtraction "local" path, taken for spatially compact
+                                             tiles (rows ordered along a space-filling curve); the rest took the
+                                             double-single path.  Speed only -- both paths hold the force tolerance. */
 } sfm_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -187,6 +191,24 @@ int sfm_force_accumulator(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_ran
 /* Makes this rank's block of the gather buffer reflect the current master state (after an upload or refresh), so the
  * first all-gather can run before the first step. */
 int sfm_stage(sfm_ctx* ctx);
+
+/* ---- staged slot order.  Row order belongs to the caller: PedState.state is in spawn order (pedestrian_state.py:26-43,
+ *      np.append) and every result of this library is per row.  Below the API the rows of a rank are STAGED for the pair
+ *      kernel in the order of a Hilbert curve over their xy positions, so that runs of 64 consecutive staged slots are
+ *      spatially compact and the kernel can read them through the run's own origin (one float32 subtraction per
+ *      coordinate and pair instead of the three of the double-single form; sfm_stats.local_tile_pairs counts the tile
+ *      pairs that did).  Speed only: a tile whose runs are not compact takes the double-single path, both hold the force
+ *      tolerance.  The float32 partial sums of the pair force follow the tile composition, so two contexts agree BIT FOR
+ *      BIT only under the same order -- sfm_get_slot_order / sfm_set_slot_order carry it from one to the other (bench.py's
+ *      single-GPU replay of a multi-rank tick); with the default interval 0 the order is the identity and nothing changes.
+ *      No counterpart in the reference (its pair force materialises the dense (N, N-1) arrays of stateutils.py:32-75). */
+/* Rebuild the order from the current positions every `ticks` ticks / restagings (0 = never: keep the current order). */
+int sfm_set_reorder_interval(sfm_ctx* ctx, int ticks);
+/* Rebuild the order now; the rows are restaged by the next step (multi-rank peer contexts: by the next sfm_stage). */
+int sfm_reorder_slots(sfm_ctx* ctx);
+/* slot_of_row: int32 [n], a permutation of [0, n) -- the staged slot of every row of this context. */
+int sfm_get_slot_order(sfm_ctx* ctx, int64_t n, int32_t* slot_of_row);
+int sfm_set_slot_order(sfm_ctx* ctx, int64_t n, const int32_t* slot_of_row);
 
 /* ---- peer-memory exchange over NVLink (K7): the two collectives of the multi-GPU tick folded into the kernels next to
  *      them.  Set-up (once, after sfm_set_partition + sfm_upload_state on every rank): each rank exports three

@@ -33,10 +33,10 @@ def test_library_exports_every_declared_symbol(built):
 
 
 def test_struct_layout_matches_header():
-    # sfm_params: 5 doubles + 3 x 7 doubles + 6 int32 ; sfm_stats: 11 x 8 bytes
+    # sfm_params: 5 doubles + 3 x 7 doubles + 6 int32 ; sfm_stats: 12 x 8 bytes
     assert ctypes.sizeof(native.MoussaidParams) == 56
     assert ctypes.sizeof(native.Params) == 5 * 8 + 3 * 56 + 6 * 4
-    assert ctypes.sizeof(native.Stats) == 88
+    assert ctypes.sizeof(native.Stats) == 96
 
 
 def test_fails_loudly_without_device(built):

@@ -191,6 +191,9 @@ def test_device_identity_check_notices_replaced_objects(sfm_config, monkeypatch)
     still be noticed: the tick then hands the table back untouched and the full path rebuilds the machines, so the run
     equals one whose table held that object from the start; steady ticks never call the host-side comparison."""
     from sfm_b200 import native
+    # rows staged in row order: the two runs below are compared bit for bit, and the replaced object triggers one extra
+    # full upload -- which would rebuild the staged order (csrc/k8_order.cuh) at a different tick than the plain run does
+    monkeypatch.setenv('SFM_REORDER_EVERY', '0')
     w = synth.make_config(2, n=4096)                       # >= 4096 rows: the 2-D DMA write-back path
     calls = []
     real = native.column_equal

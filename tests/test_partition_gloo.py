@@ -42,9 +42,10 @@ def _rank_main(rank, world, port, n, out_dir):
     bounds = engine.partition_rows(w.n, world)
     rows_pad = engine.padded_rows(bounds)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    # this rank's staged block: 11 float32 planes x rows_pad -- position hi parts (2^-6 m lattice), lo parts, radius,
-    # lambda * velocity, non-planar flag (csrc/sfm_common.cuh) -- restated on the host
-    PX, PXL, PR, PVX, PFLAG, NPLANES = 0, 3, 6, 7, 10, 11
+    # this rank's staged block: 15 float32 planes x rows_pad -- position hi parts (2^-6 m lattice), lo parts, radius,
+    # lambda * velocity, non-planar flag, positions relative to the origin of the row's 64-row run, run origins + compact
+    # flags in the first 16 slots of every 256-row tile (csrc/sfm_common.cuh) -- restated on the host
+    PX, PXL, PR, PVX, PFLAG, PXR, PMETA, NPLANES = 0, 3, 6, 7, 10, 11, 14, 15
     block = torch.zeros(NPLANES, rows_pad, dtype=torch.float32)
     hi_part = np.rint(w.loc[lo:hi] * 64.0) / 64.0
     block[PX:PX + 3, :hi - lo] = torch.from_numpy(hi_part.T.astype(np.float32))
@@ -52,6 +53,17 @@ def _rank_main(rank, world, port, n, out_dir):
     block[PR, :hi - lo] = torch.from_numpy(w.radius[lo:hi].astype(np.float32))
     block[PVX:PVX + 3, :hi - lo] = torch.from_numpy((2.0 * w.vel[lo:hi]).T.astype(np.float32))
     block[PX:PX + 2, hi - lo:] = 1.0e15                             # pad rows sit far away
+    block[PXR:PXR + 2, hi - lo:] = 1.0e15
+    for run in range(rows_pad // 64):
+        rows = w.loc[lo + 64 * run:min(hi, lo + 64 * (run + 1))]
+        meta = 256 * (run // 4) + 4 * (run % 4)
+        block[PMETA, meta + 3] = 1.0                                # a run without live rows counts as compact
+        if len(rows) == 0:
+            continue
+        c = np.rint(0.5 * (rows.min(axis=0) + rows.max(axis=0)) * 64.0) / 64.0
+        block[PXR:PXR + 3, 64 * run:64 * run + len(rows)] = torch.from_numpy((rows - c).T.astype(np.float32))
+        block[PMETA, meta:meta + 3] = torch.from_numpy(c.astype(np.float32))
+        block[PMETA, meta + 3] = float(np.abs(rows - c).max() <= 16.0)
     gathered = torch.zeros(world, NPLANES, rows_pad, dtype=torch.float32)
     dist.all_gather_into_tensor(gathered.view(-1), block.view(-1))
     # rebuild the global crowd from the gathered layout (hi + lo is exact) and compute this rank's rows
@@ -61,6 +73,16 @@ def _rank_main(rank, world, port, n, out_dir):
     vel = np.concatenate([gathered[q, PVX:PVX + 3, :rows_of(q)].numpy().T for q in range(world)]).astype(np.float64) / 2.0
     rad = np.concatenate([gathered[q, PR, :rows_of(q)].numpy() for q in range(world)]).astype(np.float64)
     assert np.array_equal(loc, w.loc) and np.array_equal(vel, w.vel) and np.array_equal(rad, w.radius)
+    # the run-local copies say the same positions to float32 rounding at the run's extent (origin + xr)
+    for q in range(world):
+        for run in range((rows_of(q) + 63) // 64):
+            meta = 256 * (run // 4) + 4 * (run % 4)
+            c = gathered[q, PMETA, meta:meta + 3].numpy().astype(np.float64)
+            k = min(64, rows_of(q) - 64 * run)
+            xr = gathered[q, PXR:PXR + 3, 64 * run:64 * run + k].numpy().astype(np.float64).T
+            want = w.loc[int(bounds[q]) + 64 * run:int(bounds[q]) + 64 * run + k]
+            bound = 2.0 ** -24 * max(1.0, np.abs(want - c).max())
+            assert np.abs(c + xr - want).max() <= bound
     f = O.pedestrian_force(loc, vel, rad, rows=np.arange(lo, hi))
     np.save(os.path.join(out_dir, f'f{rank}.npy'), f)
     dist.barrier()
