@@ -6,9 +6,17 @@
 // 256-row tiles is therefore visited once ("half shell": tile I takes the partners I+1 .. I+T/2 cyclically) and the
 // result is added to the rows of I and subtracted from the rows of J.
 //
-// * Thread t of the CTA owns 2 rows of tile I (registers).  Lanes are STAGGERED over the partner tile: at step k lane l
-//   works on j-quad (k + l) mod 64, so the J-side accumulation (a per-warp shared-memory array, read-modify-write of 3
-//   float4 per step) never sees two lanes of a warp on the same j; no shared-memory atomics.
+// * Thread t of the CTA owns 4 rows of tile I (registers).  Lanes are STAGGERED over the partner tile (sym_tile: four
+//   phases, the lower half-warp on the 16 quads of run ph, the upper on run ph + 2, lane l on quad (k + l) mod 16), so
+//   the J-side accumulation (a per-warp shared-memory array, read-modify-write of 2-3 float4 per step) never sees two
+//   lanes of a warp on the same j; no shared-memory atomics.
+// * Two forms of d = p_j - p_i.  Double-single, d = (hi_j - hi_i) + (lo_j - lo_i): one float32 rounding relative to |d|
+//   wherever the crowd sits -- 3 packed operations per coordinate.  Run-local, d = xr_j - m_i with xr_j the partner's
+//   position relative to the origin of its 64-row run and m_i = (hi_i - c_run) + lo_i kept in registers for the 16 steps
+//   a lane spends on that run -- 1 operation per coordinate, float32 rounding at the scale of the run's extent (~5e-7 m).
+//   The choice is per tile pair and purely geometric (sfm_common.cuh): run-local only for partner tiles whose runs are
+//   compact and whose bounding box is >= LOCAL_SEP away from tile I's, i.e. never for a pair that is close enough to
+//   carry force; the staged slot order (k8_order.cuh) makes that the 95-99 % of the tile pairs that are not neighbours.
 // * Tile partials (256 terms per row, float32) are converted to 64-bit fixed point (2^-32 m/s^2) and accumulated with
 //   integer atomics: integer addition is associative, so the result does not depend on CTA scheduling, on the launch
 //   geometry or on how many GPUs share the crowd -- and the multi-GPU exchange is an integer reduce-scatter.
