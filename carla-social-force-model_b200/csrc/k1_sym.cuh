@@ -14,9 +14,10 @@
 //   wherever the crowd sits -- 3 packed operations per coordinate.  Run-local, d = xr_j - m_i with xr_j the partner's
 //   position relative to the origin of its 64-row run and m_i = (hi_i - c_run) + lo_i kept in registers for the 16 steps
 //   a lane spends on that run -- 1 operation per coordinate, float32 rounding at the scale of the run's extent (~5e-7 m).
-//   The choice is per tile pair and purely geometric (sfm_common.cuh): run-local only for partner tiles whose runs are
-//   compact and whose bounding box is >= LOCAL_SEP away from tile I's, i.e. never for a pair that is close enough to
-//   carry force; the staged slot order (k8_order.cuh) makes that the 95-99 % of the tile pairs that are not neighbours.
+//   The choice is per tile pair and purely geometric (sfm_common.cuh): run-local only for partner tiles whose bounding
+//   box is >= max(1 m, a quarter of their widest run's half-extent) away from tile I's -- never for a pair close enough
+//   to carry much force, and always with |d| large against the rounding; the staged slot order (k8_order.cuh) makes that
+//   the 93-99 % of the tile pairs that are not neighbours.
 // * Tile partials (256 terms per row, float32) are converted to 64-bit fixed point (2^-32 m/s^2) and accumulated with
 //   integer atomics: integer addition is associative, so the result does not depend on CTA scheduling, on the launch
 //   geometry or on how many GPUs share the crowd -- and the multi-GPU exchange is an integer reduce-scatter.
@@ -347,7 +348,7 @@ __device__ __forceinline__ void sym_tile(const float (*__restrict__ tl)[K1_TJ], 
 #pragma unroll
         for (int r = 0; r < KS_IR; ++r) Iw[r] = I[r];
         if (LOCAL) {
-            const float4 meta = *reinterpret_cast<const float4*>(&tl[PMETA][4 * run]);     // (c_x, c_y, c_z, compact)
+            const float4 meta = *reinterpret_cast<const float4*>(&tl[PMETA][4 * run]);     // (c_x, c_y, c_z, half-extent)
 #pragma unroll
             for (int r = 0; r < KS_IR; ++r) {
                 Iw[r].x = splat2((If[r].x - meta.x) + If[r].xl);     // hi_i - c: exact (lattice points)
@@ -493,13 +494,14 @@ __global__ void SFM_KS_BOUNDS k1_sym_pairs(const SymArgs a) {
 #pragma unroll
         for (int r = 0; r < KS_IR; ++r) flag_j |= (tile[stage][PFLAG][tid + r * KS_THREADS] != 0.0f);
         const bool tile_nonplanar = __syncthreads_or(flag_j) != 0;
-        // local path: every 64-row run of the partner tile is compact around its own origin (K3 decides, per tick) and
-        // the two tiles' bounding boxes are at least LOCAL_SEP apart -- every pair closer than that stays double-single
+        // local path: the two tiles' bounding boxes are at least max(LOCAL_SEP, LOCAL_SEP_FACTOR * ext) apart, ext the
+        // largest half-extent of the partner tile's four runs (+inf for a run that does not qualify; K3 decides, per
+        // tick) -- every pair closer than that stays double-single (sfm_common.cuh)
         const float* meta = tile[stage][PMETA];
         const float sep = fmaxf(fmaxf(meta[META_BOX] - own_box[2], own_box[0] - meta[META_BOX + 2]),
                                 fmaxf(meta[META_BOX + 1] - own_box[3], own_box[1] - meta[META_BOX + 3]));
-        const bool tile_local = a.use_local && meta[3] != 0.0f && meta[7] != 0.0f && meta[11] != 0.0f && meta[15] != 0.0f &&
-                                sep >= LOCAL_SEP;
+        const float ext = fmaxf(fmaxf(meta[3], meta[7]), fmaxf(meta[11], meta[15]));
+        const bool tile_local = a.use_local && sep >= fmaxf(LOCAL_SEP, LOCAL_SEP_FACTOR * ext);
         if (J == I) {
             // diagonal tile: guarded asymmetric evaluation with self pairs removed, rows of I only
             PairAcc acc[KS_IR];

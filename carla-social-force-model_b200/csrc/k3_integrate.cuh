@@ -72,11 +72,13 @@ __device__ __forceinline__ void split_hi_lo(double x, float& hi, float& lo) {
     lo = (float)(x - (double)hi);
 }
 
-// Bounds of one run of SUB_ROWS rows, from the per-warp bounding boxes `bb[warp][min xyz, max xyz]`: the run's origin c
-// (centre of the box on the position lattice; 0 for a run without live rows) and whether the run is compact -- every live
-// row within LOCAL_LIMIT of c in every coordinate, c itself within the range where hi - c is exact (sfm_common.cuh).
-__device__ __forceinline__ bool run_origin(const double (*bb)[6], int run, double (&c)[3]) {
-    bool compact = true;
+// Bounds of one run of SUB_ROWS slots, from the per-warp bounding boxes `bb[warp][min xyz, max xyz]`: the run's origin c
+// (centre of the box on the position lattice; 0 for a run without live rows) and its half-extent -- the largest
+// |x - origin - c| over its live rows and coordinates -- or +inf when the run cannot take the local path: wider than
+// LOCAL_LIMIT, or so far from the staging origin that hi - c is no longer exact (sfm_common.cuh).
+__device__ __forceinline__ float run_origin(const double (*bb)[6], int run, double (&c)[3]) {
+    double ext = 0.0;
+    bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double mn = fmin(bb[2 * run][k], bb[2 * run + 1][k]);
@@ -86,14 +88,15 @@ __device__ __forceinline__ bool run_origin(const double (*bb)[6], int run, doubl
             continue;
         }
         c[k] = rint(0.5 * (mn + mx) * POS_LATTICE) * (1.0 / POS_LATTICE);
-        compact = compact && (mx - c[k] <= LOCAL_LIMIT) && (c[k] - mn <= LOCAL_LIMIT) && (fabs(c[k]) <= LOCAL_RANGE);
+        ext = fmax(ext, fmax(mx - c[k], c[k] - mn));
+        ok = ok && (fabs(c[k]) <= LOCAL_RANGE);
     }
-    return compact;
+    return (ok && ext <= LOCAL_LIMIT) ? (float)ext : CUDART_INF_F;      // (a NaN extent fails the comparison: +inf)
 }
 
 // Stages one 256-slot tile: EVERY thread of the CTA (thread t <-> slot 256 * blockIdx.x + t) calls this, live or not.
 // Besides the (hi, lo) parts each row gets its position relative to the origin of its 64-row run (the pair kernel's
-// "local" path, sfm_common.cuh); the run origins and compact flags go to the first 16 slots of the tile's PMETA plane,
+// "local" path, sfm_common.cuh); the run origins and half-extents go to the first 16 slots of the tile's PMETA plane,
 // the tile's xy bounding box to the next four.
 __device__ __forceinline__ void stage_tile(const StepArgs& a, int64_t i, bool live, double x, double y, double z, double r,
                                            double vx, double vy, double vz) {
@@ -145,9 +148,9 @@ __device__ __forceinline__ void stage_tile(const StepArgs& a, int64_t i, bool li
     }
     if (threadIdx.x < 4 * SUBS_PER_TILE) {
         double c[3];
-        const bool compact = run_origin(bb, threadIdx.x >> 2, c);
+        const float ext = run_origin(bb, threadIdx.x >> 2, c);
         const int k = threadIdx.x & 3;
-        v[PMETA] = (k == 0) ? (float)c[0] : (k == 1) ? (float)c[1] : (k == 2) ? (float)c[2] : (compact ? 1.0f : 0.0f);
+        v[PMETA] = (k == 0) ? (float)c[0] : (k == 1) ? (float)c[1] : (k == 2) ? (float)c[2] : ext;
     } else if (threadIdx.x < META_BOX + 4) {
         // the tile's xy bounding box (min x, min y, max x, max y; +inf / -inf for a tile without live rows)
         const int k = threadIdx.x - META_BOX, col = (k & 1) + ((k >> 1) ? 3 : 0);

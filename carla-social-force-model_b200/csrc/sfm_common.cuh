@@ -18,22 +18,25 @@ namespace sfm {
 // rounding RELATIVE TO |d| -- independent of how far the crowd is from the origin.  (A single float32 per coordinate
 // rounds to 1.5e-5 m at |x| >= 256 m, which alone breaks the 1e-4 / 1e-5 force tolerance on integrated states.)
 //
-// Sub-tile-local copies (the pair kernel's "local" path).  Every run of SUB_ROWS = 64 consecutive rows (a quarter of a
-// 256-row tile) also carries its positions as ONE float32 per coordinate relative to the run's own origin c -- the centre
-// of its bounding box, on the same lattice: xr = float32(x - origin - c).  When the run is spatially compact (every
-// |x - origin - c| <= LOCAL_LIMIT) the kernel forms d = xr_j - m_i with m_i = (hi_i - c_J) + lo_i computed once per
-// (row, sub-tile): ONE subtraction per coordinate and pair instead of three.  Rounding: xr_j to 2^-25 |xr_j|, m_i to
-// 2^-25 |x_i - c_J| (hi_i - c_J is exact: lattice points), the difference to 2^-25 |d| -- for the pairs that carry the
-// force (|d| of a metre or two, both magnitudes below ~8 m in a crowd ordered along a space-filling curve) about 5e-7 m,
-// against 1.5e-5 m for a single global origin.  Whether a run is compact is decided where it is staged (K3), per tick;
-// tiles with a run that is not take the double-single path, so the row order is a matter of speed, never of accuracy
-// (profiles/local_origin_emulation.py: staging error alone, both paths, against the force tolerance).
-// Which pairs may take it is decided per TILE pair, by geometry alone: only when the xy bounding boxes of the two 256-row
-// tiles are at least LOCAL_SEP apart.  Every pair closer than that -- the pairs that carry the force, and with it the
-// sensitivity to d -- is evaluated in double-single form (or by the guarded diagonal code), so the local path only ever
-// sees the far field, where a micrometre is nothing; what it saves is the work on the 95-99 % of the tile pairs that are
-// not neighbours.
-// The plane PMETA carries, in the first 16 slots of every tile, (c_x, c_y, c_z, compact ? 1 : 0) of its four runs, and in
+// Run-local copies (the pair kernel's "local" path).  Every run of SUB_ROWS = 64 consecutive slots (a quarter of a
+// 256-slot tile) also carries its positions as ONE float32 per coordinate relative to the run's own origin c -- the centre
+// of its bounding box, on the same lattice: xr = float32(x - origin - c).  The kernel can then form d = xr_j - m_i with
+// m_i = (hi_i - c_J) + lo_i computed once per (row, run): ONE subtraction per coordinate and pair instead of three.
+// Rounding: xr_j to 2^-25 |xr_j|, m_i to 2^-25 |x_i - c_J| (hi_i - c_J is exact: lattice points), the difference to
+// 2^-25 |d| -- an ABSOLUTE error of about 2^-24 ext for a run of half-extent ext (5e-7 m at 8 m), where the double-single
+// form is exact relative to |d|.  That is harmless in the far field and not good enough for the pairs that carry the force
+// (the model amplifies a relative error of d by 2 (n' B)^2 theta ~ 20-50), so the choice is made per TILE pair, by
+// geometry alone: only when the xy bounding boxes of the two 256-slot tiles are at least
+//     max(LOCAL_SEP, LOCAL_SEP_FACTOR * ext)      (ext = largest half-extent of the partner tile's four runs)
+// apart.  Every pair closer than that is evaluated in double-single form (or by the guarded diagonal code); on the local
+// path |d| >= ext / 4, so the relative error of d stays below 2^-22 = 2.4e-7 whatever the run looks like -- at most a tenth
+// of the force tolerance after the model's amplification, and the far field carries little force to begin with
+// (profiles/local_origin_emulation.py: staging error alone, both paths, against the force tolerance).  What the path
+// saves is the work on the 93-99 % of the tile pairs that are not neighbours -- provided consecutive slots are close in
+// space, which is what the staged slot order (k8_order.cuh) arranges; rows staged in arbitrary order have runs as wide as
+// the crowd and simply never qualify: the order is a matter of speed, never of accuracy.
+// The plane PMETA carries, in the first 16 slots of every tile, (c_x, c_y, c_z, ext) of its four runs (ext = +inf for a
+// run that does not qualify: wider than LOCAL_LIMIT, or too far from the staging origin for hi - c to be exact), and in
 // slots META_BOX .. META_BOX + 3 the tile's xy bounding box (min x, min y, max x, max y, origin-relative).
 constexpr int NPLANES = 15;
 enum Plane { PX = 0, PY = 1, PZ = 2, PXL = 3, PYL = 4, PZL = 5, PR = 6, PVX = 7, PVY = 8, PVZ = 9, PFLAG = 10,
@@ -43,8 +46,9 @@ constexpr float PAD_POS = 1.0e15f;          // padded rows sit this far away: ex
 constexpr double POS_LATTICE = 64.0;        // hi parts are multiples of 1 / POS_LATTICE metres
 constexpr int SUB_ROWS = 64;                // rows per sub-tile run (two warps of the staging CTA)
 constexpr int SUBS_PER_TILE = ROW_ALIGN / SUB_ROWS;
-constexpr double LOCAL_LIMIT = 16.0;        // largest |x - origin - c| of a compact run, metres
-constexpr float LOCAL_SEP = 1.0f;           // tile pairs whose bounding boxes are closer than this stay double-single
+constexpr double LOCAL_LIMIT = 64.0;        // runs wider than this (half-extent, metres) never take the local path
+constexpr float LOCAL_SEP = 1.0f;           // tile pairs whose bounding boxes are closer than this stay double-single ...
+constexpr float LOCAL_SEP_FACTOR = 0.25f;   // ... or closer than this times the partner tile's largest run half-extent
 constexpr int META_BOX = 16;                // first slot of the tile's bounding box in its PMETA plane
 constexpr double LOCAL_RANGE = 131072.0;    // run origins beyond 2^17 m from the staging origin: hi - c no longer exact
 

@@ -12,6 +12,7 @@ for z in (0.0, 0.2):
         w = synth.make_config(5, n=n, z_spread=z)
         ctx = native.Context(0)
         ctx.set_params(native.params_from_config(cfg, 0.05))
+        ctx.set_reorder_interval(int(os.environ.get('SFM_REORDER_EVERY', '32')))
         ctx.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
         out = np.empty((n, 3))
         for _ in range(3): ctx.force(native.PEDESTRIAN, out)
@@ -20,5 +21,6 @@ for z in (0.0, 0.2):
         s = ctx.stats()
         ms = s['ms_pairs'] / s['pair_launches']
         print(json.dumps({'path': ('3-D' if z else 'planar') + (' + radius' if radius else ''), 'ms': ms,
-                          'pair_terms_per_s': s['pair_evaluations'] / s['pair_launches'] / (ms * 1e-3), 'fixup_rows': s['fixup_rows']}), flush=True)
+                          'pair_terms_per_s': s['pair_evaluations'] / s['pair_launches'] / (ms * 1e-3), 'fixup_rows': s['fixup_rows'],
+                          'local_tile_pair_fraction': s['local_tile_pairs'] * 65536.0 / max(s['pair_evaluations'], 1)}), flush=True)
         ctx.close()

@@ -10,6 +10,7 @@ cfg = tomllib.load(open(os.path.join(ROOT, 'carla-social-force-model_b200/config
 w = synth.make_config(3)
 ctx = native.Context(0)
 ctx.set_params(native.params_from_config(cfg, w.step_length))
+ctx.set_reorder_interval(int(os.environ.get('SFM_REORDER_EVERY', '32')))     # staged along the Hilbert curve, like Engine
 ctx.upload_state(w.loc, w.vel, w.next_waypoint, w.radius, w.target_speed, w.mode)
 ctx.set_borders(w.borders, w.section_center, w.section_length)
 ctx.set_obstacles(native.STATIC_OBSTACLE, [c for c, _ in w.static_obstacles], [r for _, r in w.static_obstacles])

@@ -21,7 +21,7 @@ from oracle import sfm_oracle as O            # noqa: E402
 from sfm_b200 import synth                    # noqa: E402
 
 f32 = np.float32
-LOCAL_SEP = 1.0           # metres between tile bounding boxes below which a tile pair stays double-single
+LOCAL_SEP, LOCAL_SEP_FACTOR, LOCAL_LIMIT = 1.0, 0.25, 64.0      # csrc/sfm_common.cuh
 
 
 def hilbert_order(loc, cell=0.25, bits=16):
@@ -110,20 +110,21 @@ def main():
     tol = 1e-5 + 1e-4 * np.abs(exact) + risk[:, None]
     worst = {'double-single': 0.0, 'local': 0.0}
     ratios = {'double-single': [], 'local': []}
-    # which (row, partner) pairs take the local path: the partner's tile has four compact runs and the bounding boxes of
-    # the two 256-row tiles are at least LOCAL_SEP apart (k1_sym.cuh); everything else -- the row's own tile, adjacent
-    # tiles, tiles with a spread-out run -- takes the double-single path
+    # which (row, partner) pairs take the local path: the bounding boxes of the two 256-row tiles are at least
+    # max(LOCAL_SEP, LOCAL_SEP_FACTOR * widest run of the partner tile) apart (k1_sym.cuh); everything else -- the row's own
+    # tile, adjacent tiles, tiles with a spread-out run -- takes the double-single path
     rel = (loc - origin)[:, :2]
     tiles = rel.reshape(-1, 256, 2)
     t_lo, t_hi = tiles.min(1), tiles.max(1)
-    compact = (ext <= 16.0).all(1).reshape(-1, 4).all(1)
+    run_ext = np.where(ext.max(1) <= LOCAL_LIMIT, ext.max(1), np.inf).reshape(-1, 4).max(1)     # widest run of each tile
     taken = 0
     for s in range(0, len(rows), 32):
         r = rows[s:s + 32]
         own = r[:, None] == np.arange(w.n)[None, :]
         ti = r // 256
         gap = np.maximum(t_lo[None, :, :] - t_hi[ti, None, :], t_lo[ti, None, :] - t_hi[None, :, :]).max(-1)   # (rows, tiles)
-        local_tile = compact[None, :] & (gap >= LOCAL_SEP) & (ti[:, None] != np.arange(len(compact))[None, :])
+        local_tile = (gap >= np.maximum(LOCAL_SEP, LOCAL_SEP_FACTOR * run_ext)[None, :]) & \
+                     (ti[:, None] != np.arange(len(run_ext))[None, :])
         local_pair = np.repeat(local_tile, 256, axis=1)
         taken += int(local_pair.sum())
         d_ds = (hi[None, :, :] - hi[r, None, :]) + (lo[None, :, :] - lo[r, None, :])          # float32 throughout
