@@ -58,7 +58,11 @@ def main():
     if args.phase == 'multi':
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
     w = synth.make_config(5, n=args.n)
-    e = eng.Engine(cfg, w.step_length, device=local)
+    # rows staged in ROW order on both sides: then the tile pairs of the 8-rank run are those of the single-GPU run and the
+    # trajectories agree bit for bit.  (With the rank-local Hilbert staging -- Engine's default -- a rank's tiles differ from
+    # the single-GPU run's, and the agreement is to float32 rounding of the tile partials; bench.py's parity block replays a
+    # tick under the ranks' own orders for the bitwise check in that mode.)
+    e = eng.Engine(cfg, w.step_length, device=local, reorder_every=int(os.environ.get('SFM_REORDER_EVERY', '0')))
     e.load(w)
     extra = {}
     if args.phase == 'single':

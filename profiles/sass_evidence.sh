@@ -1,5 +1,5 @@
 #!/bin/bash
-# Regenerates profiles/r2_sass_evidence.txt: opcode counts that show what the kernels are built from (UBLKCP = TMA bulk
+# regenerates profiles/r2_sass_evidence.txt (v4) / r2_sass_evidence_v5.txt: opcode counts that show what the kernels are built from (UBLKCP = TMA bulk
 # copy, SYNCS = mbarrier, FFMA2/FMUL2/FADD2 = packed FP32x2, REDG = the integer accumulator atomics, MEMBAR.*.SYS =
 # the system-scope fences of the peer barrier).  Run from the repo root after __graft_entry__.build().
 LIB=carla-social-force-model_b200/sfm_b200/libsfm_b200.so
