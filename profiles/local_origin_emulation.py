@@ -81,10 +81,9 @@ def force_from_d(d, vel_i, vel, own, p):
     return force.sum(1)
 
 
-def main():
-    cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else None
-    n_rows = int(sys.argv[3]) if len(sys.argv) > 3 else 96
+def emulate(cfg=3, n=None, n_rows=96, verbose=True):
+    """Returns {'local_share': ..., 'double-single': worst error / tolerance, 'local': worst error / tolerance}."""
+    say = print if verbose else (lambda *a, **k: None)
     w = synth.make_config(cfg, n=n, scale_sets=False) if n else synth.make_config(cfg)
     rng = np.random.default_rng(7)
     shift = np.array([512.1, -498.9, 0.0])
@@ -96,14 +95,14 @@ def main():
     hi, lo = staged(loc, origin)
     c, xr = tile_origins(loc, origin)
     ext = np.abs(xr[:, :2]).reshape(-1, 64, 2).max(1)
-    print(f'cfg{cfg} N={w.n}: run half-extent median {np.median(ext):.1f} m, 99 % {np.quantile(ext, 0.99):.1f} m, '
+    say(f'cfg{cfg} N={w.n}: run half-extent median {np.median(ext):.1f} m, 99 % {np.quantile(ext, 0.99):.1f} m, '
           f'max {ext.max():.1f} m')
     far = np.argsort(-np.abs(loc[:, :2] - origin[:2]).max(1))[:n_rows // 3]
     from scipy.spatial import cKDTree
     nn = cKDTree(loc[:, :2]).query(loc[:, :2], k=2)[0][:, 1]
     close = np.argsort(nn)[:n_rows // 3]                         # the rows with the closest neighbours (down to millimetres)
     rows = np.unique(np.concatenate((rng.choice(w.n, n_rows - len(far) - len(close), replace=False), far, close)))
-    print(f'  sampled rows: {len(rows)} (a third each: uniform, farthest from the origin, closest neighbour -- from '
+    say(f'  sampled rows: {len(rows)} (a third each: uniform, farthest from the origin, closest neighbour -- from '
           f'{nn[close].min() * 1e3:.1f} mm)')
     p = dict(O.PED_DEFAULTS)
     exact, risk = O.pedestrian_force(loc, vel, w.radius, rows=rows, return_risk=True)
@@ -134,11 +133,19 @@ def main():
             ratio = np.abs(force_from_d(d, vel[r], vel, own, p) - exact[s:s + 32]) / tol[s:s + 32]
             worst[name] = max(worst[name], float(ratio.max()))
             ratios[name].append(ratio.max(1))
-    print(f'  pairs on the local path: {taken / (len(rows) * (w.n - 1)):.3f} of all pairs of the sampled rows')
+    say(f'  pairs on the local path: {taken / (len(rows) * (w.n - 1)):.3f} of all pairs of the sampled rows')
     for name, v in worst.items():
         q = np.concatenate(ratios[name])
-        print(f'  {name:14s} staging error / tolerance over {len(rows)} rows: median {np.median(q):.4f}, 99 % '
+        say(f'  {name:14s} staging error / tolerance over {len(rows)} rows: median {np.median(q):.4f}, 99 % '
               f'{np.quantile(q, 0.99):.4f}, worst {v:.4f}')
+    return {'local_share': taken / (len(rows) * (w.n - 1)), 'double-single': worst['double-single'], 'local': worst['local']}
+
+
+def main():
+    cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else None
+    n_rows = int(sys.argv[3]) if len(sys.argv) > 3 else 96
+    emulate(cfg, n, n_rows)
 
 
 if __name__ == '__main__':
