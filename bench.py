@@ -509,7 +509,8 @@ def run_ours(args, world, rank, local_rank):
             'metric': 'pair_interactions_per_s', 'value': value, 'unit': 'pair-interactions/s',
             'agent_steps_per_s': value / (n - 1), 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 pair forces on double-single positions / f64 state, cell-list forces and integration',
+            'dtype': 'f32 pair forces (double-single positions on neighbouring tiles, run-local float32 positions in the far field) / '
+                     'f64 state, cell-list forces and integration',
             'data': 'synthetic', 'config': bench_config(name, w, world, args.workload), 'transport': transport,
             'exchange_bytes_per_pedestrian': {'all_gather': PLANE_BYTES, 'reduce_scatter': 32},
             'e2e': {'value': e2e_value, 'unit': 'pair-interactions/s', 'ms_per_step': e2e_ms_per_step,
