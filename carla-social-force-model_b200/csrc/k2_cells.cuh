@@ -364,8 +364,6 @@ struct SegArgs {
     MoussaidD mp;
     double border_a, border_b, neg_inv_border_b;   // -1 / b, so that exp(-dist / b) costs no division
     int use_radius;
-    float skip_dist;                // border kernel: (pedestrian, section) terms whose nearest point is provably farther than
-                                    // this (after the radius) are dropped -- each is < 1e-17 m/s^2; +inf: drop nothing
     double2* f_out;                 // [n]
     int n_groups;                   // ceil(n / 32) pedestrian groups
     int* work_counter;              // persistent mode: next group to hand out (zeroed before the launch); null: one CTA per group
@@ -537,22 +535,6 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
         y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
         y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
     }
-    // Negligible border terms (KIND 0).  a exp(-(dist - r) / b) with b = 0.1 m is < 1e-17 m/s^2 beyond ~4 m, while a
-    // section is a candidate out to its own length (20 m): nine terms in ten are numerically nothing.  A term is dropped
-    // when the pedestrian is PROVABLY farther than skip_dist from every point of the section: every point lies within E of
-    // its model position on the chord (chord0 record), so dist >= Ds - E with Ds the distance to the nearest model point.
-    // The decision depends on (pedestrian, section) only -- never on who shares the group -- so results stay bitwise
-    // independent of the pedestrian order; sections the whole group is far from are not even handed to a warp (their
-    // chord's bounding box is farther than skip_dist + E + the group's largest radius from the group's box, which implies
-    // the per-pedestrian test for every lane: the margins below are nested).  Off in the enumeration / counting passes.
-    const bool skip_on = (KIND == 0) && a.skip_dist < 3.0e38f && a.chord0 != nullptr;
-    float radf = 0.0f, rmaxf = 0.0f;
-    if (skip_on && a.use_radius) {
-        radf = active ? (float)radius * 1.000001f + 1.0e-6f : 0.0f;
-        rmaxf = radf;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rmaxf = fmaxf(rmaxf, __shfl_xor_sync(0xffffffffu, rmaxf, o));
-    }
     const CellGrid g = a.grid;
     const int cx0 = max(cell_coord(x0, g.x0, g.inv_cell, g.nx) - 1, 0);
     const int cx1 = min(cell_coord(x1, g.x0, g.inv_cell, g.nx) + 1, g.nx - 1);
@@ -584,17 +566,6 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                 const double gx = fmax(fmax(x0 - cen_l.x, cen_l.x - x1), 0.0);
                 const double gy = fmax(fmax(y0 - cen_l.y, cen_l.y - y1), 0.0);
                 accept_l = !(gx * gx + gy * gy > cut_l * cut_l * 1.000000001);
-                if (skip_on && accept_l) {
-                    const float4 h0 = __ldg(&a.chord0[2 * s_l]), h1 = __ldg(&a.chord0[2 * s_l + 1]);
-                    if (h1.x > 0.0f || h1.z == 0.0f) {                  // usable chord record (same test as below)
-                        const double ax = cen_l.x + (double)h0.x, ay = cen_l.y + (double)h0.y;
-                        const double bx = ax + (double)h0.z, by = ay + (double)h0.w;
-                        const double hx = fmax(fmax(fmin(ax, bx) - x1, x0 - fmax(ax, bx)), 0.0);
-                        const double hy = fmax(fmax(fmin(ay, by) - y1, y0 - fmax(ay, by)), 0.0);
-                        const double G = sqrt(hx * hx + hy * hy);       // every model point is at least this far from the box
-                        if (G * 0.999 - (double)h1.y - 2.0e-3 - (double)rmaxf > (double)a.skip_dist) accept_l = false;
-                    }
-                }
             }
             // item -> warp by the item's own index, so a pedestrian's summation order does not depend on which other
             // pedestrians share its group (results are reproducible under any pedestrian ordering)
@@ -629,7 +600,7 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                 }
                 int best_q = o0;
                 // ---- direct path: index window around the projection on the item's chord (header), float64 inside it
-                bool direct = false, far = false;
+                bool direct = false;
                 int k_lo = 0, k_cnt = 0;
                 double best = -1.0;                 // distance to the nearest point where the search already has it
                 float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
@@ -649,11 +620,8 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                     const float rho = fmaf(sqrtf(fmaf(del, del, Q)), 1.001f, 0.004f);
                     const float lo_f = fminf(fmaxf(ceilf(kap - rho), 0.0f), ks), hi_f = fmaxf(fminf(floorf(kap + rho), nm1), ks);
                     const bool ok = (hi_f - lo_f) < 8.0f;                                          // NaN / inf -> false
-                    // provably negligible term (see skip_on): dist >= Ds - E; NaN -> not far
-                    far = skip_on && (Ds * 0.9999f - c1.y - 1.0e-3f - radf > a.skip_dist);
-                    if (skip_on && !__any_sync(0xffffffffu, pass && !far)) continue;
-                    direct = __all_sync(0xffffffffu, !pass || far || ok);
-                    if (direct && pass && !far) {                  // (a far lane needs no nearest point: its term is dropped)
+                    direct = __all_sync(0xffffffffu, !pass || ok);
+                    if (direct && pass) {
                         k_lo = (int)lo_f;
                         k_cnt = (int)hi_f - k_lo + 1;
                     }
@@ -671,7 +639,7 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                             }
                         }
                     }
-                    if (pass && !far && !(best < __longlong_as_double(0x7ff0000000000000LL))) {
+                    if (pass && !(best < __longlong_as_double(0x7ff0000000000000LL))) {
                         best_q = exact_argmin(a.point, o0, o1, px, py, best);      // non-finite coordinates: full scan
                     }
                 } else {
@@ -749,12 +717,10 @@ __global__ void __launch_bounds__(K2_THREADS, SFM_K2_MINB) k2_segments(const Seg
                                        : exact_argmin(a.point, lo, min(hi + 1, o1), px, py, best);
                 }
                 if (pass) {
-                    if (!far) {                  // (a far term is < 1e-17 m/s^2 and dropped whatever the grouping)
-                        const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
-                                                              KIND ? a.velocity[s] : make_double2(0.0, 0.0), best);
-                        fx = __dadd_rn(fx, f.x);
-                        fy = __dadd_rn(fy, f.y);
-                    }
+                    const double2 f = segment_force<KIND>(a, px, py, vx, vy, radius, a.point[best_q],
+                                                          KIND ? a.velocity[s] : make_double2(0.0, 0.0), best);
+                    fx = __dadd_rn(fx, f.x);
+                    fy = __dadd_rn(fy, f.y);
                     if (a.emit) {
                         const unsigned long long e = atomicAdd(a.emit_count, 1ull);
                         if ((long long)e < a.emit_capacity) {

@@ -179,7 +179,6 @@ struct sfm_ctx {
     DevBuf<int> k2_counter;
     bool k2_prune = true;           // SFM_K2_PRUNE=0: cell-list kernels scan every point of an item (no chunk bounds)
     bool k2_direct = true;          // SFM_K2_DIRECT=0: no chord-projection windows (every item takes the float32 scan)
-    bool k2_skip = true;            // SFM_K2_SKIP=0: the border kernel evaluates every term, however small
     int k1_smem_pad = 0;            // dynamic shared memory added to the pair kernel: caps its CTAs per SM so that the
                                     // cell-list kernels stay co-resident on every SM (see step_begin)
     DevBuf<long long> facc;         // [world * rows_pad][4] fixed-point force accumulators + poison counter
@@ -900,12 +899,6 @@ int launch_segments(sfm_ctx* c, int cls, bool emit, int64_t emit_capacity, cudaS
     a.use_radius = c->params.use_ped_radius;
     a.f_out = out.p;
     a.eval_count = eval_count;
-    // negligible border terms (k2_cells.cuh): beyond b ln(a / 1e-17) past the radius a term is < 1e-17 m/s^2 -- thousands of
-    // them stay six orders of magnitude below the 1e-11 these kernels are held to.  Never in the enumeration / counting
-    // passes, which report the reference's own (pedestrian, section, nearest point) triplets.
-    a.skip_dist = INFINITY;
-    if (cls == SFM_FORCE_BORDER && c->k2_skip && !emit && !eval_count && c->params.border_b > 0.0 && c->params.border_a > 0.0)
-        a.skip_dist = (float)std::max(0.0, c->params.border_b * std::log(c->params.border_a / 1.0e-17));
     if (emit) {
         a.emit = c->emit.p; a.emit_count = c->emit_count.p; a.emit_capacity = emit_capacity;
     }
@@ -1124,7 +1117,6 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_K1_FIRST")) c->k1_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_PRUNE")) c->k2_prune = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K2_DIRECT")) c->k2_direct = std::atoi(env) != 0;
-    if (const char* env = std::getenv("SFM_K2_SKIP")) c->k2_skip = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_SORT_SINGLE_MAX")) c->sort_single_max = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("SFM_BARRIER_TIMEOUT_MS"))
         c->barrier_timeout_cycles = std::max(1LL, (long long)(std::atof(env) * 1.0e-3 * (double)prop.clockRate * 1.0e3));
