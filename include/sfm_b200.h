@@ -172,11 +172,12 @@ int sfm_apply_force(sfm_ctx* ctx, int64_t n, const double* force, double* new_ve
 int sfm_download_force(sfm_ctx* ctx, int64_t n, double* out);
 int sfm_download_class_force(sfm_ctx* ctx, int force_class, int64_t n, double* out);
 
-/* ---- multi-GPU plumbing: the staged (pos hi/lo, lambda*vel, radius) planes every rank all-gathers once per step ---
+/* ---- multi-GPU plumbing: the staged planes (pos hi/lo, lambda*vel, radius, run-local pos, run/tile metadata) every
+ *      rank all-gathers once per step ---
  * (SURVEY.md 8b sketched `sfm_comm_init(ctx, nccl_unique_id, rank, world)`: the library does not own a communicator --
  *  NCCL is driven by the caller (torch.distributed) over tensor views of the two buffers below, or bypassed altogether by
  *  the peer-memory exchange further down, where both collectives are fused into the library's own kernels.) */
-/* Device pointer of the gather buffer [world][11][rows_pad] float32, and the size of one rank's block in bytes.
+/* Device pointer of the gather buffer [world][15][rows_pad] float32, and the size of one rank's block in bytes.
  * After each sfm_step the caller all-gathers block `rank` into every rank's buffer (NCCL, in place). */
 int sfm_gather_buffer(sfm_ctx* ctx, void** device_ptr, size_t* bytes_per_rank);
 /* Multi-GPU tick in two halves.  sfm_step_begin enqueues the pair accumulation (each unordered pedestrian pair is
@@ -197,7 +198,7 @@ int sfm_stage(sfm_ctx* ctx);
  *      kernel in the order of a Hilbert curve over their xy positions, so that runs of 64 consecutive staged slots are
  *      spatially compact and the kernel can read them through the run's own origin (one float32 subtraction per
  *      coordinate and pair instead of the three of the double-single form; sfm_stats.local_tile_pairs counts the tile
- *      pairs that did).  Speed only: a tile whose runs are not compact takes the double-single path, both hold the force
+ *      pairs that did).  Speed only: neighbouring tiles and tiles with wide runs take the double-single path, both hold the force
  *      tolerance.  The float32 partial sums of the pair force follow the tile composition, so two contexts agree BIT FOR
  *      BIT only under the same order -- sfm_get_slot_order / sfm_set_slot_order carry it from one to the other (bench.py's
  *      single-GPU replay of a multi-rank tick); with the default interval 0 the order is the identity and nothing changes.
