@@ -15,4 +15,10 @@ import sys, json
 l = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('in-tree library persist=%s tick %.3f ms  k1 in step %.3f' % ('$p', l['ms_per_step'], l['roofline']['ms_per_launch_inside_step']))" >> $O/bench_variants_r2_v5.log
 done
+for ctas in 4736 18944; do
+  SFM_K1_TARGET_CTAS=$ctas python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-extra --no-parity --no-dropin 2>/dev/null | python -c "
+import sys, json
+l = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('in-tree library target CTAs %-6s tick %.3f ms  k1 alone %.3f  k1 in step %.3f' % ('$ctas', l['ms_per_step'], l['roofline']['ms_per_launch'], l['roofline']['ms_per_launch_inside_step']))" >> $O/bench_variants_r2_v5.log
+done
 cat $O/bench_variants_r2_v5.log
