@@ -170,7 +170,8 @@ struct sfm_ctx {
     double ms[ST_COUNT] = {0, 0, 0, 0, 0};
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> event_pool;
-    int k1_target_ctas = 148 * 4 * 16;
+    int k1_target_ctas = 148 * 4 * 32;     // grid depth of the pair kernel: CTAs of 1-2 partner tiles at cfg3 (profiles/k1_target_ctas_r2_v5.log:
+                                           // 3.49 -> 3.43 ms alone against 148 * 4 * 16; flat from 24 to 64 waves)
     bool k1_first = false;
     int k2_persist = 2;             // SFM_K2_PERSIST: CTAs per SM of the persistent cell-list kernels beside the pair kernel (0: one CTA
                                     // per group); profiles/k2_persist_sweep_r1.log: 4.54 -> 4.48 ms per tick, 4.71 -> 4.56 ms through host buffers
@@ -1133,7 +1134,7 @@ int sfm_create(int device, sfm_ctx** out) {
     if (const char* env = std::getenv("SFM_OVERLAP")) c->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K1_LOCAL")) c->k1_local = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_K1_TARGET_CTAS")) c->k1_target_ctas = std::max(1, std::atoi(env));
-    else c->k1_target_ctas = prop.multiProcessorCount * 4 * 16;
+    else c->k1_target_ctas = prop.multiProcessorCount * 4 * 32;
     *out = c;
     return 0;
 }
