@@ -1,4 +1,6 @@
-"""CPU emulation of the tile-local staging of the pair kernel (round 2, K1s "local" path): what does the float32
+"""TEST INFRASTRUCTURE, not product code (imports the CPU oracle; run by tests/test_staging_emulation.py and by hand).
+
+CPU emulation of the tile-local staging of the pair kernel (round 2, K1s "local" path): what does the float32
 rounding of the staged coordinates ALONE cost against the 1e-4 rel / 1e-5 abs force tolerance?
 
 For sampled rows i and every j, the position difference d is formed exactly as the kernel forms it (numpy float32
