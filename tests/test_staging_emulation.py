@@ -30,3 +30,24 @@ def test_staging_error_of_the_local_path_stays_at_the_double_single_level():
     out = E.emulate(cfg=2, n=4096, n_rows=48, verbose=False)
     assert out['local_share'] > 0.3, out
     assert out['double-single'] < 0.05 and out['local'] < 0.05, out
+
+
+def test_hilbert_order_keeps_runs_compact():
+    """The host restatement of the staged slot order (csrc/k8_order.cuh): a stable permutation under which every run of 64
+    consecutive rows of a 1 pedestrian / m^2 crowd spans a few metres -- including the rows on the far edges of the
+    bounding square (a curve over a square larger than the crowd would send them to the end of the order) -- while in
+    the crowd's own (random) row order a run spans the whole square."""
+    import numpy as np
+    import local_origin_emulation as E
+    from sfm_b200 import synth
+    w = synth.make_config(2)                                     # N = 4,096 on 64 x 64 m
+    order = E.hilbert_order(w.loc)
+    assert sorted(order.tolist()) == list(range(w.n))
+    runs = w.loc[order, :2].reshape(-1, 64, 2)
+    extent = (runs.max(axis=1) - runs.min(axis=1)).max(axis=1)
+    assert extent.max() < 24.0 and np.median(extent) < 12.0, (extent.max(), np.median(extent))
+    unordered = w.loc[:, :2].reshape(-1, 64, 2)
+    assert (unordered.max(axis=1) - unordered.min(axis=1)).max(axis=1).min() > 40.0
+    # stable: rows in the same cell keep their order
+    same = np.zeros((8, 3))
+    assert E.hilbert_order(same).tolist() == list(range(8))
